@@ -1,0 +1,98 @@
+/* proqa_b200 — C ABI of the B200-native exact top-k MIPS engine.
+ *
+ * This is the drop-in boundary for ProQA's retrieval hot path.  The reference reaches the path
+ * through the FAISS Python (SWIG) API of faiss-cpu==1.6.3 (/root/reference/requirements.txt:2);
+ * each entry point below names the reference call it stands behind.  Plain pointers and sizes
+ * only — no torch, numpy or C++ types cross this boundary.  All functions return 0 on success or
+ * a negative pq_status; pq_last_error() gives the thread-local message.  Nothing aborts.
+ *
+ * Ownership: the caller owns every host buffer passed in; the engine copies what it keeps and
+ * owns all device memory.  Output buffers are caller-allocated and fully written before return
+ * (search is synchronous, like IndexFlat::search).  One index may be searched from one thread at a
+ * time; distinct indexes may be used from distinct threads.
+ *
+ * CUDA is initialised lazily by the first call that needs the device (never at load time):
+ * retrieval/eval_retrieval.py:92-96 forks its worker pool after `import faiss` (:4).
+ */
+#ifndef PROQA_B200_H_
+#define PROQA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pq_index pq_index;
+
+enum pq_metric { PQ_METRIC_IP = 0, PQ_METRIC_L2 = 1 };
+
+enum pq_status {
+    PQ_OK = 0,
+    PQ_ERR_INVALID = -1,     /* bad argument (shape, k, null pointer, d != 128 ...)          */
+    PQ_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed; message has the details  */
+    PQ_ERR_NO_DEVICE = -3,   /* no sm_100 device visible: there is NO CPU fallback            */
+    PQ_ERR_OOM = -4,         /* device or pinned-host allocation failed                       */
+    PQ_ERR_UNSUPPORTED = -5  /* k above PQ_MAX_K, or a tier that cannot serve the request     */
+};
+
+/* Search tiers (pq_index_set_tier / env PROQA_B200_TIER):
+ *   AUTO : fp32 scan for small batches / small corpora, tensor-core filter otherwise.
+ *   FP32 : always the exact fp32 streaming scan (coalesced FFMA path).
+ *   BF16 : always the tcgen05 bf16 filter + exact fp32 rescoring with an exactness certificate;
+ *          queries whose certificate fails are re-run through the fp32 scan.
+ * Every tier returns the same bits: the top-k under the engine's defined fp32 score. */
+enum pq_tier { PQ_TIER_AUTO = 0, PQ_TIER_FP32 = 1, PQ_TIER_BF16 = 2 };
+
+#define PQ_MAX_K 15360
+
+/* faiss.IndexFlatIP(d) / faiss.IndexFlatL2(d)
+ *   retrieval/eval_retrieval.py:102, retrieval/group_paras.py:36,38, retrieval/trec_process.py:74.
+ * d must be 128 (eval_retrieval.py:98 hard-codes it).  device < 0 selects the current device
+ * (or env PROQA_B200_DEVICE / LOCAL_RANK). */
+int pq_index_create(int d, int metric, int device, pq_index** out);
+void pq_index_free(pq_index* idx);
+
+/* index.add(xb)  — eval_retrieval.py:103, group_paras.py:50, trec_process.py:75.
+ * Appends n rows (C-contiguous float32 [n, d]); ids are sequential insertion order. */
+int pq_index_add(pq_index* idx, int64_t n, const float* x_host);
+/* Same, rows already in device memory (skips the .npy -> host -> device round trip). */
+int pq_index_add_device(pq_index* idx, int64_t n, const float* x_dev);
+
+/* index.search(xq, k) -> (D, I)  — eval_retrieval.py:104 (k=80), trec_process.py:76 (k=10000),
+ * group_paras.py:51 and Clustering.train's per-iteration assignment (k=1).
+ * D: float32 [nq, k] best-first (IP: descending score; L2: ascending squared distance),
+ * I: int64  [nq, k]; slots beyond ntotal are I=-1, D=-FLT_MAX (IP) / +FLT_MAX (L2). */
+int pq_index_search(pq_index* idx, int64_t nq, const float* xq_host, int64_t k, float* D_host, int64_t* I_host);
+/* Same with queries and outputs in device memory (used by the multi-GPU layer and the k-means
+ * driver; D_dev/I_dev are written on the index's stream and the call returns after it drained). */
+int pq_index_search_device(pq_index* idx, int64_t nq, const float* xq_dev, int64_t k, float* D_dev, int64_t* I_dev);
+
+/* index.reset()  — group_paras.py:49.  ntotal = 0; device storage is kept for reuse. */
+int pq_index_reset(pq_index* idx);
+/* index.ntotal / index.d / index.metric_type */
+int64_t pq_index_ntotal(const pq_index* idx);
+int pq_index_d(const pq_index* idx);
+int pq_index_metric(const pq_index* idx);
+
+/* Row ids reported by search are local row + id_base (multi-GPU row shards: base of the shard). */
+int pq_index_set_id_base(pq_index* idx, int64_t id_base);
+int pq_index_set_tier(pq_index* idx, int tier);
+/* Counters of the last search: [0]=queries served by the tensor-core tier, [1]=queries re-run by the
+ * fp32 scan after a failed certificate, [2]=fp32-scan launches, [3]=tensor-core filter launches,
+ * [4]=select/merge/rescore launches, [5]=total kernel launches, [6]=device microseconds (CUDA events). */
+int pq_index_last_stats(const pq_index* idx, int64_t* out, int n);
+
+/* Merge G per-shard result lists (each [nq,k], best-first, global ids) into one — the kernel run
+ * after the NCCL all-gather in the multi-GPU layer.  All pointers are device pointers on `device`. */
+int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists_dev,
+                           const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev);
+
+const char* pq_last_error(void);
+/* "proqa_b200 <version> sm_100a" */
+const char* pq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROQA_B200_H_ */

@@ -1,0 +1,85 @@
+"""ctypes binding of libproqa_b200.so (the C ABI declared in include/proqa_b200.h).
+
+The library is loaded lazily on first use and NEVER at import of ``faiss``: the reference forks its worker
+pool after ``import faiss`` (retrieval/eval_retrieval.py:4,92-96).  Loading the .so does not touch CUDA either
+(the C side initialises the device on the first add/search).  If the library is missing the call fails
+loudly — there is no Python/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+PQ_OK = 0
+PQ_MAX_K = 15360
+TIER_AUTO, TIER_FP32, TIER_BF16 = 0, 1, 2
+
+# name -> (restype, argtypes); the single source the symbol test checks against include/proqa_b200.h
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_vp = ctypes.c_void_p
+SIGNATURES = {
+    "pq_index_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "pq_index_free": (None, [_vp]),
+    "pq_index_add": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
+    "pq_index_add_device": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
+    "pq_index_search": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, _vp]),
+    "pq_index_search_device": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, _vp]),
+    "pq_index_reset": (ctypes.c_int, [_vp]),
+    "pq_index_ntotal": (ctypes.c_int64, [_vp]),
+    "pq_index_d": (ctypes.c_int, [_vp]),
+    "pq_index_metric": (ctypes.c_int, [_vp]),
+    "pq_index_set_id_base": (ctypes.c_int, [_vp, ctypes.c_int64]),
+    "pq_index_set_tier": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "pq_index_last_stats": (ctypes.c_int, [_vp, _i64p, ctypes.c_int]),
+    "pq_merge_shard_results": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp,
+                                              _vp, _vp]),
+    "pq_last_error": (ctypes.c_char_p, []),
+    "pq_version": (ctypes.c_char_p, []),
+}
+
+
+def library_path() -> str:
+    return os.environ.get("PROQA_B200_LIB", os.path.join(_HERE, "libproqa_b200.so"))
+
+
+def lib():
+    """Load (once) and return the C-ABI library.  Raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"proqa_b200: native library not found at {path}. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C proqa_b200/csrc` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def last_error() -> str:
+    return lib().pq_last_error().decode("utf-8", "replace")
+
+
+def version() -> str:
+    return lib().pq_version().decode()
+
+
+def check(rc: int, what: str):
+    """Map C-ABI status codes to the exceptions FAISS's SWIG layer raises (RuntimeError) / numpy-ish ValueError."""
+    if rc == PQ_OK:
+        return
+    msg = f"proqa_b200: {what} failed ({rc}): {last_error()}"
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -4:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)

@@ -1,0 +1,82 @@
+// proqa_b200 — host-side state shared by pq_index.cu (C ABI, fp32 tier) and pq_mma.cu (tensor-core tier).
+#pragma once
+
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/proqa_b200.h"
+#include "pq_internal.h"
+
+namespace pq {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* file, int line);
+
+#define PQ_CUDA(expr)                                                    \
+    do {                                                                 \
+        cudaError_t _e = (expr);                                         \
+        if (_e != cudaSuccess) return ::pq::cuda_fail(_e, __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);  // grow-only; contents are NOT preserved across growth
+    void release();
+};
+
+int make_row_tensor_map(CUtensorMap* out, const void* base, long long rows, int elem_bytes, int box_cols, int box_rows);
+
+// Tensor-core tier limits
+constexpr int kMmaMaxK = 1024;          // carry list K' <= 4096 entries
+constexpr int kMmaMinQueries = 9;       // below this the fp32 scan is HBM-bound anyway
+constexpr int kMmaMinRows = 16384;      // below this the epoch machinery is pure overhead
+
+}  // namespace pq
+
+struct pq_index {
+    int d = 128;
+    int metric = 0;
+    int tier = 0;
+    int requested_device = -1;
+    int device = -1;
+    bool device_ready = false;
+    int n_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int64_t ntotal = 0;
+    int64_t capacity = 0;
+    int64_t id_base = 0;
+    float max_norm2 = 0.f;       // max squared row norm (drives the bf16 filter's error bound)
+    bool has_nonfinite = false;  // some row is inf/NaN (or overflows bf16): tensor-core tier disabled
+
+    // HBM layout of the shard: fp32 rows [cap,128] (512 B/row), bf16 copy [cap,128] (256 B/row), squared norms [cap]
+    pq::DevBuf rows_f32, rows_bf16, norms, scalars;
+    CUtensorMap tmap_f32, tmap_bf16;
+
+    // per-search workspaces (grow-only)
+    pq::DevBuf ws_q, ws_D, ws_I, ws_qnorm, ws_qbf16, ws_qbad;
+    pq::DevBuf ws_scan_keys, ws_gthr;
+    pq::DevBuf ws_rr_idx, ws_rr_q, ws_rr_qn, ws_rr_D, ws_rr_I;
+    pq::DevBuf ws_mma[12];
+
+    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    void release_all() {
+        pq::DevBuf* all[] = {&rows_f32, &rows_bf16, &norms,    &scalars,  &ws_q,     &ws_D,      &ws_I,      &ws_qnorm, &ws_qbf16,
+                             &ws_qbad,  &ws_scan_keys, &ws_gthr, &ws_rr_idx, &ws_rr_q, &ws_rr_qn, &ws_rr_D,   &ws_rr_I};
+        for (pq::DevBuf* b : all) b->release();
+        for (pq::DevBuf& b : ws_mma) b.release();
+    }
+};
+
+namespace pq {
+// fp32 tier: exact scan of all local rows.  Queries, norms and outputs are device pointers.
+int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norms, int k, float* dD, long long* dI);
+// tensor-core tier (pq_mma.cu): bf16 tcgen05 filter + fp32 rescoring.  Requires ws_qbf16 / ws_qnorm / ws_qbad to be
+// prepared.  On return dD/dI hold final results for every query whose exactness certificate passed; the indices of
+// the others are appended to *rerun (the stream has been synchronised for the flag read-back).
+int search_mma_filter(pq_index* ix, int nq, const float* dq, int k, float* dD, long long* dI, std::vector<int>* rerun);
+}  // namespace pq

@@ -1,0 +1,503 @@
+// proqa_b200 — host driver and C ABI (include/proqa_b200.h).
+//
+// Mirrors the slice of the FAISS API that ProQA's retrieval path calls (IndexFlatIP/IndexFlatL2:
+// add, search, reset, ntotal — retrieval/eval_retrieval.py:102-104, retrieval/group_paras.py:35-51,
+// retrieval/trec_process.py:74-76) on top of the sm_100a kernels.  There is no CPU path: without an
+// sm_100 device every call that needs one fails with PQ_ERR_NO_DEVICE.
+#include "pq_common.cuh"
+#include "pq_host.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace pq {
+
+static thread_local char g_err[1024] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* file, int line) {
+    const int code = (e == cudaErrorMemoryAllocation) ? PQ_ERR_OOM : PQ_ERR_CUDA;
+    cudaGetLastError();  // clear the sticky-less error state
+    return set_error(code, "CUDA error %s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+}
+
+// The fp32 scan keeps its queries in one __constant__ bank, so device work is serialised process-wide.
+static std::mutex g_device_mutex;
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, 128] row-major matrix, box = box_cols x box_rows elements, 128-byte swizzle, zero fill out of bounds.
+int make_row_tensor_map(CUtensorMap* out, const void* base, long long rows, int elem_bytes, int box_cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(PQ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from the driver");
+    if (rows < 1) rows = 1;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kDim, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kDim * elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PQ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return PQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device buffers
+// ------------------------------------------------------------------------------------------------
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return PQ_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        cudaGetLastError();
+        return set_error(PQ_ERR_OOM, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return PQ_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+static int pick_device(int requested, int* out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(PQ_ERR_NO_DEVICE, "no CUDA device visible (%s); proqa_b200 has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    int dev = requested;
+    if (dev < 0) {
+        const char* s = getenv("PROQA_B200_DEVICE");
+        if (!s || !*s) s = getenv("LOCAL_RANK");
+        if (s && *s) {
+            dev = atoi(s) % n;
+        } else if (cudaGetDevice(&dev) != cudaSuccess) {
+            dev = 0;
+        }
+    }
+    if (dev >= n) return set_error(PQ_ERR_INVALID, "device %d requested but only %d visible", dev, n);
+    cudaDeviceProp prop;
+    PQ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return set_error(PQ_ERR_NO_DEVICE, "device %d is sm_%d%d; proqa_b200 only runs on sm_100 (B200) and has no fallback", dev,
+                         prop.major, prop.minor);
+    *out = dev;
+    return PQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index
+// ------------------------------------------------------------------------------------------------
+static int index_init_device(pq_index* ix) {
+    if (ix->device_ready) return PQ_OK;
+    int dev = -1;
+    int rc = pick_device(ix->requested_device, &dev);
+    if (rc) return rc;
+    ix->device = dev;
+    PQ_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    PQ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    ix->n_sms = prop.multiProcessorCount;
+    PQ_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    PQ_CUDA(cudaEventCreate(&ix->ev0));
+    PQ_CUDA(cudaEventCreate(&ix->ev1));
+    rc = ix->scalars.ensure(256);
+    if (rc) return rc;
+    PQ_CUDA(cudaMemsetAsync(ix->scalars.p, 0, 256, ix->stream));
+    ix->device_ready = true;
+    return PQ_OK;
+}
+
+static int index_refresh_maps(pq_index* ix) {
+    if (ix->ntotal == 0) return PQ_OK;
+    int rc = make_row_tensor_map(&ix->tmap_f32, ix->rows_f32.p, ix->ntotal, 4, 32, kFfmaTileRows);
+    if (rc) return rc;
+    return make_row_tensor_map(&ix->tmap_bf16, ix->rows_bf16.p, ix->ntotal, 2, 64, 128);
+}
+
+static int index_grow(pq_index* ix, int64_t need_rows) {
+    if (need_rows <= ix->capacity) return PQ_OK;
+    int64_t newcap = need_rows;
+    if (ix->capacity > 0) newcap = std::max<int64_t>(need_rows, ix->capacity + ix->capacity / 2);
+    newcap = (newcap + 255) / 256 * 256;
+    DevBuf nf, nb, nn;
+    int rc = nf.ensure((size_t)newcap * kDim * 4);
+    if (!rc) rc = nb.ensure((size_t)newcap * kDim * 2);
+    if (!rc) rc = nn.ensure((size_t)newcap * 4);
+    if (rc) {
+        nf.release();
+        nb.release();
+        nn.release();
+        return rc;
+    }
+    if (ix->ntotal > 0) {
+        PQ_CUDA(cudaMemcpyAsync(nf.p, ix->rows_f32.p, (size_t)ix->ntotal * kDim * 4, cudaMemcpyDeviceToDevice, ix->stream));
+        PQ_CUDA(cudaMemcpyAsync(nb.p, ix->rows_bf16.p, (size_t)ix->ntotal * kDim * 2, cudaMemcpyDeviceToDevice, ix->stream));
+        PQ_CUDA(cudaMemcpyAsync(nn.p, ix->norms.p, (size_t)ix->ntotal * 4, cudaMemcpyDeviceToDevice, ix->stream));
+        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    }
+    ix->rows_f32.release();
+    ix->rows_bf16.release();
+    ix->norms.release();
+    ix->rows_f32 = nf;
+    ix->rows_bf16 = nb;
+    ix->norms = nn;
+    ix->capacity = newcap;
+    return PQ_OK;
+}
+
+static int index_add_impl(pq_index* ix, int64_t n, const float* x, bool on_device) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    if (n < 0 || (n > 0 && !x)) return set_error(PQ_ERR_INVALID, "add: bad arguments (n=%lld, x=%p)", (long long)n, (const void*)x);
+    if (n == 0) return PQ_OK;
+    if (ix->ntotal + n > (int64_t)0x7fffff00) return set_error(PQ_ERR_UNSUPPORTED, "add: more than 2^31 rows per shard");
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    int rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    rc = index_grow(ix, ix->ntotal + n);
+    if (rc) return rc;
+    float* dst = (float*)ix->rows_f32.p + (size_t)ix->ntotal * kDim;
+    PQ_CUDA(cudaMemcpyAsync(dst, x, (size_t)n * kDim * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ix->stream));
+    uint32_t* sc = (uint32_t*)ix->scalars.p;
+    PQ_CUDA(prep_rows_launch(dst, n, (uint16_t*)ix->rows_bf16.p + (size_t)ix->ntotal * kDim, (float*)ix->norms.p + ix->ntotal, sc + 0,
+                             sc + 1, nullptr, ix->stream));
+    uint32_t host_sc[2];
+    PQ_CUDA(cudaMemcpyAsync(host_sc, sc, 8, cudaMemcpyDeviceToHost, ix->stream));
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    memcpy(&ix->max_norm2, &host_sc[0], 4);
+    ix->has_nonfinite = host_sc[1] != 0;
+    ix->ntotal += n;
+    return index_refresh_maps(ix);
+}
+
+// Exact fp32 scan over all local rows for queries [0, nq) already on the device.
+int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norms, int k, float* dD, long long* dI) {
+    const int qmax = ffma_max_queries_for_k(k);
+    if (qmax < 1) return set_error(PQ_ERR_UNSUPPORTED, "k=%d is above what the fp32 scan supports", k);
+    const int n_tiles = (int)((ix->ntotal + kFfmaTileRows - 1) / kFfmaTileRows);
+    const int n_ctas = std::max(1, std::min(ix->n_sms, n_tiles));
+    int rc = ix->ws_scan_keys.ensure((size_t)n_ctas * qmax * k * 8);
+    if (!rc) rc = ix->ws_gthr.ensure(kFfmaMaxQ * 4);
+    if (rc) return rc;
+    for (int q0 = 0; q0 < nq; q0 += qmax) {
+        const int nqb = std::min(qmax, nq - q0);
+        PQ_CUDA(cudaMemsetAsync(ix->ws_gthr.p, 0, kFfmaMaxQ * 4, ix->stream));
+        FfmaLaunch f;
+        f.tmap_rows_f32 = &ix->tmap_f32;
+        f.row_norms = (const float*)ix->norms.p;
+        f.queries_dev = dq + (size_t)q0 * kDim;
+        f.out_keys = (uint64_t*)ix->ws_scan_keys.p;
+        f.gthr = (uint32_t*)ix->ws_gthr.p;
+        f.n_rows = ix->ntotal;
+        f.n_ctas = n_ctas;
+        f.nq = nqb;
+        f.k = k;
+        f.metric = ix->metric;
+        PQ_CUDA(ffma_scan_launch(f, ix->stream));
+        MergeLaunch m;
+        memset(&m, 0, sizeof(m));
+        m.keys = (const uint64_t*)ix->ws_scan_keys.p;
+        m.q_stride = k;
+        m.list_stride = (long long)nqb * k;
+        m.n_lists = n_ctas;
+        m.list_len = k;
+        m.gthr = (const uint32_t*)ix->ws_gthr.p;
+        m.nq = nqb;
+        m.k = k;
+        m.metric = ix->metric;
+        m.q_norms = dq_norms + q0;
+        m.id_base = ix->id_base;
+        m.D = dD + (size_t)q0 * k;
+        m.I = dI + (size_t)q0 * k;
+        PQ_CUDA(merge_lists_launch(m, ix->stream));
+        ix->stats[2] += 1;
+        ix->stats[4] += 1;
+        ix->stats[5] += 2;
+    }
+    return PQ_OK;
+}
+
+__global__ void pq_fill_empty_kernel(float* D, long long* I, long long n, float dval) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        D[i] = dval;
+        I[i] = -1;
+    }
+}
+
+// Gather / scatter helpers for the certificate-failure re-run.
+__global__ void pq_gather_queries_kernel(const float* __restrict__ q, const float* __restrict__ qn, const int* __restrict__ idx, int n,
+                                         float* __restrict__ out_q, float* __restrict__ out_qn) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const int src = idx[i];
+    out_q[(size_t)i * kDim + threadIdx.x] = q[(size_t)src * kDim + threadIdx.x];
+    if (threadIdx.x == 0) out_qn[i] = qn[src];
+}
+__global__ void pq_scatter_results_kernel(const float* __restrict__ Ds, const long long* __restrict__ Is, const int* __restrict__ idx,
+                                          int n, int k, float* __restrict__ D, long long* __restrict__ I) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const int dst = idx[i];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        D[(size_t)dst * k + j] = Ds[(size_t)i * k + j];
+        I[(size_t)dst * k + j] = Is[(size_t)i * k + j];
+    }
+}
+
+static bool tier_uses_mma(const pq_index* ix, int64_t nq, int64_t k) {
+    if (ix->has_nonfinite) return false;
+    if (ix->metric != kMetricIP) return false;  // the bf16 filter scores inner products only (L2: fp32 scan)
+    if (k > kMmaMaxK) return false;
+    if (ix->tier == PQ_TIER_FP32) return false;
+    if (ix->tier == PQ_TIER_BF16) return ix->ntotal >= 1;
+    return nq >= kMmaMinQueries && ix->ntotal >= kMmaMinRows;
+}
+
+// Device-resident search: dq [nq,128] fp32 -> dD [nq,k], dI [nq,k]; all on ix->stream; leaves the stream drained.
+static int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t k, float* dD, long long* dI) {
+    memset(ix->stats, 0, sizeof(ix->stats));
+    if (nq == 0) return PQ_OK;
+    if (ix->ntotal == 0) {
+        const long long n = nq * k;
+        pq_fill_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(dD, dI, n, ix->metric == kMetricL2 ? FLT_MAX : -FLT_MAX);
+        PQ_CUDA(cudaGetLastError());
+        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+        return PQ_OK;
+    }
+    PQ_CUDA(cudaEventRecord(ix->ev0, ix->stream));
+    // Query preparation: squared norms (L2 output + error bound), bf16 copy, per-query non-finite flags.
+    const int64_t nq_pad = (nq + 127) / 128 * 128;
+    int rc = ix->ws_qnorm.ensure((size_t)nq_pad * 4);
+    if (!rc) rc = ix->ws_qbf16.ensure((size_t)nq_pad * kDim * 2);
+    if (!rc) rc = ix->ws_qbad.ensure((size_t)nq_pad);
+    if (rc) return rc;
+    PQ_CUDA(cudaMemsetAsync(ix->ws_qbf16.p, 0, (size_t)nq_pad * kDim * 2, ix->stream));
+    PQ_CUDA(prep_rows_launch(dq, nq, (uint16_t*)ix->ws_qbf16.p, (float*)ix->ws_qnorm.p, nullptr, nullptr, (uint8_t*)ix->ws_qbad.p,
+                             ix->stream));
+    ix->stats[5] += 1;
+
+    if (tier_uses_mma(ix, nq, k)) {
+        std::vector<int> rerun;
+        rc = search_mma_filter(ix, (int)nq, dq, (int)k, dD, dI, &rerun);
+        if (rc) return rc;
+        ix->stats[0] = nq - (int64_t)rerun.size();
+        ix->stats[1] = (int64_t)rerun.size();
+        if (!rerun.empty()) {
+            const int nr = (int)rerun.size();
+            rc = ix->ws_rr_idx.ensure((size_t)nr * 4);
+            if (!rc) rc = ix->ws_rr_q.ensure((size_t)nr * kDim * 4);
+            if (!rc) rc = ix->ws_rr_qn.ensure((size_t)nr * 4);
+            if (!rc) rc = ix->ws_rr_D.ensure((size_t)nr * k * 4);
+            if (!rc) rc = ix->ws_rr_I.ensure((size_t)nr * k * 8);
+            if (rc) return rc;
+            PQ_CUDA(cudaMemcpyAsync(ix->ws_rr_idx.p, rerun.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, ix->stream));
+            pq_gather_queries_kernel<<<nr, kDim, 0, ix->stream>>>(dq, (const float*)ix->ws_qnorm.p, (const int*)ix->ws_rr_idx.p, nr,
+                                                                  (float*)ix->ws_rr_q.p, (float*)ix->ws_rr_qn.p);
+            PQ_CUDA(cudaGetLastError());
+            rc = search_fp32_scan(ix, nr, (const float*)ix->ws_rr_q.p, (const float*)ix->ws_rr_qn.p, (int)k, (float*)ix->ws_rr_D.p,
+                                  (long long*)ix->ws_rr_I.p);
+            if (rc) return rc;
+            pq_scatter_results_kernel<<<nr, 128, 0, ix->stream>>>((const float*)ix->ws_rr_D.p, (const long long*)ix->ws_rr_I.p,
+                                                                  (const int*)ix->ws_rr_idx.p, nr, (int)k, dD, dI);
+            PQ_CUDA(cudaGetLastError());
+            ix->stats[5] += 2;
+            PQ_CUDA(cudaStreamSynchronize(ix->stream));  // `rerun` (host vector) must outlive the H2D copy
+        }
+    } else {
+        rc = search_fp32_scan(ix, (int)nq, dq, (const float*)ix->ws_qnorm.p, (int)k, dD, dI);
+        if (rc) return rc;
+    }
+    PQ_CUDA(cudaEventRecord(ix->ev1, ix->stream));
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    float ms = 0.f;
+    PQ_CUDA(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+    ix->stats[6] = (int64_t)(ms * 1000.f);
+    return PQ_OK;
+}
+
+static int check_search_args(pq_index* ix, int64_t nq, const void* xq, int64_t k, const void* D, const void* I) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    if (nq < 0 || k < 1) return set_error(PQ_ERR_INVALID, "search: bad arguments (nq=%lld, k=%lld)", (long long)nq, (long long)k);
+    if (nq > 0 && (!xq || !D || !I)) return set_error(PQ_ERR_INVALID, "search: null buffer");
+    if (k > PQ_MAX_K) return set_error(PQ_ERR_UNSUPPORTED, "search: k=%lld exceeds PQ_MAX_K=%d", (long long)k, PQ_MAX_K);
+    if (nq > (int64_t)0x7fffff00) return set_error(PQ_ERR_UNSUPPORTED, "search: more than 2^31 queries in one call");
+    return PQ_OK;
+}
+
+}  // namespace pq
+
+using namespace pq;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int pq_index_create(int d, int metric, int device, pq_index** out) {
+    if (!out) return set_error(PQ_ERR_INVALID, "create: null out pointer");
+    *out = nullptr;
+    if (d != kDim) return set_error(PQ_ERR_INVALID, "create: d=%d, but this engine is built for d=128 (eval_retrieval.py:98)", d);
+    if (metric != PQ_METRIC_IP && metric != PQ_METRIC_L2) return set_error(PQ_ERR_INVALID, "create: unknown metric %d", metric);
+    pq_index* ix = new (std::nothrow) pq_index();
+    if (!ix) return set_error(PQ_ERR_OOM, "create: host allocation failed");
+    ix->d = d;
+    ix->metric = metric;
+    ix->requested_device = device;
+    ix->tier = PQ_TIER_AUTO;
+    const char* t = getenv("PROQA_B200_TIER");
+    if (t) {
+        if (!strcmp(t, "fp32")) ix->tier = PQ_TIER_FP32;
+        else if (!strcmp(t, "bf16")) ix->tier = PQ_TIER_BF16;
+    }
+    *out = ix;  // CUDA is touched lazily (first add/search): the reference forks after importing faiss
+    return PQ_OK;
+}
+
+void pq_index_free(pq_index* ix) {
+    if (!ix) return;
+    if (ix->device_ready) {
+        std::lock_guard<std::mutex> lock(g_device_mutex);
+        cudaSetDevice(ix->device);
+        cudaStreamSynchronize(ix->stream);
+        ix->release_all();
+        cudaEventDestroy(ix->ev0);
+        cudaEventDestroy(ix->ev1);
+        cudaStreamDestroy(ix->stream);
+    }
+    delete ix;
+}
+
+int pq_index_add(pq_index* ix, int64_t n, const float* x_host) { return index_add_impl(ix, n, x_host, false); }
+int pq_index_add_device(pq_index* ix, int64_t n, const float* x_dev) { return index_add_impl(ix, n, x_dev, true); }
+
+int pq_index_search(pq_index* ix, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I) {
+    int rc = check_search_args(ix, nq, xq, k, D, I);
+    if (rc) return rc;
+    if (nq == 0) return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    rc = ix->ws_q.ensure((size_t)nq * kDim * 4);
+    if (!rc) rc = ix->ws_D.ensure((size_t)nq * k * 4);
+    if (!rc) rc = ix->ws_I.ensure((size_t)nq * k * 8);
+    if (rc) return rc;
+    PQ_CUDA(cudaMemcpyAsync(ix->ws_q.p, xq, (size_t)nq * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
+    rc = search_device_impl(ix, nq, (const float*)ix->ws_q.p, k, (float*)ix->ws_D.p, (long long*)ix->ws_I.p);
+    if (rc) return rc;
+    PQ_CUDA(cudaMemcpyAsync(D, ix->ws_D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+    PQ_CUDA(cudaMemcpyAsync(I, ix->ws_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ix->stream));
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    return PQ_OK;
+}
+
+int pq_index_search_device(pq_index* ix, int64_t nq, const float* xq_dev, int64_t k, float* D_dev, int64_t* I_dev) {
+    int rc = check_search_args(ix, nq, xq_dev, k, D_dev, I_dev);
+    if (rc) return rc;
+    if (nq == 0) return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    // The caller's tensors were produced on its own stream(s); order after all prior device work.
+    PQ_CUDA(cudaDeviceSynchronize());
+    return search_device_impl(ix, nq, xq_dev, k, D_dev, (long long*)I_dev);
+}
+
+int pq_index_reset(pq_index* ix) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    ix->ntotal = 0;
+    ix->max_norm2 = 0.f;
+    ix->has_nonfinite = false;
+    if (ix->device_ready) {
+        PQ_CUDA(cudaSetDevice(ix->device));
+        PQ_CUDA(cudaMemsetAsync(ix->scalars.p, 0, 256, ix->stream));
+        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    }
+    return PQ_OK;
+}
+
+int64_t pq_index_ntotal(const pq_index* ix) { return ix ? ix->ntotal : 0; }
+int pq_index_d(const pq_index* ix) { return ix ? ix->d : 0; }
+int pq_index_metric(const pq_index* ix) { return ix ? ix->metric : -1; }
+
+int pq_index_set_id_base(pq_index* ix, int64_t id_base) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    ix->id_base = id_base;
+    return PQ_OK;
+}
+int pq_index_set_tier(pq_index* ix, int tier) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    if (tier < PQ_TIER_AUTO || tier > PQ_TIER_BF16) return set_error(PQ_ERR_INVALID, "unknown tier %d", tier);
+    ix->tier = tier;
+    return PQ_OK;
+}
+int pq_index_last_stats(const pq_index* ix, int64_t* out, int n) {
+    if (!ix || !out || n < 0) return set_error(PQ_ERR_INVALID, "last_stats: bad arguments");
+    for (int i = 0; i < n; ++i) out[i] = i < 8 ? ix->stats[i] : 0;
+    return PQ_OK;
+}
+
+int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists, const int64_t* I_lists,
+                           float* D_out, int64_t* I_out) {
+    if (n_lists < 1 || nq < 0 || k < 1 || !D_lists || !I_lists || !D_out || !I_out)
+        return set_error(PQ_ERR_INVALID, "merge_shard_results: bad arguments");
+    if ((int64_t)n_lists * k > 16384) return set_error(PQ_ERR_UNSUPPORTED, "merge_shard_results: n_lists*k=%lld > 16384", (long long)(n_lists * k));
+    int dev = -1;
+    int rc = pick_device(device, &dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    PQ_CUDA(cudaSetDevice(dev));
+    PQ_CUDA(cudaDeviceSynchronize());
+    PQ_CUDA(merge_di_launch(D_lists, (const long long*)I_lists, n_lists, (int)nq, (int)k, metric, D_out, (long long*)I_out, 0));
+    PQ_CUDA(cudaDeviceSynchronize());
+    return PQ_OK;
+}
+
+const char* pq_last_error(void) { return g_err; }
+const char* pq_version(void) { return "proqa_b200 0.1.0 sm_100a"; }
+
+}  // extern "C"

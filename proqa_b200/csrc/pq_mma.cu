@@ -1,0 +1,629 @@
+// proqa_b200 — tensor-core tier: tcgen05 bf16 filter + exact fp32 rescoring with an exactness certificate.
+//
+// For large query batches the Q.C^T contraction of IndexFlat::search (reference call site
+// retrieval/eval_retrieval.py:104; FAISS 1.6.3 runs it as sgemm_ on 4096x1024 blocks) is a dense
+// GEMM with K = 128.  This file runs it on the 5th-generation tensor cores and never writes the
+// score matrix:
+//
+//   pq_mma_filter_kernel  (one CTA per SM, warp-specialised)
+//     warp 0      TMA producer: query tiles once, then corpus tiles (128 rows x 256 B bf16) through a
+//                 4-stage shared-memory ring, SWIZZLE_128B, mbarrier completion
+//     warp 1      one elected thread issues tcgen05.mma (M=128 queries x N=128 rows x K=16, bf16 -> fp32)
+//                 into 4 rotating TMEM accumulators (4 x 128 columns = all 512)
+//     warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers; one thread owns one query
+//                 (a TMEM lane), so the admission threshold is a register compare; survivors (rare)
+//                 are appended to the query's private candidate slab in global memory
+//   pq_epoch_select_kernel  folds the slabs of one epoch into a per-query carry list (top-K' by bf16
+//                 score) and raises the query's admission threshold to  A_k - 2E
+//   pq_rescore_kernel       recomputes the carry list's scores with the engine's defined fp32 chain,
+//                 sorts, emits (D, I) and evaluates the exactness certificate.
+//
+// Exactness: |bf16 score - fp32 score| <= E_q = eps * |q| * max|c|.  Every row of the
+// true top-k has approximate score >= A_k - 2E (A_k = k-th best approximate score), so filtering at
+// any threshold <= A_k(seen so far) - 2E loses nothing.  The only lossy step is truncating the carry
+// list at K' entries; the largest score ever truncated is tracked ("dropmax") and the certificate is
+// dropmax < A_k(final) - 2E.  Queries that fail it (or overflow a slab) are re-run by the fp32 scan.
+#include "pq_common.cuh"
+#include "pq_host.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace pq {
+
+constexpr int kBM = 128;            // queries per M tile (TMEM lanes)
+constexpr int kBN = 128;            // corpus rows per B tile (TMEM columns per accumulator)
+constexpr int kStages = 4;          // B ring depth
+constexpr int kAccBufs = 4;         // TMEM accumulators (4 x 128 cols = 512)
+constexpr int kPanelBytes = 128 * 128;         // 128 rows x 128 B (64 bf16): one swizzle-128B K panel
+constexpr int kTileBytes = 2 * kPanelBytes;    // K = 128 -> two panels, 32 KB
+constexpr int kEpiWarps = 8;
+constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
+constexpr int kMaxMTiles = 3;
+
+// eps: bf16 rounding of both operands (2^-8 + 2^-18), tensor-core fp32 accumulation slack (2^-13) and the
+// fp32 chain's own rounding (128 * 2^-24), relative to sum|q_i c_i| <= |q||c|; plus 2% head-room.
+constexpr float kEps = 0.0042f;
+
+struct MmaCtrl {
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t tmem_full[kAccBufs];
+    uint64_t tmem_empty[kAccBufs];
+    uint64_t a_full;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+struct MmaParams {
+    uint64_t* cand_keys;   // [nq_pad][n_sub][cap]
+    uint32_t* cand_cnt;    // [nq_pad][n_sub]
+    const float* thr;      // [nq_pad]
+    const float* two_e;    // [nq_pad]
+    long long row_begin;   // multiple of 128
+    long long row_end;     // exclusive, <= ntotal
+    int tiles_per_slice;
+    int n_mtiles;          // total query tiles
+    int cap;
+    int n_sub;
+    int k1_adapt;
+};
+
+template <int M_TILES>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, const MmaParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;                                        // M_TILES x 32 KB
+    uint8_t* smem_b = smem + (size_t)M_TILES * kTileBytes;         // kStages x 32 KB
+    MmaCtrl* ctrl = reinterpret_cast<MmaCtrl*>(smem_b + (size_t)kStages * kTileBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int group = blockIdx.x;
+    const int slice = blockIdx.y;
+    const int mt0 = group * M_TILES;
+    const int m = min(M_TILES, p.n_mtiles - mt0);
+
+    const long long total_tiles = (p.row_end - p.row_begin + kBN - 1) / kBN;
+    const long long tile_begin = (long long)slice * p.tiles_per_slice;
+    long long nt = total_tiles - tile_begin;
+    nt = nt < 0 ? 0 : (nt > p.tiles_per_slice ? p.tiles_per_slice : nt);
+    const int ntiles = (int)nt;
+    const long long row0 = p.row_begin + tile_begin * kBN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_c);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) {
+                mbar_init(&ctrl->full[s], 1);
+                mbar_init(&ctrl->empty[s], 1);
+            }
+            for (int b = 0; b < kAccBufs; ++b) {
+                mbar_init(&ctrl->tmem_full[b], 1);
+                mbar_init(&ctrl->tmem_empty[b], kEpiWarps);
+            }
+            mbar_init(&ctrl->a_full, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(&ctrl->tmem_base);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = ctrl->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0 && ntiles > 0) {
+            mbar_arrive_expect_tx(&ctrl->a_full, (uint32_t)m * kTileBytes);
+            for (int mi = 0; mi < m; ++mi)
+                for (int pnl = 0; pnl < 2; ++pnl)
+                    tma_load_2d(smem_a + (size_t)mi * kTileBytes + pnl * kPanelBytes, &tmap_q, pnl * 64, (mt0 + mi) * kBM, &ctrl->a_full);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kStages;
+                const uint32_t ph = (uint32_t)(t / kStages) & 1u;
+                mbar_wait(&ctrl->empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&ctrl->full[s], kTileBytes);
+                const int y = (int)(row0 + (long long)t * kBN);
+                for (int pnl = 0; pnl < 2; ++pnl)
+                    tma_load_2d(smem_b + (size_t)s * kTileBytes + pnl * kPanelBytes, &tmap_c, pnl * 64, y, &ctrl->full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0 && ntiles > 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN);
+            const uint32_t a_addr = smem_u32(smem_a);
+            const uint32_t b_addr = smem_u32(smem_b);
+            mbar_wait(&ctrl->a_full, 0);
+            tc_fence_after_sync();
+            int it = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kStages;
+                const uint32_t ph = (uint32_t)(t / kStages) & 1u;
+                mbar_wait(&ctrl->full[s], ph);
+                tc_fence_after_sync();
+                for (int mi = 0; mi < m; ++mi, ++it) {
+                    const int b = it % kAccBufs;
+                    const uint32_t aph = (uint32_t)(it / kAccBufs) & 1u;
+                    mbar_wait(&ctrl->tmem_empty[b], aph ^ 1u);
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)b * kBN;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t koff = (uint32_t)(ks >> 2) * kPanelBytes + (uint32_t)(ks & 3) * 32u;
+                        const uint64_t adesc = umma_desc_k128(a_addr + (uint32_t)mi * kTileBytes + koff);
+                        const uint64_t bdesc = umma_desc_k128(b_addr + (uint32_t)s * kTileBytes + koff);
+                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&ctrl->tmem_full[b]);
+                }
+                umma_commit(&ctrl->empty[s]);
+            }
+        }
+    } else {
+        // ===================== epilogue: threshold filter =====================
+        const int e = warp - 2;
+        const int quarter = warp & 3;   // TMEM lane quarter this warp may read
+        const int half = e >> 2;        // which 64 columns of each 128-column accumulator
+        const int lane_q = quarter * 32 + lane;
+        const int sub = slice * 2 + half;
+        float thr[M_TILES], two_e[M_TILES];
+        uint32_t cnt[M_TILES];
+        uint64_t* slab[M_TILES];
+#pragma unroll
+        for (int mi = 0; mi < M_TILES; ++mi) {
+            cnt[mi] = 0;
+            thr[mi] = INFINITY;
+            two_e[mi] = 0.f;
+            slab[mi] = nullptr;
+            if (mi < m) {
+                const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
+                thr[mi] = p.thr[q];
+                two_e[mi] = p.two_e[q];
+                slab[mi] = p.cand_keys + (q * p.n_sub + sub) * (size_t)p.cap;
+            }
+        }
+        int it = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const long long tile_row = row0 + (long long)t * kBN + half * 64;
+#pragma unroll
+            for (int mi = 0; mi < M_TILES; ++mi) {
+                if (mi < m) {
+                    const int b = it % kAccBufs;
+                    const uint32_t aph = (uint32_t)(it / kAccBufs) & 1u;
+                    ++it;
+                    mbar_wait(&ctrl->tmem_full[b], aph);
+                    tc_fence_after_sync();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kBN + half * 64);
+                    float v[2][32];
+                    tmem_ld_32x32(taddr, v[0]);
+                    tmem_ld_32x32(taddr + 32, v[1]);
+                    tmem_ld_wait();
+                    // The accumulator is in registers now: hand the TMEM buffer back before filtering.
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const long long base_row = tile_row + c * 32;
+                        if (base_row + 32 > p.row_end) {  // ragged last tile: TMA zero-filled or next-epoch rows
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (base_row + i >= p.row_end) v[c][i] = -INFINITY;
+                        }
+                        float mx = v[c][0];
+#pragma unroll
+                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[c][i]);
+                        const float th = thr[mi];
+                        if (p.k1_adapt) thr[mi] = fmaxf(th, mx - two_e[mi]);
+                        if (__any_sync(0xffffffffu, mx >= th)) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                if (v[c][i] >= th) {
+                                    if (cnt[mi] < (uint32_t)p.cap) slab[mi][cnt[mi]] = make_key(v[c][i], (uint32_t)(base_row + i));
+                                    ++cnt[mi];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < M_TILES; ++mi) {
+            if (mi < m) {
+                const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
+                p.cand_cnt[q * p.n_sub + sub] = cnt[mi];
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-query state
+// ------------------------------------------------------------------------------------------------
+struct QState {
+    float* thr;          // [nq_pad] admission threshold (bf16-score domain)
+    float* two_e;        // [nq_pad]
+    float* dropmax;      // [nq_pad]
+    uint32_t* overflow;  // [nq_pad]
+    uint64_t* carry;     // [nq_pad][kp]
+};
+
+__global__ void pq_mma_init_state_kernel(QState st, const float* __restrict__ q_norm2, const uint8_t* __restrict__ q_bad, int nq,
+                                         int nq_pad, int kp, float max_norm2) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq_pad) return;
+    const bool live = q < nq && !q_bad[q];
+    // 2E with E = eps * |q| * max|c|; sqrt rounded up by the head-room in kEps
+    const float e2 = live ? 2.f * kEps * sqrtf(q_norm2[q]) * sqrtf(max_norm2) : 0.f;
+    st.two_e[q] = e2;
+    st.thr[q] = live ? PQ_THR_FLOOR : INFINITY;
+    st.dropmax[q] = -INFINITY;
+    st.overflow[q] = (live && isfinite(e2)) ? 0u : (q < nq ? 1u : 0u);
+}
+
+struct EpochSelParams {
+    QState st;
+    const uint64_t* cand_keys;
+    const uint32_t* cand_cnt;
+    int n_sub, cap, kp, k, work;
+};
+
+// One CTA per query: carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
+__global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ int s_fill;
+    __shared__ float s_drop;
+    __shared__ int s_ovf;
+    const int q = blockIdx.x;
+    const int t = threadIdx.x;
+    uint64_t* carry = p.st.carry + (size_t)q * p.kp;
+    if (t == 0) {
+        s_fill = 0;
+        s_drop = -INFINITY;
+        s_ovf = 0;
+    }
+    __syncthreads();
+    for (int i = t; i < p.kp; i += 256) {
+        const uint64_t key = carry[i];
+        if (key != 0ull) work[atomicAdd(&s_fill, 1)] = key;
+    }
+    __syncthreads();
+    const int round = p.work - p.kp;
+    const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
+    const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
+    const int total = p.n_sub * p.cap;
+    for (int r0 = 0; r0 < total || r0 == 0; r0 += round) {
+        const int r1 = min(r0 + round, total);
+        for (int idx = r0 + t; idx < r1; idx += 256) {
+            const int sub = idx / p.cap, pos = idx - sub * p.cap;
+            const uint32_t c = cnts[sub];
+            if (pos == 0 && c > (uint32_t)p.cap) s_ovf = 1;
+            if ((uint32_t)pos < c) work[atomicAdd(&s_fill, 1)] = keys[idx];
+        }
+        __syncthreads();
+        const int fill = s_fill;
+        const bool last = (r1 >= total);
+        if (last || fill + round > p.work) {
+            for (int i = fill + t; i < p.work; i += 256) work[i] = 0ull;
+            __syncthreads();
+            block_sort_desc<256>(work, p.work);
+            if (t == 0) {
+                if (fill > p.kp) s_drop = fmaxf(s_drop, key_score(work[p.kp]));
+                s_fill = min(fill, p.kp);
+            }
+            __syncthreads();
+        }
+        if (last) break;
+    }
+    for (int i = t; i < p.kp; i += 256) carry[i] = work[i];
+    if (t == 0) {
+        if (s_drop > -INFINITY) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], s_drop);
+        if (s_ovf) p.st.overflow[q] = 1u;
+        if (s_fill >= p.k) {
+            const float ak = key_score(work[p.k - 1]);
+            p.st.thr[q] = fmaxf(p.st.thr[q], ak - p.st.two_e[q]);
+        }
+    }
+}
+
+struct RescoreParams {
+    QState st;
+    const float* queries;    // [nq][128] fp32
+    const float* rows;       // [ntotal][128] fp32
+    const float* row_norms;
+    const float* q_norms;
+    const uint8_t* q_bad;
+    int kp, k, metric, work;
+    long long id_base;
+    float* D;
+    long long* I;
+    uint8_t* fail;
+};
+
+// One CTA per query: exact fp32 scores for the carry list, final order, certificate.
+__global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ float s_q[kDim];
+    const int q = blockIdx.x;
+    const int t = threadIdx.x;
+    const uint64_t* carry = p.st.carry + (size_t)q * p.kp;
+    if (t < kDim) s_q[t] = p.queries[(size_t)q * kDim + t];
+    __syncthreads();
+    for (int i = t; i < p.work; i += 256) {
+        uint64_t out = 0ull;
+        if (i < p.kp) {
+            const uint64_t key = carry[i];
+            if (key != 0ull) {
+                const uint32_t row = key_row(key);
+                const float4* r4 = reinterpret_cast<const float4*>(p.rows + (size_t)row * kDim);
+                float acc = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < kDim / 4; ++j) {
+                    const float4 v = __ldg(r4 + j);
+                    acc = fmaf(v.x, s_q[4 * j + 0], acc);
+                    acc = fmaf(v.y, s_q[4 * j + 1], acc);
+                    acc = fmaf(v.z, s_q[4 * j + 2], acc);
+                    acc = fmaf(v.w, s_q[4 * j + 3], acc);
+                }
+                if (p.metric == kMetricL2) acc = fmaf(2.f, acc, -__ldg(p.row_norms + row));
+                if (acc >= PQ_THR_FLOOR) out = make_key(acc, row);
+            }
+        }
+        work[i] = out;
+    }
+    __syncthreads();
+    block_sort_desc<256>(work, p.work);
+    for (int i = t; i < p.k; i += 256) {
+        const uint64_t key = work[i];
+        float d;
+        long long id;
+        if (key == 0ull) {
+            id = -1;
+            d = (p.metric == kMetricL2) ? FLT_MAX : -FLT_MAX;
+        } else {
+            id = (long long)key_row(key) + p.id_base;
+            const float s = key_score(key);
+            d = (p.metric == kMetricL2) ? fmaxf(0.f, p.q_norms[q] - s) : s;
+        }
+        p.D[(size_t)q * p.k + i] = d;
+        p.I[(size_t)q * p.k + i] = id;
+    }
+    if (t == 0) {
+        bool fail = p.q_bad[q] != 0 || p.st.overflow[q] != 0;
+        const float two_e = p.st.two_e[q];
+        const float dropmax = p.st.dropmax[q];
+        const uint64_t kth = carry[p.k - 1];
+        if (dropmax > -INFINITY && two_e > 0.f) {
+            const float bar = (kth != 0ull) ? key_score(kth) - two_e : -INFINITY;
+            if (dropmax >= bar) fail = true;
+        }
+        p.fail[q] = fail ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+static int next_pow2i(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <int M>
+static cudaError_t launch_filter(const CUtensorMap& tq, const CUtensorMap& tc, const MmaParams& p, dim3 grid, cudaStream_t stream) {
+    const size_t smem = (size_t)M * kTileBytes + (size_t)kStages * kTileBytes + sizeof(MmaCtrl);
+    cudaError_t e = cudaFuncSetAttribute(pq_mma_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pq_mma_filter_kernel<M><<<grid, kMmaThreads, smem, stream>>>(tq, tc, p);
+    return cudaGetLastError();
+}
+
+struct EpochPlan {
+    long long begin, end;
+    int n_slices, tiles_per_slice, cap;
+};
+
+static int carry_size_for_k(int k) {
+    int kp = next_pow2i((k * 5 + 1) / 2);
+    return std::max(kp, 64);
+}
+
+static int pick_slices(int n_groups, long long tiles, int n_sms) {
+    long long s;
+    if (n_groups <= n_sms) {
+        s = n_sms / n_groups;
+    } else {
+        double best = 0.0;
+        s = 1;
+        for (int c = 1; c <= 8; ++c) {
+            const long long ctas = (long long)n_groups * c;
+            const double eff = (double)ctas / ((double)n_sms * (double)((ctas + n_sms - 1) / n_sms));
+            if (eff > best + 1e-9) {
+                best = eff;
+                s = c;
+            }
+        }
+    }
+    if (s > tiles) s = tiles;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, float* dD_all, long long* dI_all,
+                      std::vector<int>* rerun) {
+    const long long N = ix->ntotal;
+    const int kp = carry_size_for_k(k);
+    const bool k1 = (k == 1);
+    constexpr int kMaxBatch = 262144;  // queries per pass (bounds the candidate slabs)
+
+    for (int qb = 0; qb < nq_total; qb += kMaxBatch) {
+        const int nq = std::min(kMaxBatch, nq_total - qb);
+        const int nq_pad = (nq + kBM - 1) / kBM * kBM;
+        const int n_mtiles = nq_pad / kBM;
+        const int M = std::min(kMaxMTiles, n_mtiles);
+        const int n_groups = (n_mtiles + M - 1) / M;
+        const float* dq = dq_all + (size_t)qb * kDim;
+        const uint16_t* dq_bf16 = (const uint16_t*)ix->ws_qbf16.p + (size_t)qb * kDim;
+        const float* dq_norm = (const float*)ix->ws_qnorm.p + qb;
+        const uint8_t* dq_bad = (const uint8_t*)ix->ws_qbad.p + qb;
+
+        // ---- epoch plan -----------------------------------------------------------------------
+        std::vector<EpochPlan> plan;
+        if (k1) {
+            EpochPlan ep;
+            ep.begin = 0;
+            ep.end = N;
+            const long long tiles = (N + kBN - 1) / kBN;
+            ep.n_slices = pick_slices(n_groups, tiles, ix->n_sms);
+            ep.tiles_per_slice = (int)((tiles + ep.n_slices - 1) / ep.n_slices);
+            ep.n_slices = (int)((tiles + ep.tiles_per_slice - 1) / ep.tiles_per_slice);
+            ep.cap = 128;
+            plan.push_back(ep);
+        } else {
+            const long long n0 = std::min<long long>(N, std::max(1024, next_pow2i(2 * kp)));
+            long long begin = 0, end = n0;
+            while (begin < N) {
+                EpochPlan ep;
+                ep.begin = begin;
+                ep.end = std::min(end, N);
+                const long long tiles = (ep.end - ep.begin + kBN - 1) / kBN;
+                if (begin == 0) {  // bootstrap: every score is a candidate, one tile per slice
+                    ep.n_slices = (int)tiles;
+                    ep.tiles_per_slice = 1;
+                    ep.cap = 64;
+                } else {
+                    ep.n_slices = pick_slices(n_groups, tiles, ix->n_sms);
+                    ep.tiles_per_slice = (int)((tiles + ep.n_slices - 1) / ep.n_slices);
+                    ep.n_slices = (int)((tiles + ep.tiles_per_slice - 1) / ep.tiles_per_slice);
+                    const double expect = (double)kp * log((double)ep.end / (double)ep.begin) / (2.0 * ep.n_slices);
+                    ep.cap = std::min(4096, std::max(64, next_pow2i((int)(4.0 * expect) + 32)));
+                }
+                plan.push_back(ep);
+                begin = ep.end;
+                end = (ep.end >= N / 2 || ep.end * 8 >= N) ? N : ep.end * 8;
+            }
+        }
+        size_t max_slab = 0, max_cnt = 0;
+        for (const EpochPlan& ep : plan) {
+            max_slab = std::max(max_slab, (size_t)nq_pad * ep.n_slices * 2 * ep.cap * 8);
+            max_cnt = std::max(max_cnt, (size_t)nq_pad * ep.n_slices * 2 * 4);
+        }
+
+        // ---- workspaces -----------------------------------------------------------------------
+        DevBuf* w = ix->ws_mma;
+        int rc = w[0].ensure((size_t)nq_pad * 4);                 // thr
+        if (!rc) rc = w[1].ensure((size_t)nq_pad * 4);            // two_e
+        if (!rc) rc = w[2].ensure((size_t)nq_pad * 4);            // dropmax
+        if (!rc) rc = w[3].ensure((size_t)nq_pad * 4);            // overflow
+        if (!rc) rc = w[4].ensure((size_t)nq_pad * kp * 8);       // carry
+        if (!rc) rc = w[5].ensure(max_slab);                      // candidate slabs
+        if (!rc) rc = w[6].ensure(max_cnt);                       // slab counts
+        if (!rc) rc = w[7].ensure((size_t)nq_pad);                // fail flags
+        if (rc) return rc;
+        QState st;
+        st.thr = (float*)w[0].p;
+        st.two_e = (float*)w[1].p;
+        st.dropmax = (float*)w[2].p;
+        st.overflow = (uint32_t*)w[3].p;
+        st.carry = (uint64_t*)w[4].p;
+
+        CUtensorMap tmap_q;
+        rc = make_row_tensor_map(&tmap_q, dq_bf16, nq_pad, 2, 64, kBM);
+        if (rc) return rc;
+
+        PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
+        pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, dq_bad, nq, nq_pad, kp, ix->max_norm2);
+        PQ_CUDA(cudaGetLastError());
+        ix->stats[5] += 1;
+
+        // ---- epochs ---------------------------------------------------------------------------
+        for (const EpochPlan& ep : plan) {
+            MmaParams mp;
+            mp.cand_keys = (uint64_t*)w[5].p;
+            mp.cand_cnt = (uint32_t*)w[6].p;
+            mp.thr = st.thr;
+            mp.two_e = st.two_e;
+            mp.row_begin = ep.begin;
+            mp.row_end = ep.end;
+            mp.tiles_per_slice = ep.tiles_per_slice;
+            mp.n_mtiles = n_mtiles;
+            mp.cap = ep.cap;
+            mp.n_sub = ep.n_slices * 2;
+            mp.k1_adapt = k1 ? 1 : 0;
+            const dim3 grid((unsigned)n_groups, (unsigned)ep.n_slices);
+            cudaError_t e;
+            if (M == 1) e = launch_filter<1>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
+            else if (M == 2) e = launch_filter<2>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
+            else e = launch_filter<3>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
+            PQ_CUDA(e);
+
+            EpochSelParams sp;
+            sp.st = st;
+            sp.cand_keys = mp.cand_keys;
+            sp.cand_cnt = mp.cand_cnt;
+            sp.n_sub = mp.n_sub;
+            sp.cap = ep.cap;
+            sp.kp = kp;
+            sp.k = k;
+            sp.work = std::max(2048, next_pow2i(kp + 1024));
+            const size_t smem = (size_t)sp.work * 8;
+            PQ_CUDA(cudaFuncSetAttribute(pq_epoch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
+            PQ_CUDA(cudaGetLastError());
+            ix->stats[3] += 1;
+            ix->stats[4] += 1;
+            ix->stats[5] += 2;
+        }
+
+        // ---- exact rescoring + certificate ------------------------------------------------------
+        RescoreParams rp;
+        rp.st = st;
+        rp.queries = dq;
+        rp.rows = (const float*)ix->rows_f32.p;
+        rp.row_norms = (const float*)ix->norms.p;
+        rp.q_norms = dq_norm;
+        rp.q_bad = dq_bad;
+        rp.kp = kp;
+        rp.k = k;
+        rp.metric = ix->metric;
+        rp.work = std::max(kp, next_pow2i(k));
+        rp.id_base = ix->id_base;
+        rp.D = dD_all + (size_t)qb * k;
+        rp.I = dI_all + (size_t)qb * k;
+        rp.fail = (uint8_t*)w[7].p;
+        const size_t rsmem = (size_t)rp.work * 8;
+        PQ_CUDA(cudaFuncSetAttribute(pq_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        pq_rescore_kernel<<<nq, 256, rsmem, ix->stream>>>(rp);
+        PQ_CUDA(cudaGetLastError());
+        ix->stats[4] += 1;
+        ix->stats[5] += 1;
+
+        std::vector<uint8_t> fail((size_t)nq);
+        PQ_CUDA(cudaMemcpyAsync(fail.data(), w[7].p, (size_t)nq, cudaMemcpyDeviceToHost, ix->stream));
+        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+        for (int q = 0; q < nq; ++q)
+            if (fail[q]) rerun->push_back(qb + q);
+    }
+    return PQ_OK;
+}
+
+}  // namespace pq

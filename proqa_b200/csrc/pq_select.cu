@@ -1,0 +1,222 @@
+// proqa_b200 — selection / merge kernels and row preparation.
+//
+//  * pq_merge_lists_kernel : per query, fold any number of candidate key lists into the final
+//    sorted top-k and write FAISS-shaped outputs (D fp32 [nq,k], I int64 [nq,k], padding
+//    I=-1 / D=-FLT_MAX as IndexFlat::search does when k > ntotal; L2 reports squared distances
+//    ascending, clamped at 0).  Used after the fp32 scan (one list per CTA).
+//  * pq_merge_di_kernel    : fold G already-final (D, I) lists (one per GPU shard, after the
+//    NCCL all-gather) into one; ties resolve to the lower global id.
+//  * pq_prep_rows_kernel   : at add(): squared row norms, bf16 copy for the tensor-core filter,
+//    running max norm and non-finite detection.
+#include "pq_common.cuh"
+#include "pq_internal.h"
+
+namespace pq {
+
+constexpr int kSelThreads = 256;
+
+struct MergeParams {
+    MergeLaunch a;
+    int work;  // power-of-two size of the shared work array
+};
+
+__device__ __forceinline__ void emit_result(const MergeLaunch& a, int q, int i, uint64_t key) {
+    float d;
+    long long id;
+    if (key == 0ull) {
+        id = -1;
+        d = (a.metric == kMetricL2) ? FLT_MAX : -FLT_MAX;
+    } else {
+        id = (long long)key_row(key) + a.id_base;
+        const float s = key_score(key);
+        d = (a.metric == kMetricL2) ? fmaxf(0.f, a.q_norms[q] - s) : s;
+    }
+    if (a.D) a.D[(size_t)q * a.k + i] = d;
+    if (a.I) a.I[(size_t)q * a.k + i] = id;
+    if (a.out_keys) a.out_keys[(size_t)q * a.k + i] = key;
+}
+
+__global__ void __launch_bounds__(kSelThreads) pq_merge_lists_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ int s_fill;
+    const MergeLaunch& a = p.a;
+    const int q = blockIdx.x;
+    const int t = threadIdx.x;
+    const uint32_t thr = a.gthr ? a.gthr[q] : 0u;
+    const uint64_t* base = a.keys + (size_t)q * a.q_stride;
+    const long long total = (long long)a.n_lists * a.list_len;
+    const int round = p.work - a.k;  // candidates examined between two compaction checks
+
+    if (t == 0) s_fill = 0;
+    __syncthreads();
+    for (long long r0 = 0; r0 < total; r0 += round) {
+        const long long r1 = (r0 + round < total) ? r0 + round : total;
+        for (long long idx = r0 + t; idx < r1; idx += kSelThreads) {
+            const int list = (int)(idx / a.list_len);
+            const int pos = (int)(idx - (long long)list * a.list_len);
+            if (a.counts && pos >= (int)a.counts[(size_t)q * a.cnt_q_stride + list]) continue;
+            const uint64_t key = base[(size_t)list * a.list_stride + pos];
+            if (key != 0ull && uint32_t(key >> 32) >= thr) work[atomicAdd(&s_fill, 1)] = key;
+        }
+        __syncthreads();
+        const int fill = s_fill;
+        const bool last = (r1 == total);
+        if (last || fill + round > p.work) {
+            for (int i = fill + t; i < p.work; i += kSelThreads) work[i] = 0ull;
+            __syncthreads();
+            block_sort_desc<kSelThreads>(work, p.work);
+            if (t == 0) s_fill = fill < a.k ? fill : a.k;
+            __syncthreads();
+        }
+    }
+    if (total == 0) {
+        for (int i = t; i < p.work; i += kSelThreads) work[i] = 0ull;
+        __syncthreads();
+    }
+    for (int i = t; i < a.k; i += kSelThreads) emit_result(a, q, i, work[i]);
+}
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+cudaError_t merge_lists_launch(const MergeLaunch& a, cudaStream_t stream) {
+    if (a.nq <= 0) return cudaSuccess;
+    MergeParams p;
+    p.a = a;
+    p.work = next_pow2(a.k + 1024);
+    if (p.work < 2048) p.work = 2048;
+    const size_t smem = (size_t)p.work * 8;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(pq_merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pq_merge_lists_kernel<<<a.nq, kSelThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// (D, I) list merge across shards.  Lists arrive ordered by shard rank; shards own ascending,
+// disjoint id ranges and each list is already in (score desc, id asc) order, so the position
+// g*k + i is a valid tie-break proxy for the global id.
+// ------------------------------------------------------------------------------------------------
+struct MergeDIParams {
+    const float* D_in;
+    const long long* I_in;
+    float* D_out;
+    long long* I_out;
+    int n_lists, nq, k, metric, work;
+};
+
+__global__ void __launch_bounds__(kSelThreads) pq_merge_di_kernel(const MergeDIParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
+    const int q = blockIdx.x;
+    const int t = threadIdx.x;
+    const int total = p.n_lists * p.k;
+    // total <= work is guaranteed by the launcher
+    for (int idx = t; idx < p.work; idx += kSelThreads) {
+        uint64_t key = 0ull;
+        if (idx < total) {
+            const int g = idx / p.k, i = idx - g * p.k;
+            const size_t off = ((size_t)g * p.nq + q) * p.k + i;
+            const long long id = p.I_in[off];
+            if (id >= 0) {
+                const float d = p.D_in[off];
+                key = make_key(p.metric == kMetricL2 ? -d : d, (uint32_t)idx);
+            }
+        }
+        work[idx] = key;
+    }
+    __syncthreads();
+    block_sort_desc<kSelThreads>(work, p.work);
+    for (int i = t; i < p.k; i += kSelThreads) {
+        const uint64_t key = work[i];
+        float d;
+        long long id;
+        if (key == 0ull) {
+            id = -1;
+            d = (p.metric == kMetricL2) ? FLT_MAX : -FLT_MAX;
+        } else {
+            const int idx = (int)key_row(key);
+            const int g = idx / p.k, j = idx - g * p.k;
+            const size_t off = ((size_t)g * p.nq + q) * p.k + j;
+            id = p.I_in[off];
+            d = p.D_in[off];
+        }
+        p.D_out[(size_t)q * p.k + i] = d;
+        p.I_out[(size_t)q * p.k + i] = id;
+    }
+}
+
+cudaError_t merge_di_launch(const float* D_in, const long long* I_in, int n_lists, int nq, int k, int metric, float* D_out,
+                            long long* I_out, cudaStream_t stream) {
+    if (nq <= 0) return cudaSuccess;
+    MergeDIParams p{D_in, I_in, D_out, I_out, n_lists, nq, k, metric, 0};
+    p.work = next_pow2(n_lists * k);
+    if (p.work < 2) p.work = 2;
+    const size_t smem = (size_t)p.work * 8;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(pq_merge_di_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pq_merge_di_kernel<<<nq, kSelThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// add(): per-row preparation.  One warp per row; lane l owns dims 4l..4l+3 for the bf16 copy,
+// lane 0 runs the sequential norm chain (the norm is part of the engine's defined L2 score).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pq_prep_rows_kernel(const float* __restrict__ rows, long long n, uint16_t* __restrict__ rows_bf16,
+                                                           float* __restrict__ norms, uint32_t* max_norm_bits,
+                                                           uint32_t* nonfinite_flag, uint8_t* __restrict__ row_bad) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float local_max = 0.f;
+    bool bad = false;
+    for (long long row = warp; row < n; row += n_warps) {
+        const float4 v = *reinterpret_cast<const float4*>(rows + row * kDim + lane * 4);
+        // bf16 copy (round to nearest even)
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 packed;
+        packed.x = *reinterpret_cast<uint32_t*>(&lo);
+        packed.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(rows_bf16 + row * kDim + lane * 4) = packed;
+        // non-finite after rounding (covers inf/NaN inputs and fp32 values that overflow bf16)
+        const float bx = __low2float(lo), by = __high2float(lo), bz = __low2float(hi), bw = __high2float(hi);
+        // squared norm as a sequential fmaf chain over dims 0..127 (lane order), carried by shuffles
+        float acc = 0.f;
+#pragma unroll 1
+        for (int l = 0; l < 32; ++l) {
+            const float x = __shfl_sync(0xffffffffu, v.x, l), y = __shfl_sync(0xffffffffu, v.y, l);
+            const float z = __shfl_sync(0xffffffffu, v.z, l), w = __shfl_sync(0xffffffffu, v.w, l);
+            acc = fmaf(x, x, acc);
+            acc = fmaf(y, y, acc);
+            acc = fmaf(z, z, acc);
+            acc = fmaf(w, w, acc);
+        }
+        if (lane == 0) norms[row] = acc;
+        bool row_is_bad = !(isfinite(bx) && isfinite(by) && isfinite(bz) && isfinite(bw));
+        row_is_bad = __any_sync(0xffffffffu, row_is_bad) || !(acc <= FLT_MAX);  // inf or NaN norm
+        if (row_bad && lane == 0) row_bad[row] = row_is_bad ? 1 : 0;
+        bad |= row_is_bad;
+        local_max = fmaxf(local_max, acc);
+    }
+    if (nonfinite_flag && bad && lane == 0) atomicOr(nonfinite_flag, 1u);
+    if (max_norm_bits && lane == 0 && local_max > 0.f) atomicMax(max_norm_bits, __float_as_uint(local_max));  // non-negative floats order as uints
+}
+
+cudaError_t prep_rows_launch(const float* rows, long long n, uint16_t* rows_bf16, float* norms, uint32_t* max_norm_bits,
+                             uint32_t* nonfinite_flag, uint8_t* row_bad, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    long long blocks = (n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pq_prep_rows_kernel<<<(int)blocks, 256, 0, stream>>>(rows, n, rows_bf16, norms, max_norm_bits, nonfinite_flag, row_bad);
+    return cudaGetLastError();
+}
+
+}  // namespace pq

@@ -1,0 +1,192 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bar (north star): integer/index work bit-exact — every tier must reproduce oracle.engine_spec (the engine's
+defined fp32 score and order) bit for bit; and against the fp64 ground truth scores within 1e-4 relative,
+ids identical except within that tolerance of a tie.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import data
+
+pytestmark = pytest.mark.gpu
+
+
+def _index(metric, xb, tier):
+    import proqa_b200 as pq
+    ix = pq.IndexFlatIP(128) if metric == 0 else pq.IndexFlatL2(128)
+    ix.set_tier(tier)
+    if len(xb):
+        ix.add(xb)
+    return ix
+
+
+def _assert_bit_exact(D, I, Dr, Ir):
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D.view(np.uint32), Dr.view(np.uint32))
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("nq,nb,k", [(1, 1000, 10), (3, 5000, 80), (16, 20000, 100), (19, 4097, 1), (21, 12345, 80),
+                                      (40, 777, 128), (5, 300, 1000), (2, 20000, 1000)])
+def test_fp32_tier_bit_exact(metric, nq, nb, k):
+    xb, xq = data.corpus(nb), data.queries(nq)
+    ix = _index(metric, xb, "fp32")
+    D, I = ix.search(xq, k)
+    Dr, Ir = oracle.engine_spec(xq, xb, k, metric)
+    _assert_bit_exact(D, I, Dr, Ir)
+    assert not oracle.check_against_truth(D, I, xq, xb, k, metric)
+
+
+@pytest.mark.parametrize("nq,nb,k,kind", [(128, 40000, 80, "normal"), (300, 100000, 100, "normal"), (64, 65536, 1, "normal"),
+                                           (200, 50000, 10, "fp16"), (130, 30000, 80, "unit"), (100, 60000, 80, "skewed"),
+                                           (512, 20000, 256, "normal"), (1000, 33000, 5, "normal")])
+def test_bf16_tier_bit_exact(nq, nb, k, kind):
+    xb, xq = data.corpus(nb, kind=kind), data.queries(nq, kind=kind)
+    ix = _index(0, xb, "bf16")
+    D, I = ix.search(xq, k)
+    Dr, Ir = oracle.engine_spec(xq, xb, k, 0)
+    _assert_bit_exact(D, I, Dr, Ir)
+    st = ix.last_stats
+    assert st[0] + st[1] == nq
+    assert st[3] > 0, "tensor-core filter did not run"
+
+
+def test_tiers_agree_and_match_truth():
+    xb, xq = data.corpus(200000), data.queries(256)
+    res = {}
+    for tier in ("fp32", "bf16", "auto"):
+        ix = _index(0, xb, tier)
+        res[tier] = ix.search(xq, 80)
+        del ix
+    _assert_bit_exact(*res["fp32"], *res["bf16"])
+    _assert_bit_exact(*res["fp32"], *res["auto"])
+    assert not oracle.check_against_truth(*res["auto"], xq, xb, 80, 0)
+
+
+def test_faiss_restatement_agrees_within_tolerance():
+    """What FAISS would print (oracle restatement) vs the engine: same ids except near-ties, scores within 1e-4."""
+    xb, xq = data.corpus(50000), data.queries(64)
+    ix = _index(0, xb, "auto")
+    D, I = ix.search(xq, 80)
+    fo = oracle.IndexFlatIP(128)
+    fo.add(xb)
+    Df, If = fo.search(xq, 80)
+    np.testing.assert_allclose(D, Df, rtol=1e-4, atol=1e-4)
+    assert (I == If).mean() > 0.999
+    assert not oracle.check_against_truth(Df, If, xq, xb, 80, 0)
+
+
+@pytest.mark.parametrize("tier", ["fp32", "bf16"])
+def test_k_larger_than_ntotal_pads(tier):
+    xb, xq = data.corpus(50), data.queries(4)
+    ix = _index(0, xb, tier)
+    D, I = ix.search(xq, 80)
+    assert (I[:, 50:] == -1).all() and (D[:, 50:] == -oracle.FLT_MAX).all()
+    Dr, Ir = oracle.engine_spec(xq, xb, 80, 0)
+    _assert_bit_exact(D, I, Dr, Ir)
+
+
+def test_empty_index_and_empty_queries():
+    import proqa_b200 as pq
+    ix = pq.IndexFlatIP(128)
+    D, I = ix.search(data.queries(3), 5)
+    assert (I == -1).all() and (D == -oracle.FLT_MAX).all()
+    ix.add(data.corpus(100))
+    D, I = ix.search(np.zeros((0, 128), np.float32), 5)
+    assert D.shape == (0, 5) and I.shape == (0, 5)
+
+
+@pytest.mark.parametrize("tier", ["fp32", "bf16"])
+def test_exact_ties_resolve_to_lowest_ids(tier):
+    """Duplicated rows straddling the k-th place and the 5/10/20/50 recall cut-offs (eval_retrieval.py:59-64)."""
+    base = data.corpus(20000)
+    xq = data.queries(32)
+    xb = base.copy()
+    S = xq[:1] @ base.T
+    top = np.argsort(-S[0])[:60]
+    for j, t in enumerate(top[:30]):       # every one of the best 30 rows gets 3 exact copies at higher ids
+        xb[10000 + 3 * j: 10000 + 3 * j + 3] = base[t]
+    ix = _index(0, xb, tier)
+    D, I = ix.search(xq, 80)
+    Dr, Ir = oracle.engine_spec(xq, xb, 80, 0)
+    _assert_bit_exact(D, I, Dr, Ir)
+    # within a run of equal scores ids ascend
+    for q in range(len(xq)):
+        same = D[q, 1:] == D[q, :-1]
+        assert (I[q, 1:][same] > I[q, :-1][same]).all()
+
+
+@pytest.mark.parametrize("tier", ["fp32", "bf16"])
+def test_zero_queries_and_zero_rows(tier):
+    xb = data.corpus(30000)
+    xb[5:9] = 0
+    xq = data.queries(16)
+    xq[3] = 0
+    ix = _index(0, xb, tier)
+    D, I = ix.search(xq, 10)
+    Dr, Ir = oracle.engine_spec(xq, xb, 10, 0)
+    _assert_bit_exact(D, I, Dr, Ir)
+    assert I[3].tolist() == list(range(10))  # all-equal scores: FAISS keeps the first k ids
+
+
+@pytest.mark.parametrize("tier", ["fp32", "auto"])
+def test_nan_inf_rows_never_enter(tier):
+    xb = data.corpus(20000)
+    xb[7, 3] = np.nan
+    xb[11, 0] = np.inf
+    xb[13, 0] = -np.inf
+    xq = np.abs(data.queries(12))
+    ix = _index(0, xb, tier)
+    D, I = ix.search(xq, 20)
+    assert 7 not in I and 13 not in I
+    assert np.isfinite(D[:, 1:]).all()
+    Dr, Ir = oracle.engine_spec(xq, xb, 20, 0)
+    np.testing.assert_array_equal(I[:, 1:], Ir[:, 1:])
+
+
+def test_repeated_add_reset_and_id_order():
+    import proqa_b200 as pq
+    xb = data.corpus(9000)
+    ix = pq.IndexFlatIP(128)
+    ix.set_tier("fp32")
+    for a, b in [(0, 1), (1, 1000), (1000, 1001), (1001, 9000)]:
+        ix.add(xb[a:b])
+    assert ix.ntotal == 9000
+    xq = data.queries(7)
+    D, I = ix.search(xq, 33)
+    _assert_bit_exact(D, I, *oracle.engine_spec(xq, xb, 33, 0))
+    ix.reset()
+    assert ix.ntotal == 0
+    ix.add(xb[:500])
+    D, I = ix.search(xq, 33)
+    _assert_bit_exact(D, I, *oracle.engine_spec(xq, xb[:500], 33, 0))
+
+
+def test_kmeans_assignment_shape_l2_and_ip():
+    """group_paras.py:49-51 — many points against few centroids, k = 1, both metrics."""
+    cents = data.corpus(1000, seed=7)
+    pts = data.queries(20000, seed=8)
+    for metric in (0, 1):
+        ix = _index(metric, cents, "auto")
+        D, I = ix.search(pts, 1)
+        Dr, Ir = oracle.engine_spec(pts, cents, 1, metric)
+        _assert_bit_exact(D, I, Dr, Ir)
+
+
+def test_id_base_offsets_ids():
+    xb, xq = data.corpus(3000), data.queries(5)
+    ix = _index(0, xb, "fp32")
+    ix.set_id_base(10_000_000_000)
+    D, I = ix.search(xq, 8)
+    _, Ir = oracle.engine_spec(xq, xb, 8, 0, id_base=10_000_000_000)
+    np.testing.assert_array_equal(I, Ir)
+
+
+def test_large_k_trec_shape():
+    """trec_process.py:76 searches with k = 10000."""
+    xb, xq = data.corpus(30000), data.queries(2)
+    ix = _index(0, xb, "auto")
+    D, I = ix.search(xq, 10000)
+    _assert_bit_exact(D, I, *oracle.engine_spec(xq, xb, 10000, 0))
