@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py — exact top-k MIPS throughput on B200 (BASELINE.json metric) with roofline and CPU baseline.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm, N = 1
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # our arm, corpus row-sharded over N ranks
+    python bench.py --impl reference ...                      # the reference's CPU algorithm on host cores
+
+One "step" = one search of the whole query batch against the whole (resident) corpus.  Default workload is
+BASELINE.json configs[1] ("c2"): 3610 queries x 21M x 128 fp32 corpus, k = 100.  Prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c1": dict(nq=2032, rows=1_000_000, k=80, desc="eval_retrieval.py shape: 2032 queries x 1M x 128 fp32, k=80"),
+    "c2": dict(nq=3610, rows=21_000_000, k=100, desc="NQ-scale search: 3610 queries x 21M x 128 fp32 corpus, k=100"),
+    "c3": dict(nq=65536, rows=21_000_000, k=80, desc="large batch: 65536 queries x 21M x 128 fp32, k=80"),
+    "s0": dict(nq=16, rows=21_000_000, k=80, desc="small-batch sweep point: 16 queries x 21M x 128 fp32, k=80 (HBM-bound)"),
+}
+CHUNK = 1_000_000  # rows per generated chunk; chunk c is seeded with 1234 + c so the corpus does not depend on N
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p["bf16_tflops"]),
+                    bf16_tflops_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def host_queries(nq):
+    return np.random.default_rng(4321).standard_normal((nq, 128), dtype=np.float32)
+
+
+def host_corpus_sample(rows):
+    return np.random.default_rng(1234).standard_normal((rows, 128), dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the FAISS-1.6.3 restatement (oracle) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_search_time(xq, k, rows, reps=1):
+    from oracle import oracle
+    xb = host_corpus_sample(rows)
+    ix = oracle.IndexFlatIP(128)
+    ix.add(xb)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ix.search(xq, k)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def cpu_baseline(wl, budget_s=12.0):
+    """Bounded sample of the same workload: all queries, a prefix of the corpus; linear extrapolation in N."""
+    xq = host_queries(wl["nq"])
+    probe_rows = 20_000
+    t_probe = cpu_search_time(xq, wl["k"], probe_rows)
+    rows = int(min(wl["rows"], max(probe_rows, probe_rows * budget_s / max(t_probe, 1e-6))))
+    rows = min(rows, 2_000_000)
+    t = cpu_search_time(xq, wl["k"], rows)
+    full_t = t * wl["rows"] / rows
+    return {"value": wl["nq"] / full_t, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"all {wl['nq']} queries x first {rows} of {wl['rows']} rows in {t:.2f}s, extrapolated linearly in rows; "
+                      "FAISS-1.6.3 restatement (OpenBLAS sgemm 4096x1024 blocks + per-query heap), not FAISS"}
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    xq = host_queries(wl["nq"])
+    total = args.steps + args.warmup
+    per_step_budget = max(2.0, min(20.0, 150.0 / max(total, 1)))
+    probe_rows = 20_000
+    t_probe = cpu_search_time(xq, wl["k"], probe_rows)
+    rows = int(min(wl["rows"], 2_000_000, max(probe_rows, probe_rows * per_step_budget / max(t_probe, 1e-6))))
+    from oracle import oracle
+    ix = oracle.IndexFlatIP(128)
+    ix.add(host_corpus_sample(rows))
+    for _ in range(args.warmup):
+        ix.search(xq, wl["k"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ix.search(xq, wl["k"])
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    full_t = dt * wl["rows"] / rows
+    value = wl["nq"] / full_t
+    sample = (f"each step: all {wl['nq']} queries x first {rows} of {wl['rows']} rows ({dt:.2f}s), extrapolated linearly in rows; "
+              "FAISS-1.6.3 restatement (OpenBLAS sgemm + heap), not FAISS (faiss-cpu is not installable here)")
+    out = {"impl": "reference", "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_t * 1e3, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl),
+           "corpus_gbs": wl["rows"] * 512 / full_t / 1e9,
+           "cpu_baseline": {"value": value, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, wl):
+    return {"workload": wl["desc"], "name": args.workload, "nq": wl["nq"], "rows": wl["rows"], "d": 128, "k": wl["k"],
+            "l2_flush": "inputs larger than L2 (bf16 corpus copy %.1f GB per step)" % (wl["rows"] * 256 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_shard(index, lo, hi, dev, sharded=None, n_global=None):
+    """Generate rows [lo, hi) of the synthetic corpus on the device, chunk by chunk, and append them."""
+    import torch
+    first = True
+    c0, c1 = lo // CHUNK, (hi + CHUNK - 1) // CHUNK
+    for c in range(c0, c1):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + c)
+        rows = min(CHUNK, n_global - c * CHUNK)
+        x = torch.randn((rows, 128), generator=g, device=dev, dtype=torch.float32)
+        a, b = max(lo, c * CHUNK) - c * CHUNK, min(hi, c * CHUNK + rows) - c * CHUNK
+        part = x[a:b].contiguous()
+        torch.cuda.synchronize()
+        if first and sharded is not None:
+            sharded._local.set_id_base(lo)
+        first = False
+        index.add_device(part.data_ptr(), part.shape[0])
+        del x, part
+
+
+def truth_topk_fp64(xq_dev, lo, hi, n_global, k, dev):
+    """fp64 ground truth for a query slice over rows [lo, hi) — checker only (torch matmul in float64)."""
+    import torch
+    q = xq_dev.double()
+    best_d = torch.full((q.shape[0], k), -float("inf"), dtype=torch.float64, device=dev)
+    best_i = torch.full((q.shape[0], k), -1, dtype=torch.int64, device=dev)
+    for c in range(lo // CHUNK, (hi + CHUNK - 1) // CHUNK):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + c)
+        rows = min(CHUNK, n_global - c * CHUNK)
+        x = torch.randn((rows, 128), generator=g, device=dev, dtype=torch.float32)
+        a, b = max(lo, c * CHUNK) - c * CHUNK, min(hi, c * CHUNK + rows) - c * CHUNK
+        s = q @ x[a:b].double().T
+        d, i = torch.topk(s, min(k, s.shape[1]), dim=1)
+        i = i + (c * CHUNK + a)
+        cat_d, cat_i = torch.cat([best_d, d], 1), torch.cat([best_i, i], 1)
+        top = torch.topk(cat_d, k, dim=1)
+        best_d, best_i = top.values, torch.gather(cat_i, 1, top.indices)
+        del x, s
+    return best_d, best_i
+
+
+def parity_gate(D, I, Dt, It, rtol=1e-4):
+    """Scores within rtol of the fp64 truth position by position; ids equal except inside near-ties."""
+    import torch
+    D64 = D.double()
+    scale = torch.maximum(Dt.abs(), torch.full_like(Dt, 1e-3))
+    score_ok = bool(((D64 - Dt).abs() <= rtol * scale + 1e-6).all())
+    neq = I != It
+    frac_equal = 1.0 - float(neq.double().mean())
+    # where ids differ the two candidates must be a near-tie: their fp64 scores (same rank) agree within tolerance
+    tie_ok = bool((((D64 - Dt).abs() <= rtol * scale + 1e-6) | ~neq).all())
+    return score_ok and tie_ok and frac_equal > 0.999, frac_equal
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import proqa_b200 as pq
+    from proqa_b200 import _lib
+    from proqa_b200.sharded import ShardedIndexFlat, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; proqa_b200 has no CPU path (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    nq, N, k = wl["nq"], wl["rows"], wl["k"]
+    lo, hi = shard_bounds(N, world, rank)
+    sh = ShardedIndexFlat(128, pq.METRIC_INNER_PRODUCT, device=local_rank)
+    ix = sh.local
+    if args.tier:
+        ix.set_tier(args.tier)
+    t_build = time.perf_counter()
+    build_shard(ix, lo, hi, dev, sharded=sh, n_global=N)
+    sh._first_add, sh.ntotal = False, N
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+
+    stream = torch.cuda.current_stream()
+    ix.set_stream(stream.cuda_stream)
+
+    xq_host = torch.from_numpy(host_queries(nq)).pin_memory()
+    q = xq_host.to(dev)
+    D_loc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    I_loc = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    D_all = torch.empty((world, nq, k), dtype=torch.float32, device=dev) if world > 1 else None
+    I_all = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
+    D_out, I_out = torch.empty_like(D_loc), torch.empty_like(I_loc)
+    D_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    I_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+
+    def step_device():
+        sh.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
+        return ix.last_stats[5] + (1 if world > 1 else 0)
+
+    def step_e2e():
+        if world == 1:
+            rc = _lib.lib().pq_index_search(ix._h, nq, ctypes.c_void_p(xq_host.data_ptr()), k, ctypes.c_void_p(D_host.data_ptr()),
+                                           ctypes.c_void_p(I_host.data_ptr()))
+            _lib.check(rc, "search")
+        else:
+            if rank == 0:
+                q.copy_(xq_host, non_blocking=True)
+            dist.broadcast(q, 0)
+            sh.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
+            if rank == 0:
+                D_host.copy_(D_out, non_blocking=True)
+                I_host.copy_(I_out, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity gate: >= 256 queries against the fp64 ground truth (checker: torch float64) ---------
+    step_device()
+    torch.cuda.synchronize()
+    nchk = min(nq, 256)
+    Dt, It = truth_topk_fp64(q[:nchk], lo, hi, N, k, dev)
+    if world > 1:
+        Dt_all = torch.empty((world, nchk, k), dtype=torch.float64, device=dev)
+        It_all = torch.empty((world, nchk, k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(Dt_all, Dt.contiguous())
+        dist.all_gather_into_tensor(It_all, It.contiguous())
+        cat_d = Dt_all.permute(1, 0, 2).reshape(nchk, -1)
+        cat_i = It_all.permute(1, 0, 2).reshape(nchk, -1)
+        top = torch.topk(cat_d, k, dim=1)
+        Dt, It = top.values, torch.gather(cat_i, 1, top.indices)
+    parity_ok, frac_equal = parity_gate(D_out[:nchk], I_out[:nchk], Dt, It)
+
+    # ---- timed region: device-resident -------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    rerun_q = 0
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        launches += step_device()
+        rerun_q += ix.last_stats[1]
+    ev1.record(stream)
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) / 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt.item())
+
+    # ---- end to end: host buffers in, host buffers out ----------------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+
+    # ---- dominant-kernel time (CUDA events around the kernel on its launching stream) --------------
+    ix.set_profile(True)
+    kern_us = []
+    for _ in range(3):
+        step_device()
+        kern_us.append(ix.last_stats[7])
+    ix.set_profile(False)
+    st = ix.last_stats
+    kernel_s = float(np.mean(kern_us)) * 1e-6
+    peaks = load_peaks()
+    local_rows = hi - lo
+    tensor_path = st[3] > 0
+    if tensor_path:
+        flops = 2.0 * nq * local_rows * 128
+        long_run = t_dev > 1.0
+        peak = peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]
+        achieved = flops / kernel_s / 1e12 if kernel_s > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "pq_mma_filter_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": load_traffic("pq_mma_filter_kernel"),
+                    "peak_source": f"{peaks['source']} cuBLAS bf16 ({'sustained' if long_run else 'burst'})",
+                    "frac_of_burst": achieved / peaks["bf16_tflops"], "algorithmic": "256 flop per (query,row) score",
+                    "launches_per_step": int(st[3]), "kernel_ms_per_step": kernel_s * 1e3}
+    else:
+        nbytes = 512.0 * local_rows * max(1, st[2])
+        achieved = nbytes / kernel_s / 1e9 if kernel_s > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "pq_ffma_scan_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("pq_ffma_scan_kernel"),
+                    "peak_source": f"{peaks['source']} copy bandwidth", "algorithmic": "512 B of corpus per row per pass",
+                    "launches_per_step": int(st[2]), "kernel_ms_per_step": kernel_s * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline(wl) if (world == 1 and not args.no_cpu_baseline) else None
+    ms = t_dev / args.steps * 1e3
+    out = {
+        "metric": "queries_per_sec", "value": (nq * args.steps / t_dev) if parity_ok else None, "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16 filter + f32 rescoring" if tensor_path else "f32",
+        "data": "synthetic", "config": workload_config(args, wl),
+        "corpus_gbs": N * 512 * args.steps / t_dev / 1e9,
+        "e2e": {"value": nq * args.steps / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * 512, "d2h_bytes_per_step": nq * k * 12,
+                "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "parity": {"queries_checked": nchk, "ok": parity_ok, "ids_equal_frac": frac_equal, "against": "fp64 brute force (torch, checker only)",
+                   "fp32_rerun_queries_per_step": rerun_q / max(1, args.steps)},
+        "index_build_s": t_build,
+    }
+    if not parity_ok:
+        out["error"] = "parity gate failed: no speed reported"
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--nq", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--tier", default=None, choices=[None, "auto", "fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    for key in ("rows", "nq", "k"):
+        if getattr(args, key) is not None:
+            wl[key] = getattr(args, key)
+            wl["desc"] += f" [{key}={wl[key]} override]"
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -78,9 +78,17 @@ int pq_index_metric(const pq_index* idx);
 /* Row ids reported by search are local row + id_base (multi-GPU row shards: base of the shard). */
 int pq_index_set_id_base(pq_index* idx, int64_t id_base);
 int pq_index_set_tier(pq_index* idx, int tier);
+/* Run this index's device work on the caller's CUDA stream (cudaStream_t passed as void*; is_external=1), or
+ * back on the index's own stream (is_external=0).  With an external stream, *_device calls do not
+ * device-synchronise first: the caller's prior work on that stream is already ordered before ours. */
+int pq_index_set_stream(pq_index* idx, void* cuda_stream, int is_external);
+/* Time the dominant kernel of every search (fp32 scan / tensor-core filter) with CUDA events on the
+ * launching stream; the total lands in stats[7] (microseconds). */
+int pq_index_set_profile(pq_index* idx, int on);
 /* Counters of the last search: [0]=queries served by the tensor-core tier, [1]=queries re-run by the
  * fp32 scan after a failed certificate, [2]=fp32-scan launches, [3]=tensor-core filter launches,
- * [4]=select/merge/rescore launches, [5]=total kernel launches, [6]=device microseconds (CUDA events). */
+ * [4]=select/merge/rescore launches, [5]=total kernel launches, [6]=device microseconds (CUDA events),
+ * [7]=microseconds inside the dominant kernel (only with pq_index_set_profile). */
 int pq_index_last_stats(const pq_index* idx, int64_t* out, int n);
 
 /* Merge G per-shard result lists (each [nq,k], best-first, global ids) into one — the kernel run

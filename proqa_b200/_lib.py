@@ -34,6 +34,8 @@ SIGNATURES = {
     "pq_index_metric": (ctypes.c_int, [_vp]),
     "pq_index_set_id_base": (ctypes.c_int, [_vp, ctypes.c_int64]),
     "pq_index_set_tier": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "pq_index_set_stream": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
+    "pq_index_set_profile": (ctypes.c_int, [_vp, ctypes.c_int]),
     "pq_index_last_stats": (ctypes.c_int, [_vp, _i64p, ctypes.c_int]),
     "pq_merge_shard_results": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp,
                                               _vp, _vp]),

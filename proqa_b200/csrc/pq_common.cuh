@@ -198,15 +198,15 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-// Descending bitonic sort of n (power of two) keys in shared memory by the whole CTA.
+// Bitonic sort of n (power of two) keys in shared memory by the whole CTA; ascending or descending.
 template <int kThreads>
-__device__ __forceinline__ void block_sort_desc(uint64_t* a, int n) {
+__device__ __forceinline__ void block_sort(uint64_t* a, int n, bool ascending) {
     for (int size = 2; size <= n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = threadIdx.x; i < (n >> 1); i += kThreads) {
                 const int lo = 2 * i - (i & (stride - 1));
                 const int hi = lo + stride;
-                const bool desc = (lo & size) == 0;
+                const bool desc = ((lo & size) == 0) != ascending;
                 const uint64_t x = a[lo], y = a[hi];
                 if ((x < y) == desc) {
                     a[lo] = y;
@@ -217,7 +217,26 @@ __device__ __forceinline__ void block_sort_desc(uint64_t* a, int n) {
         }
     }
 }
-
+template <int kThreads>
+__device__ __forceinline__ void block_sort_desc(uint64_t* a, int n) {
+    block_sort<kThreads>(a, n, false);
+}
+// a[0..n) is bitonic (descending run followed by an ascending run): log2(n) steps leave it sorted descending.
+template <int kThreads>
+__device__ __forceinline__ void block_bitonic_merge_desc(uint64_t* a, int n) {
+    for (int stride = n >> 1; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < (n >> 1); i += kThreads) {
+            const int lo = 2 * i - (i & (stride - 1));
+            const int hi = lo + stride;
+            const uint64_t x = a[lo], y = a[hi];
+            if (x < y) {
+                a[lo] = y;
+                a[hi] = x;
+            }
+        }
+        __syncthreads();
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace pq

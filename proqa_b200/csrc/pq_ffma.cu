@@ -200,8 +200,8 @@ static int ffma_cap_for_k(int k) { return next_pow2(k + kFfmaTileRows) < 256 ? 2
 int ffma_max_queries_for_k(int k) {
     if (k < 1) return 0;
     const long long cap = ffma_cap_for_k(k);
-    const long long room = kSmemLimit - 2LL * kFfmaStageBytes - 256 - 1024;  // two stages minimum
-    long long q = room / (cap * 8);
+    long long q = (kSmemLimit - 2LL * kFfmaStageBytes - 256 - 1024) / (cap * 8);  // prefer a double-buffered ring
+    if (q < 1) q = (kSmemLimit - 1LL * kFfmaStageBytes - 256 - 1024) / (cap * 8); // huge k: single stage
     if (q > kFfmaMaxQ) q = kFfmaMaxQ;
     return (int)q;
 }
@@ -219,7 +219,8 @@ cudaError_t ffma_scan_launch(const FfmaLaunch& a, cudaStream_t stream) {
     p.cap = ffma_cap_for_k(a.k);
     p.metric = a.metric;
     const size_t buf_bytes = (size_t)a.nq * p.cap * 8 + 256;
-    p.n_stages = (3 * (size_t)kFfmaStageBytes + buf_bytes <= (size_t)kSmemLimit) ? 3 : 2;
+    p.n_stages = 3;
+    while (p.n_stages > 1 && (size_t)p.n_stages * kFfmaStageBytes + buf_bytes > (size_t)kSmemLimit) --p.n_stages;
     const size_t smem = (size_t)p.n_stages * kFfmaStageBytes + buf_bytes;
     if (a.nq < 1 || a.nq > kFfmaMaxQ || smem > (size_t)kSmemLimit) return cudaErrorInvalidValue;
 

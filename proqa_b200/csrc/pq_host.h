@@ -64,6 +64,39 @@ struct pq_index {
 
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+    // optional per-kernel timing of the dominant kernel (fp32 scan / tensor-core filter): event pairs on the stream
+    bool profile = false;
+    bool stream_is_external = false;
+    cudaStream_t own_stream = nullptr;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;
+    int prof_begin() {
+        if (!profile) return 0;
+        if (prof_used + 2 > prof_events.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) return -1;
+                prof_events.push_back(e);
+            }
+        }
+        return cudaEventRecord(prof_events[prof_used], stream) == cudaSuccess ? 0 : -1;
+    }
+    void prof_end() {
+        if (!profile) return;
+        cudaEventRecord(prof_events[prof_used + 1], stream);
+        prof_used += 2;
+    }
+    // after the stream drained: total microseconds between the recorded pairs
+    int64_t prof_collect() {
+        double us = 0.0;
+        for (size_t i = 0; i + 1 < prof_used; i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, prof_events[i], prof_events[i + 1]) == cudaSuccess) us += ms * 1000.0;
+        }
+        prof_used = 0;
+        return (int64_t)(us + 0.5);
+    }
+
     void release_all() {
         pq::DevBuf* all[] = {&rows_f32, &rows_bf16, &norms,    &scalars,  &ws_q,     &ws_D,      &ws_I,      &ws_qnorm, &ws_qbf16,
                              &ws_qbad,  &ws_scan_keys, &ws_gthr, &ws_rr_idx, &ws_rr_q, &ws_rr_qn, &ws_rr_D,   &ws_rr_I};

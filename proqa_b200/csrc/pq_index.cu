@@ -138,7 +138,8 @@ static int index_init_device(pq_index* ix) {
     cudaDeviceProp prop;
     PQ_CUDA(cudaGetDeviceProperties(&prop, dev));
     ix->n_sms = prop.multiProcessorCount;
-    PQ_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    PQ_CUDA(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+    if (!ix->stream_is_external) ix->stream = ix->own_stream;
     PQ_CUDA(cudaEventCreate(&ix->ev0));
     PQ_CUDA(cudaEventCreate(&ix->ev1));
     rc = ix->scalars.ensure(256);
@@ -234,7 +235,9 @@ int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norm
         f.nq = nqb;
         f.k = k;
         f.metric = ix->metric;
+        ix->prof_begin();
         PQ_CUDA(ffma_scan_launch(f, ix->stream));
+        ix->prof_end();
         MergeLaunch m;
         memset(&m, 0, sizeof(m));
         m.keys = (const uint64_t*)ix->ws_scan_keys.p;
@@ -354,6 +357,7 @@ static int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t
     float ms = 0.f;
     PQ_CUDA(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
     ix->stats[6] = (int64_t)(ms * 1000.f);
+    ix->stats[7] = ix->prof_collect();
     return PQ_OK;
 }
 
@@ -404,7 +408,8 @@ void pq_index_free(pq_index* ix) {
         ix->release_all();
         cudaEventDestroy(ix->ev0);
         cudaEventDestroy(ix->ev1);
-        cudaStreamDestroy(ix->stream);
+        for (cudaEvent_t e : ix->prof_events) cudaEventDestroy(e);
+        cudaStreamDestroy(ix->own_stream);
     }
     delete ix;
 }
@@ -441,8 +446,9 @@ int pq_index_search_device(pq_index* ix, int64_t nq, const float* xq_dev, int64_
     rc = index_init_device(ix);
     if (rc) return rc;
     PQ_CUDA(cudaSetDevice(ix->device));
-    // The caller's tensors were produced on its own stream(s); order after all prior device work.
-    PQ_CUDA(cudaDeviceSynchronize());
+    // The caller's tensors were produced on its own stream(s): unless we were given that very stream
+    // (pq_index_set_stream), order after all prior device work.
+    if (!ix->stream_is_external) PQ_CUDA(cudaDeviceSynchronize());
     return search_device_impl(ix, nq, xq_dev, k, D_dev, (long long*)I_dev);
 }
 
@@ -473,6 +479,22 @@ int pq_index_set_tier(pq_index* ix, int tier) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
     if (tier < PQ_TIER_AUTO || tier > PQ_TIER_BF16) return set_error(PQ_ERR_INVALID, "unknown tier %d", tier);
     ix->tier = tier;
+    return PQ_OK;
+}
+int pq_index_set_stream(pq_index* ix, void* cuda_stream, int is_external) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (ix->device_ready) {
+        PQ_CUDA(cudaSetDevice(ix->device));
+        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    }
+    ix->stream_is_external = is_external != 0;
+    ix->stream = is_external ? (cudaStream_t)cuda_stream : ix->own_stream;
+    return PQ_OK;
+}
+int pq_index_set_profile(pq_index* ix, int on) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    ix->profile = on != 0;
     return PQ_OK;
 }
 int pq_index_last_stats(const pq_index* ix, int64_t* out, int n) {

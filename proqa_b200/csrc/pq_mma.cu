@@ -71,6 +71,21 @@ struct MmaParams {
     int k1_adapt;
 };
 
+// Rare path, deliberately out of line: the epilogue's hot loop must stay small enough for the
+// instruction cache (an earlier fully inlined version spent most of its time in "no instruction" stalls).
+__device__ __noinline__ uint32_t mma_insert_group4(float a, float b, float c, float d, float th, uint32_t row, uint32_t row_end,
+                                                   uint64_t* slab, uint32_t cnt, uint32_t cap) {
+    const float v[4] = {a, b, c, d};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (v[i] >= th && row + i < row_end) {
+            if (cnt < cap) slab[cnt] = make_key(v[i], row + i);
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
 template <int M_TILES>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, const MmaParams p) {
@@ -190,7 +205,9 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 slab[mi] = p.cand_keys + (q * p.n_sub + sub) * (size_t)p.cap;
             }
         }
+        const uint32_t row_end32 = (uint32_t)p.row_end;
         int it = 0;
+#pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
             const long long tile_row = row0 + (long long)t * kBN + half * 64;
 #pragma unroll
@@ -212,24 +229,23 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const long long base_row = tile_row + c * 32;
-                        if (base_row + 32 > p.row_end) {  // ragged last tile: TMA zero-filled or next-epoch rows
+                        const uint32_t base_row = (uint32_t)(tile_row + c * 32);
+                        // Max tree over the 32 columns, keeping the 8 group-of-4 maxima: the rare survivor is
+                        // then located by 8 cheap group tests.  Rows past row_end (TMA zero fill in the last
+                        // tile) score 0 and are rejected inside mma_insert_group4.
+                        float g4[8];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (base_row + i >= p.row_end) v[c][i] = -INFINITY;
-                        }
-                        float mx = v[c][0];
-#pragma unroll
-                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[c][i]);
+                        for (int g = 0; g < 8; ++g)
+                            g4[g] = fmaxf(fmaxf(v[c][4 * g], v[c][4 * g + 1]), fmaxf(v[c][4 * g + 2], v[c][4 * g + 3]));
+                        const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
                         const float th = thr[mi];
-                        if (p.k1_adapt) thr[mi] = fmaxf(th, mx - two_e[mi]);
-                        if (__any_sync(0xffffffffu, mx >= th)) {
+                        if (p.k1_adapt && base_row + 32 <= row_end32) thr[mi] = fmaxf(th, mx - two_e[mi]);
+                        if (mx >= th) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                if (v[c][i] >= th) {
-                                    if (cnt[mi] < (uint32_t)p.cap) slab[mi][cnt[mi]] = make_key(v[c][i], (uint32_t)(base_row + i));
-                                    ++cnt[mi];
-                                }
+                            for (int g = 0; g < 8; ++g) {
+                                if (g4[g] >= th)
+                                    cnt[mi] = mma_insert_group4(v[c][4 * g], v[c][4 * g + 1], v[c][4 * g + 2], v[c][4 * g + 3], th,
+                                                                base_row + 4 * g, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
                             }
                         }
                     }
@@ -281,65 +297,85 @@ struct EpochSelParams {
     QState st;
     const uint64_t* cand_keys;
     const uint32_t* cand_cnt;
-    int n_sub, cap, kp, k, work;
+    int n_sub, cap, kp, k, lmax;  // lmax: power of two >= max(kp, cap); shared work array holds 2*lmax keys
 };
 
 // One CTA per query: carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
+// The carry list is kept sorted, so only the new candidates are sorted (ascending) and one bitonic
+// merge of [carry desc | new asc] finishes the job: ~10x less work than re-sorting everything.
 __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
-    __shared__ int s_fill;
+    __shared__ int s_fill, s_total, s_ovf, s_next, s_L;
     __shared__ float s_drop;
-    __shared__ int s_ovf;
     const int q = blockIdx.x;
     const int t = threadIdx.x;
     uint64_t* carry = p.st.carry + (size_t)q * p.kp;
-    if (t == 0) {
-        s_fill = 0;
-        s_drop = -INFINITY;
-        s_ovf = 0;
-    }
-    __syncthreads();
-    for (int i = t; i < p.kp; i += 256) {
-        const uint64_t key = carry[i];
-        if (key != 0ull) work[atomicAdd(&s_fill, 1)] = key;
-    }
-    __syncthreads();
-    const int round = p.work - p.kp;
     const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
     const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
-    const int total = p.n_sub * p.cap;
-    for (int r0 = 0; r0 < total || r0 == 0; r0 += round) {
-        const int r1 = min(r0 + round, total);
-        for (int idx = r0 + t; idx < r1; idx += 256) {
+    if (t == 0) {
+        s_fill = 0;
+        s_total = 0;
+        s_ovf = 0;
+        s_drop = -INFINITY;
+    }
+    __syncthreads();
+    int local = 0;
+    for (int s = t; s < p.n_sub; s += 256) {
+        const uint32_t c = cnts[s];
+        if (c > (uint32_t)p.cap) s_ovf = 1;
+        local += (int)min(c, (uint32_t)p.cap);
+    }
+    if (local) atomicAdd(&s_total, local);
+    __syncthreads();
+    if (t == 0) {
+        int L = p.kp;
+        while (L < s_total && L < p.lmax) L <<= 1;
+        s_L = L;
+    }
+    __syncthreads();
+    const int L = s_L;
+    for (int i = t; i < L; i += 256) work[i] = (i < p.kp) ? carry[i] : 0ull;
+    int s0 = 0;
+    while (s0 < p.n_sub) {
+        if (t == 0) {  // largest run of slabs whose entries fit one chunk of L
+            int s1 = s0, acc = 0;
+            while (s1 < p.n_sub) {
+                const int c = (int)min(cnts[s1], (uint32_t)p.cap);
+                if (acc + c > L) break;
+                acc += c;
+                ++s1;
+            }
+            s_next = s1;
+            s_fill = 0;
+        }
+        __syncthreads();
+        const int s1 = s_next;
+        for (int idx = s0 * p.cap + t; idx < s1 * p.cap; idx += 256) {
             const int sub = idx / p.cap, pos = idx - sub * p.cap;
-            const uint32_t c = cnts[sub];
-            if (pos == 0 && c > (uint32_t)p.cap) s_ovf = 1;
-            if ((uint32_t)pos < c) work[atomicAdd(&s_fill, 1)] = keys[idx];
+            if ((uint32_t)pos < cnts[sub]) work[L + atomicAdd(&s_fill, 1)] = keys[idx];
         }
         __syncthreads();
         const int fill = s_fill;
-        const bool last = (r1 >= total);
-        if (last || fill + round > p.work) {
-            for (int i = fill + t; i < p.work; i += 256) work[i] = 0ull;
+        if (fill > 0) {
+            for (int i = fill + t; i < L; i += 256) work[L + i] = 0ull;
             __syncthreads();
-            block_sort_desc<256>(work, p.work);
-            if (t == 0) {
-                if (fill > p.kp) s_drop = fmaxf(s_drop, key_score(work[p.kp]));
-                s_fill = min(fill, p.kp);
-            }
+            block_sort<256>(work + L, L, /*ascending=*/true);
+            block_bitonic_merge_desc<256>(work, 2 * L);
+            if (t == 0 && work[p.kp] != 0ull) s_drop = fmaxf(s_drop, key_score(work[p.kp]));
+            __syncthreads();
+            for (int i = p.kp + t; i < L; i += 256) work[i] = 0ull;  // truncate the carry back to K'
             __syncthreads();
         }
-        if (last) break;
+        s0 = s1;
     }
+    __syncthreads();
     for (int i = t; i < p.kp; i += 256) carry[i] = work[i];
     if (t == 0) {
         if (s_drop > -INFINITY) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], s_drop);
         if (s_ovf) p.st.overflow[q] = 1u;
-        if (s_fill >= p.k) {
-            const float ak = key_score(work[p.k - 1]);
-            p.st.thr[q] = fmaxf(p.st.thr[q], ak - p.st.two_e[q]);
-        }
+        const uint64_t kth = work[p.k - 1];
+        if (kth != 0ull) p.st.thr[q] = fmaxf(p.st.thr[q], key_score(kth) - p.st.two_e[q]);
     }
 }
 
@@ -571,9 +607,11 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.k1_adapt = k1 ? 1 : 0;
             const dim3 grid((unsigned)n_groups, (unsigned)ep.n_slices);
             cudaError_t e;
+            ix->prof_begin();
             if (M == 1) e = launch_filter<1>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
             else if (M == 2) e = launch_filter<2>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
             else e = launch_filter<3>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
+            ix->prof_end();
             PQ_CUDA(e);
 
             EpochSelParams sp;
@@ -584,8 +622,8 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.cap = ep.cap;
             sp.kp = kp;
             sp.k = k;
-            sp.work = std::max(2048, next_pow2i(kp + 1024));
-            const size_t smem = (size_t)sp.work * 8;
+            sp.lmax = std::max(std::max(kp, next_pow2i(ep.cap)), 1024);
+            const size_t smem = (size_t)sp.lmax * 2 * 8;
             PQ_CUDA(cudaFuncSetAttribute(pq_epoch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
             PQ_CUDA(cudaGetLastError());

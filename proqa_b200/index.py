@@ -29,7 +29,7 @@ _LAST_STATS = [0] * 8
 def last_search_stats():
     """Counters of the most recent search in this process (see pq_index_last_stats in include/proqa_b200.h)."""
     keys = ["tc_queries", "fp32_rerun_queries", "fp32_scan_launches", "tc_filter_launches", "select_launches", "kernel_launches",
-            "device_us"]
+            "device_us", "dominant_kernel_us"]
     return dict(zip(keys, _LAST_STATS))
 
 
@@ -101,6 +101,17 @@ class IndexFlat:
         """'auto' | 'fp32' | 'bf16'  (see enum pq_tier)."""
         t = {"auto": _lib.TIER_AUTO, "fp32": _lib.TIER_FP32, "bf16": _lib.TIER_BF16}[tier] if isinstance(tier, str) else int(tier)
         _lib.check(_lib.lib().pq_index_set_tier(self._h, t), "set_tier")
+
+    def set_stream(self, cuda_stream):
+        """Run on the caller's CUDA stream (an int handle, e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
+        if cuda_stream is None:
+            _lib.check(_lib.lib().pq_index_set_stream(self._h, None, 0), "set_stream")
+        else:
+            _lib.check(_lib.lib().pq_index_set_stream(self._h, ctypes.c_void_p(int(cuda_stream)), 1), "set_stream")
+
+    def set_profile(self, on=True):
+        """Time the dominant kernel with CUDA events on the launching stream (last_stats[7], microseconds)."""
+        _lib.check(_lib.lib().pq_index_set_profile(self._h, 1 if on else 0), "set_profile")
 
     def _pull_stats(self):
         buf = (ctypes.c_int64 * 8)()
