@@ -102,8 +102,9 @@ class ShardedIndexFlat:
             D_out.copy_(D_local)
             I_out.copy_(I_local)
             return
-        self._dist.all_gather_into_tensor(D_all, D_local, group=self.group)
-        self._dist.all_gather_into_tensor(I_all, I_local, group=self.group)
+        # rank-major concatenation along dim 0: [G*nq, k] is the layout every backend accepts for the output
+        self._dist.all_gather_into_tensor(D_all.view(self.world * nq, k), D_local, group=self.group)
+        self._dist.all_gather_into_tensor(I_all.view(self.world * nq, k), I_local, group=self.group)
         self._merge_device(D_all, I_all, nq, k, D_out, I_out)
 
     def gather_merge(self, Dl, Il, k):
@@ -111,8 +112,8 @@ class ShardedIndexFlat:
         nq = Dl.shape[0]
         D_all = torch.empty((self.world,) + tuple(Dl.shape), dtype=Dl.dtype, device=Dl.device)
         I_all = torch.empty((self.world,) + tuple(Il.shape), dtype=Il.dtype, device=Il.device)
-        self._dist.all_gather_into_tensor(D_all, Dl.contiguous(), group=self.group)
-        self._dist.all_gather_into_tensor(I_all, Il.contiguous(), group=self.group)
+        self._dist.all_gather_into_tensor(D_all.view(self.world * nq, k), Dl.contiguous(), group=self.group)
+        self._dist.all_gather_into_tensor(I_all.view(self.world * nq, k), Il.contiguous(), group=self.group)
         if self._merge_fn is not None:
             return self._merge_fn(D_all, I_all, k, self.metric_type)
         D_out, I_out = torch.empty_like(Dl), torch.empty_like(Il)

@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors.  Run HERE (build container; needs /root/reference), never on the GPU box.
+
+    python tests/golden/make_fixtures.py
+
+1. eval_fixture.npz — the reference's own script /root/reference/retrieval/eval_retrieval.py is run UNMODIFIED
+   (as a subprocess, cwd = a scratch tree that has ../pretrained_models/idx_id.json, exactly as the script expects)
+   on synthetic inputs with ``import faiss`` resolved to the FAISS-1.6.3 restatement (tests/golden/_oracle_faiss).
+   Stored: the inputs (float16: exactly what get_embed.py --fp16 would have written), the I the script obtained, the
+   recall lines it printed, and — from the reference's own para_has_answer/SimpleTokenizer/DocDB — the
+   [question, paragraph] "has answer" bit matrix, so the GPU box can re-derive the recall lines from its own I with
+   pure integer work and no reference code.
+2. known_answers.json — hand-checkable exact cases (small integers: every product and sum is exact in fp32, so any
+   correct implementation, any accumulation order, must return these bits).
+"""
+import json
+import os
+import sqlite3
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/retrieval"
+sys.path.insert(0, ROOT)
+
+N, NQ, K, D = 2000, 24, 80, 128
+MIN_GAP = 6e-5  # absolute; scores are O(20), fp32 dot-product error is O(2e-6): 30x head-room
+WORDS = ["alder", "birch", "cedar", "dogwood", "elm", "fir", "ginkgo", "hazel", "ironwood", "juniper", "kapok", "larch",
+         "maple", "nutmeg", "oak", "pine", "quince", "rowan", "spruce", "teak", "upas", "viburnum", "willow", "yew", "zelkova"]
+
+
+def make_inputs(seed):
+    rng = np.random.default_rng(seed)
+    xb = rng.standard_normal((N, D)).astype(np.float16)
+    xq = rng.standard_normal((NQ, D)).astype(np.float16)
+    # plant structure: query i is close to rows planted[i]; so recall is neither 0 nor 1 everywhere
+    for i in range(NQ):
+        for j in rng.choice(N, size=3, replace=False):
+            xb[j] = (0.6 * xq[i].astype(np.float32) + 0.8 * xb[j].astype(np.float32)).astype(np.float16)
+    return xb, xq
+
+
+def unambiguous(xb, xq):
+    """Every rank boundary of the fp64 top-(K+1) is much wider than fp32 rounding noise, so I does not depend on the
+    accumulation order of whoever computes the fp32 scores (OpenBLAS here, the sequential chain on the GPU): the
+    committed I is THE answer, with no near-tie to argue about."""
+    S = xq.astype(np.float64) @ xb.astype(np.float64).T
+    top = -np.sort(-S, axis=1)[:, :K + 1]
+    gap = top[:, :-1] - top[:, 1:]
+    return bool((gap > MIN_GAP).all())
+
+
+def main():
+    seed = 20240
+    while True:
+        xb, xq = make_inputs(seed)
+        if unambiguous(xb, xq):
+            break
+        seed += 1
+    rng = np.random.default_rng(seed + 7)
+    tmp = tempfile.mkdtemp(prefix="proqa_golden_")
+    os.makedirs(os.path.join(tmp, "retrieval"))
+    os.makedirs(os.path.join(tmp, "pretrained_models"))
+    # paragraphs: random word salads; the answer string of question i is planted in a few paragraphs
+    answers = [[f"{WORDS[i % len(WORDS)]} {WORDS[(7 * i + 3) % len(WORDS)]} {i}"] for i in range(NQ)]
+    texts = []
+    for j in range(N):
+        texts.append(" ".join(rng.choice(WORDS, size=12)) + f" . Paragraph {j} .")
+    S = xq.astype(np.float64) @ xb.astype(np.float64).T
+    order = np.argsort(-S, axis=1)
+    for i in range(NQ):
+        r = int(rng.integers(0, 140))  # answer sits at true rank r (beyond K for some questions: those are misses)
+        j = int(order[i, r])
+        texts[j] += f" The Answer Is {answers[i][0].upper()} , indeed ."
+    ids = [f"doc_{j:05d}" for j in range(N)]
+    db = os.path.join(tmp, "paras.db")
+    con = sqlite3.connect(db)
+    con.execute("CREATE TABLE documents (id PRIMARY KEY, text)")
+    con.executemany("INSERT INTO documents VALUES (?,?)", list(zip(ids, texts)))
+    con.commit()
+    con.close()
+    # gen_index_id_map.py:3-9 semantics: {line number: sample['id']} dumped as JSON (int keys become strings)
+    json.dump({j: ids[j] for j in range(N)}, open(os.path.join(tmp, "pretrained_models", "idx_id.json"), "w"))
+    qa = os.path.join(tmp, "qa.jsonl")
+    with open(qa, "w") as f:
+        for i in range(NQ):
+            f.write(json.dumps({"question": f"which tree number {i} ?", "answer": answers[i]}) + "\n")
+    np.save(os.path.join(tmp, "para_embed.npy"), xb)
+    np.save(os.path.join(tmp, "query_embed.npy"), xq)
+
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(HERE, "_oracle_faiss") + os.pathsep + env.get("PYTHONPATH", "")
+    env["PROQA_GOLDEN_DUMP"] = os.path.join(tmp, "dump.npz")
+    out = subprocess.run([sys.executable, os.path.join(REF, "eval_retrieval.py"), qa, os.path.join(tmp, "para_embed.npy"),
+                          os.path.join(tmp, "query_embed.npy"), db, "--topk", str(K), "--num-workers", "2"],
+                         cwd=os.path.join(tmp, "retrieval"), env=env, capture_output=True, text=True, check=True)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("Top ")]
+    assert len(lines) == 5, out.stdout + out.stderr
+    dump = np.load(os.path.join(tmp, "dump.npz"))
+
+    # has-answer matrix with the reference's own scorer (eval_retrieval.py:27-45)
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(HERE, "_oracle_faiss"))
+    import importlib
+    er = importlib.import_module("eval_retrieval")
+    er.init(db)
+    has = np.zeros((NQ, N), dtype=bool)
+    for i in range(NQ):
+        for j in range(N):
+            if answers[i][0].split()[0] in texts[j].lower():  # cheap prefilter; the reference decides
+                has[i, j] = er.para_has_answer(answers[i], texts[j])
+    np.savez_compressed(os.path.join(HERE, "eval_fixture.npz"), xb=xb, xq=xq, I=dump["I"].astype(np.int32),
+                        D=dump["D"].astype(np.float32), has_answer=np.packbits(has, axis=1), topk=np.int32(K),
+                        recall_lines=np.array(lines))
+    print("\n".join(lines))
+    print("eval_fixture.npz written; seed", seed, "bytes", os.path.getsize(os.path.join(HERE, "eval_fixture.npz")))
+
+    # ---- hand-checkable known answers ---------------------------------------------------------------------------
+    cases = []
+    # case 1: corpus row j = (j+1) * e_{j % 128}; query = e_0 + 2 e_1.  <q, x_j> = (j+1) if j%128==0, 2(j+1) if j%128==1.
+    n = 300
+    xb1 = np.zeros((n, D), np.float32)
+    for j in range(n):
+        xb1[j, j % D] = j + 1
+    q1 = np.zeros((1, D), np.float32)
+    q1[0, 0], q1[0, 1] = 1, 2
+    #   non-zero scores: j=0:1, 128:129, 256:257 ; j=1:4, 129:260, 257:516 ; all others 0 (ties -> lowest ids)
+    #   (k = 6 stops before the zero-score ties: which tied ids FAISS keeps there depends on its heap's internal order)
+    cases.append(dict(name="axis_aligned_ip", metric=0, k=6, xb_rule="row j = (j+1)*e_(j%128), n=300", n=n,
+                      xq=q1.tolist(), I=[[257, 129, 256, 128, 1, 0]], D=[[516, 260, 257, 129, 4, 1]]))
+    # case 2: same corpus, L2: |q|^2 = 5, |x_j|^2 = (j+1)^2 ; d = 5 + (j+1)^2 - 2<q,x_j>
+    #   j=0: 5+1-2=4 ; j=1: 5+4-8=1 ; j=2: 5+9=14 ; j=3: 5+16=21 ; j=4: 30 ...
+    cases.append(dict(name="axis_aligned_l2", metric=1, k=5, xb_rule="row j = (j+1)*e_(j%128), n=300", n=n,
+                      xq=q1.tolist(), I=[[1, 0, 2, 3, 4]], D=[[1, 4, 14, 21, 30]]))
+    # case 3: k > ntotal padding (IndexFlat::search fills the heap with -FLT_MAX / -1)
+    cases.append(dict(name="k_gt_ntotal", metric=0, k=6, xb_rule="row j = (j+1)*e_(j%128), n=3", n=3,
+                      xq=q1.tolist(), I=[[1, 0, 2, -1, -1, -1]],
+                      D=[[4, 1, 0, -3.4028234663852886e38, -3.4028234663852886e38, -3.4028234663852886e38]]))
+    # case 4: all-equal scores: strict '>' replacement while scanning ids upwards keeps the first k ids
+    cases.append(dict(name="all_ties_keep_lowest_ids", metric=0, k=4, xb_rule="every row = e_5, n=1000", n=1000,
+                      xq=np.eye(1, D, 5, dtype=np.float32).tolist(), I_set=[[0, 1, 2, 3]], D=[[1, 1, 1, 1]]))
+    json.dump(cases, open(os.path.join(HERE, "known_answers.json"), "w"), indent=1)
+    print("known_answers.json written")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/proqa_b200.h declares.
+
+No compute call is made here (there is no device in the build container); what a call without a device must do —
+fail loudly with PQ_ERR_NO_DEVICE, never fall back — is checked too.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "proqa_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from proqa_b200 import _lib
+    L = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/proqa_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in proqa_b200/_lib.py"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_version_and_no_cuda_at_load():
+    import proqa_b200 as pq
+    assert "sm_100a" in pq.version()
+    # creating an index must not touch CUDA (eval_retrieval.py forks after import / before index use)
+    ix = pq.IndexFlatIP(128)
+    assert ix.ntotal == 0 and ix.d == 128 and ix.is_trained
+    del ix
+
+
+def test_bad_arguments_raise_like_faiss():
+    import proqa_b200 as pq
+    with pytest.raises(ValueError):
+        pq.IndexFlatIP(64)  # engine is built for d = 128 (eval_retrieval.py:98)
+    ix = pq.IndexFlatIP(128)
+    with pytest.raises(AssertionError):
+        ix.add(np.zeros((3, 64), np.float32))
+    with pytest.raises(AssertionError):
+        ix.search(np.zeros((3, 64), np.float32), 5)
+    with pytest.raises(AssertionError):
+        ix.search(np.zeros((3, 128), np.float32), 0)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    import proqa_b200 as pq
+    ix = pq.IndexFlatIP(128)
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA device|fallback"):
+        ix.add(np.zeros((4, 128), np.float32))
+    with pytest.raises(RuntimeError):
+        ix.search(np.zeros((1, 128), np.float32), 1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "proqa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+                assert "liboracle" not in src, f"{f} links the oracle"

@@ -190,3 +190,34 @@ def test_large_k_trec_shape():
     ix = _index(0, xb, "auto")
     D, I = ix.search(xq, 10000)
     _assert_bit_exact(D, I, *oracle.engine_spec(xq, xb, 10000, 0))
+
+
+# ---- golden vectors (tests/golden/, generated from the reference's own eval_retrieval.py) ------------------------
+@pytest.mark.parametrize("tier", ["fp32", "bf16", "auto"])
+def test_eval_fixture_ids_and_recall_lines(tier):
+    """eval_retrieval.py:98-123 on the committed fixture: same I as the reference script obtained, and therefore the
+    same five 'Top k Recall' lines, byte for byte."""
+    from tests.golden_util import load_eval_fixture, recall_lines
+    fx = load_eval_fixture()
+    ix = _index(0, fx["xb"], tier)
+    D, I = ix.search(fx["xq"], fx["topk"])
+    np.testing.assert_array_equal(I, fx["I"])
+    np.testing.assert_allclose(D, fx["D"], rtol=1e-4, atol=0)
+    assert recall_lines(I, fx) == fx["recall_lines"]
+
+
+@pytest.mark.parametrize("tier", ["fp32", "bf16"])
+def test_known_answers_on_engine(tier):
+    import json
+    import os
+    from tests.test_oracle import corpus_from_rule
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "known_answers.json")))
+    for case in cases:
+        if tier == "bf16" and case["metric"] == 1:
+            continue  # L2 is served by the fp32 scan in every tier
+        xb = corpus_from_rule(case)
+        ix = _index(case["metric"], xb, tier)
+        D, I = ix.search(np.asarray(case["xq"], np.float32), case["k"])
+        np.testing.assert_array_equal(D, np.asarray(case["D"], np.float32), err_msg=case["name"])
+        want = case.get("I", case.get("I_set"))
+        np.testing.assert_array_equal(I, np.asarray(want, np.int64), err_msg=case["name"])  # engine order: id ascending in ties
