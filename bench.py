@@ -223,7 +223,8 @@ def parity_gate(D, I, Dt, It, rtol=1e-4):
     frac_equal = 1.0 - float(neq.double().mean())
     # where ids differ the two candidates must be a near-tie: their fp64 scores (same rank) agree within tolerance
     tie_ok = bool((((D64 - Dt).abs() <= rtol * scale + 1e-6) | ~neq).all())
-    return score_ok and tie_ok and frac_equal > 0.999, frac_equal
+    # an id swap inside a near-tie is allowed by the north star; frac_equal only guards against wholesale disagreement
+    return score_ok and tie_ok and frac_equal > 0.98, frac_equal
 
 
 def run_ours(args, wl):

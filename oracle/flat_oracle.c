@@ -21,8 +21,8 @@
  *              a k-th place tie); results best-first; unfilled slots id=-1, D=-FLT_MAX (IP) / +FLT_MAX
  *              (L2); L2 reported as squared distance, BLAS path  |x|^2+|y|^2-2<x,y>  clamped at 0
  *              (nq >= 20) or the direct sum of squared differences (nq < 20).
- *   engine_* : the GPU engine's *defined* score: the sequential chain
- *              acc = fmaf(row[i], q[i], acc), i = 0..d-1, ordered by (score desc, id asc).  The CUDA
+ *   engine_* : the GPU engine's *defined* score: eight fmaf chains of 16 dims each,
+ *              tree-combined (engine_chain_dot below), ordered by (score desc, id asc).  The CUDA
  *              kernels must reproduce these bits exactly.
  */
 #include <float.h>
@@ -203,10 +203,18 @@ static inline float ordered_f32(uint32_t o) {
     memcpy(&f, &u, 4);
     return f;
 }
+/* The engine's defined score for d = 128 (proqa_b200/csrc/pq_common.cuh: engine_dot): eight fmaf chains of 16
+ * consecutive dims each, combined as ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)).  For other d (tests only) the same rule
+ * with chains of ceil(d/8) dims.  Compiled with -ffp-contract=off: the additions below are never fused. */
 float engine_chain_dot(const float* row, const float* q, int d) {
-    float acc = 0.f;
-    for (int i = 0; i < d; ++i) acc = fmaf(row[i], q[i], acc);
-    return acc;
+    float p[8];
+    const int len = (d + 7) / 8;
+    for (int j = 0; j < 8; ++j) {
+        float acc = 0.f;
+        for (int i = j * len; i < (j + 1) * len && i < d; ++i) acc = fmaf(row[i], q[i], acc);
+        p[j] = acc;
+    }
+    return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
 }
 static int cmp_u64_desc(const void* a, const void* b) {
     const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;

@@ -20,8 +20,8 @@ Three oracles, from most to least authoritative:
   nq >= 20 (numpy/OpenBLAS here), a direct dot loop below 20, per-query binary heap fed in ascending id
   with strict-improvement replacement, best-first reorder, ``-1`` / ``∓FLT_MAX`` padding, L2 as
   ``|x|^2+|y|^2-2<x,y>`` clamped at 0.  This is "what FAISS would print" and the CPU baseline that is timed.
-* :func:`engine_spec`     — the GPU engine's *defined* result: score = sequential fmaf
-  chain, order = (score desc, id asc).  The CUDA path must match it bit for bit.
+* :func:`engine_spec`     — the GPU engine's *defined* result: score = eight fmaf chains of
+  16 dims tree-combined, order = (score desc, id asc).  The CUDA path must match it bit for bit.
 """
 from __future__ import annotations
 

@@ -49,6 +49,26 @@ __host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) { return ~uin
 // score >= kThrFloor where kThrFloor is the fp32 successor of -FLT_MAX.
 #define PQ_THR_FLOOR (-3.4028232635611926e38f)
 
+// ---------------------------------------------------------------------------------------------
+// The engine's DEFINED fp32 score (restated bit for bit in oracle/flat_oracle.c: engine_dot):
+//   p_j = fmaf chain over dims 16j .. 16j+15 (ascending, starting from 0)            j = 0..7
+//   <a,b> := ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7))
+// Eight independent chains instead of one 128-long one: the scan kernel gives each chain to one lane of an
+// 8-lane group and folds them with three butterfly shuffles; any other kernel (rescoring, norms) computes the
+// same bits with eight accumulators in one thread.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ float engine_dot(const float* __restrict__ a, const float* __restrict__ b) {
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc = fmaf(a[16 * j + i], b[16 * j + i], acc);
+        p[j] = acc;
+    }
+    return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // shared-memory address / mbarrier

@@ -1,14 +1,16 @@
 // proqa_b200 — exact fp32 streaming scan with fused top-k (the bandwidth-bound small-batch path).
 //
-// Replaces, for one batch of <=16 queries, what FAISS IndexFlat::search does on the host
+// Replaces, for one batch of <= 8 queries, what FAISS IndexFlat::search does on the host
 // (reference call site retrieval/eval_retrieval.py:104; FAISS 1.6.3 knn_inner_product ->
 // per-query heap, see oracle/flat_oracle.c).  Design:
 //   * corpus tiles of 128 rows x 512 B stream HBM -> shared memory through TMA (4 boxes of
-//     32 floats x 128 rows, SWIZZLE_128B, so that "one thread = one row" reads are bank-conflict
-//     free), 2-3 stages of 64 KB in flight per SM, one persistent CTA per SM;
-//   * queries sit in constant memory, so the inner loop is LDS.128 + FFMA with a constant-bank
-//     operand: score(q, row) is the sequential chain acc = fmaf(row[i], q[i], acc), i = 0..127 —
-//     the engine's *defined* fp32 score, restated bit-exactly in oracle/flat_oracle.c;
+//     32 floats x 128 rows, SWIZZLE_128B), 3 stages of 64 KB in flight per SM, one persistent
+//     CTA per SM;
+//   * queries sit in shared memory too; a lane owns a 16-dimension slice of 4 rows (lane = rg + 4*kq),
+//     so one LDS.128 of row data feeds 4*QT FFMAs and one LDS.128 of query data feeds 16: the inner
+//     loop is ~90 % FFMA.  The eight 16-dim partial chains of a row are folded across lanes with three
+//     butterfly shuffles — exactly the combination tree of the engine's *defined* fp32 score
+//     (pq_common.cuh: engine_dot; restated bit-exactly in oracle/flat_oracle.c);
 //   * top-k is fused: scores below the running per-query threshold are dropped in registers,
 //     survivors are appended to a shared-memory buffer that is bitonic-sorted back to k entries
 //     when it fills; thresholds are exchanged between CTAs through a global atomicMax so every
@@ -18,9 +20,8 @@
 
 namespace pq {
 
-__constant__ float c_queries[kFfmaMaxQ * kDim];
-
 struct FfmaParams {
+    const float* queries;  // [nq][128] fp32, device
     const float* row_norms;
     uint64_t* out_keys;
     uint32_t* gthr;
@@ -41,6 +42,8 @@ struct FfmaCtrl {                 // lives right after the tile stages in shared
     int need_compact;
     int pad[3];
 };
+constexpr int kFfmaCtrlBytes = 256;
+constexpr int kFfmaQsmBytes = kFfmaMaxQ * kDim * 4;  // queries re-laid out as [q][step][kq] float4
 
 // Sort one query's buffer, keep the best k, refresh and publish its threshold.
 __device__ __forceinline__ void ffma_compact(uint64_t* buf, FfmaCtrl* ctrl, int q, const FfmaParams& p) {
@@ -62,43 +65,83 @@ __device__ __forceinline__ void ffma_compact(uint64_t* buf, FfmaCtrl* ctrl, int 
     __syncthreads();
 }
 
-template <int QOFF, int QH>
-__device__ __forceinline__ void ffma_tile_dots(const uint8_t* stage, int r, float (&acc)[QH]) {
+// One butterfly step of the cross-lane reduction: lanes whose `hi` flag is clear keep the lower half of v[],
+// the others the upper half; each adds the partner's partial for the half it keeps.  fp32 addition is
+// commutative, so both partners of a pair produce identical bits — the combination tree of the engine's
+// defined score (pq_common.cuh: engine_dot) is reproduced exactly.
+template <int N>
+__device__ __forceinline__ void ffma_fold(const float (&v)[N], float (&out)[(N > 1 ? N / 2 : 1)], bool hi, int lane_mask) {
+    if constexpr (N > 1) {
 #pragma unroll
-    for (int j = 0; j < QH; ++j) acc[j] = 0.f;
-    const uint8_t* prow = stage + r * 128;
-    const int sw = (r & 7) << 4;
-#pragma unroll
-    for (int pnl = 0; pnl < 4; ++pnl) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(prow + pnl * (kFfmaTileRows * 128) + ((c << 4) ^ sw));
-            const int d0 = pnl * 32 + c * 4;
-#pragma unroll
-            for (int j = 0; j < QH; ++j) {
-                acc[j] = fmaf(v.x, c_queries[(QOFF + j) * kDim + d0 + 0], acc[j]);
-                acc[j] = fmaf(v.y, c_queries[(QOFF + j) * kDim + d0 + 1], acc[j]);
-                acc[j] = fmaf(v.z, c_queries[(QOFF + j) * kDim + d0 + 2], acc[j]);
-                acc[j] = fmaf(v.w, c_queries[(QOFF + j) * kDim + d0 + 3], acc[j]);
-            }
+        for (int i = 0; i < N / 2; ++i) {
+            const float mine = hi ? v[i + N / 2] : v[i];
+            const float theirs = hi ? v[i] : v[i + N / 2];
+            out[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, lane_mask);
         }
+    } else {
+        out[0] = v[0] + __shfl_xor_sync(0xffffffffu, v[0], lane_mask);
     }
 }
 
-template <int QOFF, int QH>
-__device__ __forceinline__ void ffma_tile_half(const uint8_t* stage, int r, long long row, bool valid, uint64_t* bufs,
-                                               FfmaCtrl* ctrl, const FfmaParams& p) {
-    float acc[QH];
-    ffma_tile_dots<QOFF, QH>(stage, r, acc);
-    if (!valid) return;
-    float bias = 0.f;
-    if (p.metric == kMetricL2) bias = __ldg(p.row_norms + row);
+// One 128-row tile against QT queries.  Lane = rg + 4*kq: rg (0..3) picks the row inside a group of four,
+// kq (0..7) the 16-dimension slice of the dot product this lane accumulates (partial chain p_kq).  A warp covers
+// 16 rows, the CTA's 8 warps the 128 rows of the tile.  Row and query operands both come from shared memory as
+// LDS.128: per 16*QT FFMAs a thread issues 4 + QT loads, all bank-conflict free (rows through TMA's 128-byte
+// swizzle, queries through the [q][step][kq] layout).
+template <int QT>
+__device__ __forceinline__ void ffma_tile(const uint8_t* stage, const float4* qsm, long long tile_row0, uint64_t* bufs, FfmaCtrl* ctrl,
+                                          const FfmaParams& p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rg = lane & 3, kq = lane >> 2;
+    float acc[4 * QT];
 #pragma unroll
-    for (int j = 0; j < QH; ++j) {
-        const int q = QOFF + j;
-        if (q < p.nq) {
-            float s = acc[j];
-            if (p.metric == kMetricL2) s = fmaf(2.f, s, -bias);  // larger is closer: 2<q,x> - |x|^2
+    for (int i = 0; i < 4 * QT; ++i) acc[i] = 0.f;
+    const uint8_t* panel = stage + (kq >> 1) * (kFfmaTileRows * 128);
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+        const int c = (kq & 1) * 4 + step;
+        float4 rv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = warp * 16 + r * 4 + rg;
+            rv[r] = *reinterpret_cast<const float4*>(panel + row * 128 + ((c ^ (row & 7)) << 4));
+        }
+#pragma unroll
+        for (int j = 0; j < QT; ++j) {
+            const float4 qv = qsm[(j * 4 + step) * 8 + kq];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float a = acc[r * QT + j];
+                a = fmaf(rv[r].x, qv.x, a);
+                a = fmaf(rv[r].y, qv.y, a);
+                a = fmaf(rv[r].z, qv.z, a);
+                a = fmaf(rv[r].w, qv.w, a);
+                acc[r * QT + j] = a;
+            }
+        }
+    }
+    // (p0+p1), then +(p2+p3), then +(p4..p7): three butterfly steps over the kq bits of the lane index
+    constexpr int N = 4 * QT;
+    constexpr int N1 = N / 2, N2 = (N1 > 1 ? N1 / 2 : 1), N3 = (N2 > 1 ? N2 / 2 : 1);
+    const bool b0 = kq & 1, b1 = kq & 2, b2 = kq & 4;
+    float w1[N1], w2[N2], w3[N3];
+    ffma_fold<N>(acc, w1, b0, 4);
+    ffma_fold<N1>(w1, w2, b1, 8);
+    ffma_fold<N2>(w2, w3, b2, 16);
+    // flat index a = r*QT + j of the first value this lane ends up owning
+    int a0 = (b0 ? N / 2 : 0) + (b1 ? N / 4 : 0);
+    bool owner = true;
+    if constexpr (N2 > 1) a0 += b2 ? N / 8 : 0;
+    else owner = !b2;  // N == 4: both partners of the last step hold the same value, one reports it
+    if (!owner) return;
+#pragma unroll
+    for (int i = 0; i < N3; ++i) {
+        const int a = a0 + i;
+        const int r = a / QT, q = a % QT;
+        const long long row = tile_row0 + warp * 16 + r * 4 + rg;
+        if (row < p.n_rows && q < p.nq) {
+            float s = w3[i];
+            if (p.metric == kMetricL2) s = fmaf(2.f, s, -__ldg(p.row_norms + row));  // larger is closer: 2<q,x> - |x|^2
             if (s >= ctrl->thr[q]) {
                 const int slot = atomicAdd(&ctrl->cnt[q], 1);
                 bufs[(size_t)q * p.cap + slot] = make_key(s, (uint32_t)row);
@@ -108,16 +151,17 @@ __device__ __forceinline__ void ffma_tile_half(const uint8_t* stage, int r, long
     }
 }
 
-template <int QH>
+template <int QT>
 __global__ void __launch_bounds__(kFfmaThreads, 1)
 pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stages = smem;
-    FfmaCtrl* ctrl = reinterpret_cast<FfmaCtrl*>(smem + (size_t)p.n_stages * kFfmaStageBytes);
-    uint64_t* bufs = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * kFfmaStageBytes + 256);
+    uint8_t* tail = smem + (size_t)p.n_stages * kFfmaStageBytes;
+    FfmaCtrl* ctrl = reinterpret_cast<FfmaCtrl*>(tail);
+    float4* qsm = reinterpret_cast<float4*>(tail + kFfmaCtrlBytes);
+    uint64_t* bufs = reinterpret_cast<uint64_t*>(tail + kFfmaCtrlBytes + kFfmaQsmBytes);
 
     const int t = threadIdx.x;
-    const int r = t & (kFfmaTileRows - 1);
     const int tile0 = blockIdx.x * p.tiles_per_cta;
     int ntiles = p.n_tiles - tile0;
     ntiles = ntiles < 0 ? 0 : (ntiles > p.tiles_per_cta ? p.tiles_per_cta : ntiles);
@@ -131,6 +175,12 @@ pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p
     if (t < kFfmaMaxQ) {
         ctrl->cnt[t] = 0;
         ctrl->thr[t] = (t < p.nq) ? fmaxf(PQ_THR_FLOOR, ordered_to_f32(ld_volatile_u32(p.gthr + t))) : INFINITY;
+    }
+    {   // queries: global [q][128] -> shared [q][step][kq] float4 (dims 16*kq + 4*step .. +3); unused slots are zero
+        const int q = t >> 5, c = t & 31;  // 256 threads = 8 queries x 32 float4
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < p.nq) v = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + c);
+        qsm[(q * 4 + (c & 3)) * 8 + (c >> 2)] = v;
     }
     __syncthreads();
 
@@ -152,14 +202,7 @@ pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p
         if (t == 0 && it + p.n_stages - 1 < ntiles) issue(it + p.n_stages - 1);
         const int s = it % p.n_stages;
         mbar_wait(&ctrl->full[s], (uint32_t)((it / p.n_stages) & 1));
-        const uint8_t* stage = stages + (size_t)s * kFfmaStageBytes;
-        const long long row = (long long)(tile0 + it) * kFfmaTileRows + r;
-        const bool valid = row < p.n_rows;
-        if (t < kFfmaTileRows) {
-            ffma_tile_half<0, QH>(stage, r, row, valid, bufs, ctrl, p);
-        } else if (p.nq > QH) {
-            ffma_tile_half<QH, QH>(stage, r, row, valid, bufs, ctrl, p);
-        }
+        ffma_tile<QT>(stages + (size_t)s * kFfmaStageBytes, qsm, (long long)(tile0 + it) * kFfmaTileRows, bufs, ctrl, p);
         __syncthreads();
         const bool refresh = ((it & 15) == 15);
         if (ctrl->need_compact) {  // block-uniform: written before the barrier above
@@ -200,14 +243,16 @@ static int ffma_cap_for_k(int k) { return next_pow2(k + kFfmaTileRows) < 256 ? 2
 int ffma_max_queries_for_k(int k) {
     if (k < 1) return 0;
     const long long cap = ffma_cap_for_k(k);
-    long long q = (kSmemLimit - 2LL * kFfmaStageBytes - 256 - 1024) / (cap * 8);  // prefer a double-buffered ring
-    if (q < 1) q = (kSmemLimit - 1LL * kFfmaStageBytes - 256 - 1024) / (cap * 8); // huge k: single stage
+    const long long fixed = kFfmaCtrlBytes + kFfmaQsmBytes + 1024;
+    long long q = (kSmemLimit - 2LL * kFfmaStageBytes - fixed) / (cap * 8);  // prefer a double-buffered ring
+    if (q < 1) q = (kSmemLimit - 1LL * kFfmaStageBytes - fixed) / (cap * 8); // huge k: single stage
     if (q > kFfmaMaxQ) q = kFfmaMaxQ;
     return (int)q;
 }
 
 cudaError_t ffma_scan_launch(const FfmaLaunch& a, cudaStream_t stream) {
     FfmaParams p;
+    p.queries = a.queries_dev;
     p.row_norms = a.row_norms;
     p.out_keys = a.out_keys;
     p.gthr = a.gthr;
@@ -218,17 +263,13 @@ cudaError_t ffma_scan_launch(const FfmaLaunch& a, cudaStream_t stream) {
     p.k = a.k;
     p.cap = ffma_cap_for_k(a.k);
     p.metric = a.metric;
-    const size_t buf_bytes = (size_t)a.nq * p.cap * 8 + 256;
+    const size_t buf_bytes = (size_t)a.nq * p.cap * 8 + kFfmaCtrlBytes + kFfmaQsmBytes;
     p.n_stages = 3;
     while (p.n_stages > 1 && (size_t)p.n_stages * kFfmaStageBytes + buf_bytes > (size_t)kSmemLimit) --p.n_stages;
     const size_t smem = (size_t)p.n_stages * kFfmaStageBytes + buf_bytes;
     if (a.nq < 1 || a.nq > kFfmaMaxQ || smem > (size_t)kSmemLimit) return cudaErrorInvalidValue;
 
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_queries, a.queries_dev, (size_t)a.nq * kDim * sizeof(float), 0,
-                                            cudaMemcpyDeviceToDevice, stream);
-    if (e != cudaSuccess) return e;
-
-    const int qh = a.nq <= 1 ? 1 : (a.nq <= 2 ? 1 : (a.nq <= 4 ? 2 : (a.nq <= 8 ? 4 : 8)));
+    const int qh = a.nq <= 1 ? 1 : (a.nq <= 2 ? 2 : (a.nq <= 4 ? 4 : 8));
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;

@@ -10,12 +10,12 @@ namespace pq {
 enum Metric : int { kMetricIP = 0, kMetricL2 = 1 };
 
 // ------------------------------------------------------------------------------------------------
-// Exact fp32 streaming scan (pq_ffma.cu).  One launch scans local rows [0, n_rows) for up to 16
-// queries held in constant memory and leaves one sorted k-list per (CTA, query).
+// Exact fp32 streaming scan (pq_ffma.cu).  One launch scans local rows [0, n_rows) for up to 8
+// queries held in shared memory and leaves one sorted k-list per (CTA, query).
 // ------------------------------------------------------------------------------------------------
 constexpr int kFfmaTileRows = 128;
 constexpr int kFfmaThreads = 256;
-constexpr int kFfmaMaxQ = 16;
+constexpr int kFfmaMaxQ = 8;
 constexpr int kFfmaStageBytes = kFfmaTileRows * 512;
 
 struct FfmaLaunch {
@@ -62,7 +62,7 @@ cudaError_t merge_lists_launch(const MergeLaunch& a, cudaStream_t stream);
 cudaError_t merge_di_launch(const float* D_in, const long long* I_in, int n_lists, int nq, int k, int metric, float* D_out,
                             long long* I_out, cudaStream_t stream);
 
-// Row preparation (corpus rows at add(), query rows at search()): squared norms (sequential fmaf chain),
+// Row preparation (corpus rows at add(), query rows at search()): squared norms (engine_dot(row,row)),
 // bf16 copy, max squared norm, non-finite detection (global flag and/or per-row byte).  Optional outputs may be null
 // except rows_bf16 and norms.
 cudaError_t prep_rows_launch(const float* rows, long long n, uint16_t* rows_bf16, float* norms, uint32_t* max_norm_bits,

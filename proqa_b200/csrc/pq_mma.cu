@@ -44,7 +44,7 @@ constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
 constexpr int kMaxMTiles = 3;
 
 // eps: bf16 rounding of both operands (2^-8 + 2^-18), tensor-core fp32 accumulation slack (2^-13) and the
-// fp32 chain's own rounding (128 * 2^-24), relative to sum|q_i c_i| <= |q||c|; plus 2% head-room.
+// fp32 score's own rounding (<= 19 * 2^-24), relative to sum|q_i c_i| <= |q||c|; plus 2% head-room.
 constexpr float kEps = 0.0042f;
 
 struct MmaCtrl {
@@ -409,16 +409,23 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) 
             const uint64_t key = carry[i];
             if (key != 0ull) {
                 const uint32_t row = key_row(key);
+                // the engine's defined score (pq_common.cuh: engine_dot): 8 chains of 16 dims, tree-combined
                 const float4* r4 = reinterpret_cast<const float4*>(p.rows + (size_t)row * kDim);
-                float acc = 0.f;
-#pragma unroll 8
-                for (int j = 0; j < kDim / 4; ++j) {
-                    const float4 v = __ldg(r4 + j);
-                    acc = fmaf(v.x, s_q[4 * j + 0], acc);
-                    acc = fmaf(v.y, s_q[4 * j + 1], acc);
-                    acc = fmaf(v.z, s_q[4 * j + 2], acc);
-                    acc = fmaf(v.w, s_q[4 * j + 3], acc);
+                float pj[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 v = __ldg(r4 + 4 * j + i);
+                        a = fmaf(v.x, s_q[16 * j + 4 * i + 0], a);
+                        a = fmaf(v.y, s_q[16 * j + 4 * i + 1], a);
+                        a = fmaf(v.z, s_q[16 * j + 4 * i + 2], a);
+                        a = fmaf(v.w, s_q[16 * j + 4 * i + 3], a);
+                    }
+                    pj[j] = a;
                 }
+                float acc = ((pj[0] + pj[1]) + (pj[2] + pj[3])) + ((pj[4] + pj[5]) + (pj[6] + pj[7]));
                 if (p.metric == kMetricL2) acc = fmaf(2.f, acc, -__ldg(p.row_norms + row));
                 if (acc >= PQ_THR_FLOOR) out = make_key(acc, row);
             }
