@@ -27,6 +27,7 @@
 #include "pq_host.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,14 +35,16 @@
 namespace pq {
 
 constexpr int kBM = 128;            // queries per M tile (TMEM lanes)
-constexpr int kBN = 128;            // corpus rows per B tile (TMEM columns per accumulator)
-constexpr int kStages = 4;          // B ring depth
-constexpr int kAccBufs = 4;         // TMEM accumulators (4 x 128 cols = 512)
+constexpr int kBN = 128;            // corpus rows per B tile (one TMA stage)
+constexpr int kSubN = 64;           // corpus rows per accumulator (UMMA N): two accumulators per (B tile, M tile)
+constexpr int kStages = 6;          // B ring depth
+constexpr int kAccBufs = 4;         // TMEM accumulators of kSubN columns
+constexpr int kTmemACol = kAccBufs * kSubN;    // first TMEM column of the stationary query operand
 constexpr int kPanelBytes = 128 * 128;         // 128 rows x 128 B (64 bf16): one swizzle-128B K panel
 constexpr int kTileBytes = 2 * kPanelBytes;    // K = 128 -> two panels, 32 KB
 constexpr int kEpiWarps = 8;
 constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
-constexpr int kMaxMTiles = 3;
+constexpr int kMaxMTiles = 4;       // 4 x 64 TMEM columns of bf16 queries + 4 x 64 columns of accumulators = 512
 
 // eps: bf16 rounding of both operands (2^-8 + 2^-18), tensor-core fp32 accumulation slack (2^-13) and the
 // fp32 score's own rounding (<= 19 * 2^-24), relative to sum|q_i c_i| <= |q||c|; plus 2% head-room.
@@ -52,22 +55,25 @@ struct MmaCtrl {
     uint64_t empty[kStages];
     uint64_t tmem_full[kAccBufs];
     uint64_t tmem_empty[kAccBufs];
-    uint64_t a_full;
     uint32_t tmem_base;
     uint32_t pad;
 };
 
 struct MmaParams {
-    uint64_t* cand_keys;   // [nq_pad][n_sub][cap]
-    uint32_t* cand_cnt;    // [nq_pad][n_sub]
-    const float* thr;      // [nq_pad]
-    const float* two_e;    // [nq_pad]
-    long long row_begin;   // multiple of 128
-    long long row_end;     // exclusive, <= ntotal
-    int tiles_per_slice;
-    int n_mtiles;          // total query tiles
+    const uint16_t* q_bf16;  // [nq_pad][128] bf16 queries (rows beyond nq are zero)
+    uint64_t* cand_keys;     // [nq_pad][n_sub][cap]
+    uint32_t* cand_cnt;      // [nq_pad][n_sub], zeroed before the launch
+    const float* thr;        // [nq_pad]
+    const float* two_e;      // [nq_pad]
+    long long row_begin;     // multiple of 128
+    long long row_end;       // exclusive, <= ntotal
+    int n_mtiles;            // total query tiles
+    // query tiles are dealt to `n_groups` CTA groups as evenly as possible: the first `rem` groups own base+1
+    // tiles and are given s1 row slices each, the others own `base` tiles and s0 slices (s ~ proportional to
+    // the tiles owned, so every CTA carries the same number of (query tile x row tile) products)
+    int base, rem, s1, s0;
     int cap;
-    int n_sub;
+    int n_sub;               // candidate slabs per query = max(s1, s0) * 2 (one per epilogue warp set)
     int k1_adapt;
 };
 
@@ -86,32 +92,96 @@ __device__ __noinline__ uint32_t mma_insert_group4(float a, float b, float c, fl
     return cnt;
 }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the stationary operand (queries) is read from tensor memory, so shared
+// memory only has to feed the streamed corpus tile (64 B/clk instead of 128 B/clk for the SS form).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 TMEM lanes (one per thread of the warp) x 32 consecutive 32-bit columns <- 32 registers.
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Threshold filter over 32 accumulator columns held in registers (one thread = one query).
+__device__ __forceinline__ void mma_filter32(const float (&v)[32], float& thr, float two_e, int k1_adapt, uint32_t base_row, uint32_t row_end32,
+                                             uint64_t* slab, uint32_t& cnt, uint32_t cap) {
+    // Max tree over the 32 columns, keeping the 8 group-of-4 maxima: the rare survivor is then located by 8 cheap
+    // group tests.  Rows past row_end (TMA zero fill in the last tile) score 0 and are rejected inside
+    // mma_insert_group4.
+    float g4[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) g4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+    const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
+    const float th = thr;
+    if (k1_adapt && base_row + 32 <= row_end32) thr = fmaxf(th, mx - two_e);
+    if (mx >= th) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (g4[g] >= th)
+                cnt = mma_insert_group4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], th, base_row + 4 * g, row_end32, slab, cnt, cap);
+        }
+    }
+}
+
+// Accumulator schedule shared by the MMA issuer and the epilogue.  For row tile t, query tile mi (< m) and row half h
+// one accumulator of 64 columns is produced.  The eight epilogue warps form two sets of four (one warp per TMEM lane
+// quarter); set h consumes the accumulators of row half h, in the order j = t*m + mi, through its own two TMEM buffers
+// (buffer h*2 + (j & 1), use number j >> 1).  Every buffer is therefore produced and consumed in one fixed order by
+// one fixed set of warps — an mbarrier parity wait can only tell adjacent phases apart, so a consumer must never be
+// able to run two uses ahead of a buffer it shares with someone else.
 template <int M_TILES>
 __global__ void __launch_bounds__(kMmaThreads, 1)
-pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, const MmaParams p) {
+pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* smem_a = smem;                                        // M_TILES x 32 KB
-    uint8_t* smem_b = smem + (size_t)M_TILES * kTileBytes;         // kStages x 32 KB
+    uint8_t* smem_b = smem;                                        // kStages x 32 KB
     MmaCtrl* ctrl = reinterpret_cast<MmaCtrl*>(smem_b + (size_t)kStages * kTileBytes);
 
-    const int warp = threadIdx.x >> 5;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role code below (barrier
+    // addresses, descriptors, loop counters) in uniform registers — the tcgen05.mma issue path is a handful of uniform
+    // instructions instead of a per-lane "waterfall" loop around every UTCHMMA
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const int group = blockIdx.x;
-    const int slice = blockIdx.y;
-    const int mt0 = group * M_TILES;
-    const int m = min(M_TILES, p.n_mtiles - mt0);
+
+    // which query tiles and which row slice this CTA owns
+    int group, slice, n_slices;
+    {
+        const int x = blockIdx.x, big = p.rem * p.s1;
+        if (x < big) {
+            group = x / p.s1;
+            slice = x - group * p.s1;
+            n_slices = p.s1;
+        } else {
+            group = p.rem + (x - big) / p.s0;
+            slice = (x - big) % p.s0;
+            n_slices = p.s0;
+        }
+    }
+    const int mt0 = group * p.base + min(group, p.rem);
+    const int m = min(M_TILES, p.base + (group < p.rem ? 1 : 0));
 
     const long long total_tiles = (p.row_end - p.row_begin + kBN - 1) / kBN;
-    const long long tile_begin = (long long)slice * p.tiles_per_slice;
+    const long long tiles_per_slice = (total_tiles + n_slices - 1) / n_slices;
+    const long long tile_begin = (long long)slice * tiles_per_slice;
     long long nt = total_tiles - tile_begin;
-    nt = nt < 0 ? 0 : (nt > p.tiles_per_slice ? p.tiles_per_slice : nt);
+    nt = nt < 0 ? 0 : (nt > tiles_per_slice ? tiles_per_slice : nt);
     const int ntiles = (int)nt;
     const long long row0 = p.row_begin + tile_begin * kBN;
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_c);
-    }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_c);
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) {
@@ -120,9 +190,8 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             for (int b = 0; b < kAccBufs; ++b) {
                 mbar_init(&ctrl->tmem_full[b], 1);
-                mbar_init(&ctrl->tmem_empty[b], kEpiWarps);
+                mbar_init(&ctrl->tmem_empty[b], kEpiWarps / 2);
             }
-            mbar_init(&ctrl->a_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -133,62 +202,91 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after_sync();
     const uint32_t tmem_base = ctrl->tmem_base;
 
+    const int e = warp - 2;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    const int set = e >> 2;         // epilogue warp set (0/1); meaningless for warps 0 and 1
+    if (warp >= 2) {
+        // ---- queries -> tensor memory: lane = query, 64 columns of packed bf16 pairs per query tile ----
+        for (int mi = set; mi < m; mi += 2) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.q_bf16 + ((size_t)(mt0 + mi) * kBM + quarter * 32 + lane) * kDim);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemACol + mi * 64);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 w = __ldg(src + half * 8 + j);
+                    r[4 * j + 0] = w.x;
+                    r[4 * j + 1] = w.y;
+                    r[4 * j + 2] = w.z;
+                    r[4 * j + 3] = w.w;
+                }
+                tmem_st_32x32(taddr + half * 32, r);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0 && ntiles > 0) {
-            mbar_arrive_expect_tx(&ctrl->a_full, (uint32_t)m * kTileBytes);
-            for (int mi = 0; mi < m; ++mi)
-                for (int pnl = 0; pnl < 2; ++pnl)
-                    tma_load_2d(smem_a + (size_t)mi * kTileBytes + pnl * kPanelBytes, &tmap_q, pnl * 64, (mt0 + mi) * kBM, &ctrl->a_full);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kStages;
-                const uint32_t ph = (uint32_t)(t / kStages) & 1u;
-                mbar_wait(&ctrl->empty[s], ph ^ 1u);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % kStages;
+            const uint32_t ph = (uint32_t)(t / kStages) & 1u;
+            mbar_wait(&ctrl->empty[s], ph ^ 1u);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&ctrl->full[s], kTileBytes);
                 const int y = (int)(row0 + (long long)t * kBN);
+#pragma unroll
                 for (int pnl = 0; pnl < 2; ++pnl)
                     tma_load_2d(smem_b + (size_t)s * kTileBytes + pnl * kPanelBytes, &tmap_c, pnl * 64, y, &ctrl->full[s]);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0 && ntiles > 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN);
-            const uint32_t a_addr = smem_u32(smem_a);
-            const uint32_t b_addr = smem_u32(smem_b);
-            mbar_wait(&ctrl->a_full, 0);
+        // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = umma_idesc_bf16(kBM, kSubN);
+        const uint32_t b_addr = smem_u32(smem_b);
+        // all 512 columns are ours (one CTA per SM): the allocation can only start at lane 0, column 0
+        if (tmem_base != 0) __trap();
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % kStages;
+            const uint32_t ph = (uint32_t)(t / kStages) & 1u;
+            mbar_wait(&ctrl->full[s], ph);
             tc_fence_after_sync();
-            int it = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kStages;
-                const uint32_t ph = (uint32_t)(t / kStages) & 1u;
-                mbar_wait(&ctrl->full[s], ph);
+            for (int mi = 0; mi < m; ++mi) {
+                const int j = t * m + mi;
+                const int b0 = (j & 1), b1 = 2 + (j & 1);
+                const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(&ctrl->tmem_empty[b0], aph ^ 1u);
+                mbar_wait(&ctrl->tmem_empty[b1], aph ^ 1u);
                 tc_fence_after_sync();
-                for (int mi = 0; mi < m; ++mi, ++it) {
-                    const int b = it % kAccBufs;
-                    const uint32_t aph = (uint32_t)(it / kAccBufs) & 1u;
-                    mbar_wait(&ctrl->tmem_empty[b], aph ^ 1u);
-                    tc_fence_after_sync();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)b * kBN;
+                if (elect_one()) {
+                    const uint32_t a_tmem = (uint32_t)(kTmemACol + mi * 64);
+                    const uint32_t tile_addr = b_addr + (uint32_t)s * kTileBytes;
+                    // the two row halves accumulate into different TMEM buffers: interleaving them keeps two independent
+                    // accumulation chains in the tensor pipe
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
+                        // K step ks is 32 B into the 128-B row of panel ks>>2; rows 64.. of the tile start 64*128 B into each panel
                         const uint32_t koff = (uint32_t)(ks >> 2) * kPanelBytes + (uint32_t)(ks & 3) * 32u;
-                        const uint64_t adesc = umma_desc_k128(a_addr + (uint32_t)mi * kTileBytes + koff);
-                        const uint64_t bdesc = umma_desc_k128(b_addr + (uint32_t)s * kTileBytes + koff);
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+                        umma_bf16_ts((uint32_t)(b0 * kSubN), a_tmem + (uint32_t)ks * 8u, umma_desc_k128(tile_addr + koff), idesc, ks > 0 ? 1u : 0u);
+                        umma_bf16_ts((uint32_t)(b1 * kSubN), a_tmem + (uint32_t)ks * 8u, umma_desc_k128(tile_addr + koff + kSubN * 128), idesc,
+                                     ks > 0 ? 1u : 0u);
                     }
-                    umma_commit(&ctrl->tmem_full[b]);
+                    umma_commit(&ctrl->tmem_full[b0]);
+                    umma_commit(&ctrl->tmem_full[b1]);
+                    if (mi == m - 1) umma_commit(&ctrl->empty[s]);
                 }
-                umma_commit(&ctrl->empty[s]);
+                __syncwarp();
             }
         }
     } else {
         // ===================== epilogue: threshold filter =====================
-        const int e = warp - 2;
-        const int quarter = warp & 3;   // TMEM lane quarter this warp may read
-        const int half = e >> 2;        // which 64 columns of each 128-column accumulator
         const int lane_q = quarter * 32 + lane;
-        const int sub = slice * 2 + half;
+        const int sub = slice * 2 + set;
         float thr[M_TILES], two_e[M_TILES];
         uint32_t cnt[M_TILES];
         uint64_t* slab[M_TILES];
@@ -206,49 +304,28 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
         }
         const uint32_t row_end32 = (uint32_t)p.row_end;
-        int it = 0;
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
-            const long long tile_row = row0 + (long long)t * kBN + half * 64;
+            const uint32_t base_row = (uint32_t)(row0 + (long long)t * kBN + set * kSubN);
 #pragma unroll
             for (int mi = 0; mi < M_TILES; ++mi) {
                 if (mi < m) {
-                    const int b = it % kAccBufs;
-                    const uint32_t aph = (uint32_t)(it / kAccBufs) & 1u;
-                    ++it;
+                    const int j = t * m + mi;
+                    const int b = set * 2 + (j & 1);
+                    const uint32_t aph = (uint32_t)(j >> 1) & 1u;
                     mbar_wait(&ctrl->tmem_full[b], aph);
                     tc_fence_after_sync();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kBN + half * 64);
-                    float v[2][32];
-                    tmem_ld_32x32(taddr, v[0]);
-                    tmem_ld_32x32(taddr + 32, v[1]);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kSubN);
+                    float v0[32], v1[32];
+                    tmem_ld_32x32(taddr, v0);
+                    tmem_ld_32x32(taddr + 32, v1);
                     tmem_ld_wait();
                     // The accumulator is in registers now: hand the TMEM buffer back before filtering.
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint32_t base_row = (uint32_t)(tile_row + c * 32);
-                        // Max tree over the 32 columns, keeping the 8 group-of-4 maxima: the rare survivor is
-                        // then located by 8 cheap group tests.  Rows past row_end (TMA zero fill in the last
-                        // tile) score 0 and are rejected inside mma_insert_group4.
-                        float g4[8];
-#pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            g4[g] = fmaxf(fmaxf(v[c][4 * g], v[c][4 * g + 1]), fmaxf(v[c][4 * g + 2], v[c][4 * g + 3]));
-                        const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
-                        const float th = thr[mi];
-                        if (p.k1_adapt && base_row + 32 <= row_end32) thr[mi] = fmaxf(th, mx - two_e[mi]);
-                        if (mx >= th) {
-#pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                if (g4[g] >= th)
-                                    cnt[mi] = mma_insert_group4(v[c][4 * g], v[c][4 * g + 1], v[c][4 * g + 2], v[c][4 * g + 3], th,
-                                                                base_row + 4 * g, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
-                            }
-                        }
-                    }
+                    mma_filter32(v0, thr[mi], two_e[mi], p.k1_adapt, base_row, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
+                    mma_filter32(v1, thr[mi], two_e[mi], p.k1_adapt, base_row + 32, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
                 }
             }
         }
@@ -472,17 +549,21 @@ static int next_pow2i(int v) {
 }
 
 template <int M>
-static cudaError_t launch_filter(const CUtensorMap& tq, const CUtensorMap& tc, const MmaParams& p, dim3 grid, cudaStream_t stream) {
-    const size_t smem = (size_t)M * kTileBytes + (size_t)kStages * kTileBytes + sizeof(MmaCtrl);
+static cudaError_t launch_filter(const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
+    const size_t smem = (size_t)kStages * kTileBytes + sizeof(MmaCtrl);
     cudaError_t e = cudaFuncSetAttribute(pq_mma_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pq_mma_filter_kernel<M><<<grid, kMmaThreads, smem, stream>>>(tq, tc, p);
+    pq_mma_filter_kernel<M><<<n_ctas, kMmaThreads, smem, stream>>>(tc, p);
     return cudaGetLastError();
 }
 
 struct EpochPlan {
     long long begin, end;
-    int n_slices, tiles_per_slice, cap;
+    int s1, s0, cap;   // row slices per CTA group (groups owning base+1 / base query tiles), slab capacity
+};
+
+struct GridShape {
+    int n_groups, base, rem, m_max, subs_per_slice;
 };
 
 static int carry_size_for_k(int k) {
@@ -490,25 +571,32 @@ static int carry_size_for_k(int k) {
     return std::max(kp, 64);
 }
 
-static int pick_slices(int n_groups, long long tiles, int n_sms) {
-    long long s;
-    if (n_groups <= n_sms) {
-        s = n_sms / n_groups;
+// Row slices per CTA group.  With no more groups than SMs every group gets slices in proportion to the query tiles it
+// owns (so all CTAs carry equal work and one wave fills the machine); otherwise a uniform count whose CTA total
+// wastes the least of the last wave.
+static void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n_sms, int* s1, int* s0) {
+    long long a, b;
+    if (g.n_groups <= n_sms) {
+        a = (long long)n_sms * (g.base + 1) / n_mtiles;
+        b = (long long)n_sms * g.base / n_mtiles;
+        if (g.rem == 0) a = b;
     } else {
         double best = 0.0;
-        s = 1;
+        a = 1;
         for (int c = 1; c <= 8; ++c) {
-            const long long ctas = (long long)n_groups * c;
+            const long long ctas = (long long)g.n_groups * c;
             const double eff = (double)ctas / ((double)n_sms * (double)((ctas + n_sms - 1) / n_sms));
             if (eff > best + 1e-9) {
                 best = eff;
-                s = c;
+                a = c;
             }
         }
+        b = a;
     }
-    if (s > tiles) s = tiles;
-    if (s < 1) s = 1;
-    return (int)s;
+    a = std::max(1LL, std::min(a, tiles));
+    b = std::max(1LL, std::min(b, tiles));
+    *s1 = (int)a;
+    *s0 = (int)b;
 }
 
 int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, float* dD_all, long long* dI_all,
@@ -522,8 +610,12 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         const int nq = std::min(kMaxBatch, nq_total - qb);
         const int nq_pad = (nq + kBM - 1) / kBM * kBM;
         const int n_mtiles = nq_pad / kBM;
-        const int M = std::min(kMaxMTiles, n_mtiles);
-        const int n_groups = (n_mtiles + M - 1) / M;
+        GridShape gs;
+        gs.n_groups = (n_mtiles + kMaxMTiles - 1) / kMaxMTiles;
+        gs.base = n_mtiles / gs.n_groups;
+        gs.rem = n_mtiles % gs.n_groups;
+        gs.m_max = gs.base + (gs.rem ? 1 : 0);
+        gs.subs_per_slice = 2;  // the two epilogue warp sets (row halves of every tile) keep separate slabs
         const float* dq = dq_all + (size_t)qb * kDim;
         const uint16_t* dq_bf16 = (const uint16_t*)ix->ws_qbf16.p + (size_t)qb * kDim;
         const float* dq_norm = (const float*)ix->ws_qnorm.p + qb;
@@ -535,10 +627,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             EpochPlan ep;
             ep.begin = 0;
             ep.end = N;
-            const long long tiles = (N + kBN - 1) / kBN;
-            ep.n_slices = pick_slices(n_groups, tiles, ix->n_sms);
-            ep.tiles_per_slice = (int)((tiles + ep.n_slices - 1) / ep.n_slices);
-            ep.n_slices = (int)((tiles + ep.tiles_per_slice - 1) / ep.tiles_per_slice);
+            pick_slices(gs, n_mtiles, (N + kBN - 1) / kBN, ix->n_sms, &ep.s1, &ep.s0);
             ep.cap = 128;
             plan.push_back(ep);
         } else {
@@ -549,15 +638,13 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
                 ep.begin = begin;
                 ep.end = std::min(end, N);
                 const long long tiles = (ep.end - ep.begin + kBN - 1) / kBN;
-                if (begin == 0) {  // bootstrap: every score is a candidate, one tile per slice
-                    ep.n_slices = (int)tiles;
-                    ep.tiles_per_slice = 1;
-                    ep.cap = 64;
+                if (begin == 0) {  // bootstrap: every score is a candidate, one row tile per slice
+                    ep.s1 = ep.s0 = (int)tiles;
+                    ep.cap = kBN / gs.subs_per_slice;
                 } else {
-                    ep.n_slices = pick_slices(n_groups, tiles, ix->n_sms);
-                    ep.tiles_per_slice = (int)((tiles + ep.n_slices - 1) / ep.n_slices);
-                    ep.n_slices = (int)((tiles + ep.tiles_per_slice - 1) / ep.tiles_per_slice);
-                    const double expect = (double)kp * log((double)ep.end / (double)ep.begin) / (2.0 * ep.n_slices);
+                    pick_slices(gs, n_mtiles, tiles, ix->n_sms, &ep.s1, &ep.s0);
+                    const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
+                    const double expect = (double)kp * log((double)ep.end / (double)ep.begin) / slabs;
                     ep.cap = std::min(4096, std::max(64, next_pow2i((int)(4.0 * expect) + 32)));
                 }
                 plan.push_back(ep);
@@ -567,8 +654,9 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         }
         size_t max_slab = 0, max_cnt = 0;
         for (const EpochPlan& ep : plan) {
-            max_slab = std::max(max_slab, (size_t)nq_pad * ep.n_slices * 2 * ep.cap * 8);
-            max_cnt = std::max(max_cnt, (size_t)nq_pad * ep.n_slices * 2 * 4);
+            const size_t n_sub = (size_t)std::max(ep.s1, ep.s0) * gs.subs_per_slice;
+            max_slab = std::max(max_slab, (size_t)nq_pad * n_sub * ep.cap * 8);
+            max_cnt = std::max(max_cnt, (size_t)nq_pad * n_sub * 4);
         }
 
         // ---- workspaces -----------------------------------------------------------------------
@@ -589,10 +677,6 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         st.overflow = (uint32_t*)w[3].p;
         st.carry = (uint64_t*)w[4].p;
 
-        CUtensorMap tmap_q;
-        rc = make_row_tensor_map(&tmap_q, dq_bf16, nq_pad, 2, 64, kBM);
-        if (rc) return rc;
-
         PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
         pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, dq_bad, nq, nq_pad, kp, ix->max_norm2);
         PQ_CUDA(cudaGetLastError());
@@ -601,23 +685,29 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         // ---- epochs ---------------------------------------------------------------------------
         for (const EpochPlan& ep : plan) {
             MmaParams mp;
+            mp.q_bf16 = dq_bf16;
             mp.cand_keys = (uint64_t*)w[5].p;
             mp.cand_cnt = (uint32_t*)w[6].p;
             mp.thr = st.thr;
             mp.two_e = st.two_e;
             mp.row_begin = ep.begin;
             mp.row_end = ep.end;
-            mp.tiles_per_slice = ep.tiles_per_slice;
             mp.n_mtiles = n_mtiles;
+            mp.base = gs.base;
+            mp.rem = gs.rem;
+            mp.s1 = ep.s1;
+            mp.s0 = ep.s0;
             mp.cap = ep.cap;
-            mp.n_sub = ep.n_slices * 2;
+            mp.n_sub = std::max(ep.s1, ep.s0) * gs.subs_per_slice;
             mp.k1_adapt = k1 ? 1 : 0;
-            const dim3 grid((unsigned)n_groups, (unsigned)ep.n_slices);
+            const int n_ctas = gs.rem * ep.s1 + (gs.n_groups - gs.rem) * ep.s0;
+            // slabs a CTA never touches (unequal slice counts, query tiles owned by the other warp set) must read as empty
+            PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
             cudaError_t e;
             ix->prof_begin();
-            if (M == 1) e = launch_filter<1>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
-            else if (M == 2) e = launch_filter<2>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
-            else e = launch_filter<3>(tmap_q, ix->tmap_bf16, mp, grid, ix->stream);
+            if (gs.m_max == 1) e = launch_filter<1>(ix->tmap_bf16, mp, n_ctas, ix->stream);
+            else if (gs.m_max == 2) e = launch_filter<2>(ix->tmap_bf16, mp, n_ctas, ix->stream);
+            else e = launch_filter<4>(ix->tmap_bf16, mp, n_ctas, ix->stream);
             ix->prof_end();
             PQ_CUDA(e);
 
