@@ -27,6 +27,9 @@ WORKLOADS = {
     "c2": dict(nq=3610, rows=21_000_000, k=100, desc="NQ-scale search: 3610 queries x 21M x 128 fp32 corpus, k=100"),
     "c3": dict(nq=65536, rows=21_000_000, k=80, desc="large batch: 65536 queries x 21M x 128 fp32, k=80"),
     "s0": dict(nq=16, rows=21_000_000, k=80, desc="small-batch sweep point: 16 queries x 21M x 128 fp32, k=80 (HBM-bound)"),
+    "c4": dict(nq=21_000_000, rows=10_000, k=1, kind="kmeans",
+               desc="group_paras.py k-means assignment: 21M x 128 points x 10,000 centroids, k=1 (points are the query side)"),
+    "c5": dict(nq=8192, rows=100_000_000, k=1000, desc="scale-out: 8192 queries x 100M x 128 fp32, k=1000 (needs 8 GPUs for the full corpus)"),
 }
 CHUNK = 1_000_000  # rows per generated chunk; chunk c is seeded with 1234 + c so the corpus does not depend on N
 
@@ -61,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -135,6 +138,8 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if wl.get("kind") == "kmeans":
+        return run_reference_kmeans(args, wl)
     xq = host_queries(wl["nq"])
     total = args.steps + args.warmup
     per_step_budget = max(2.0, min(20.0, 150.0 / max(total, 1)))
@@ -158,6 +163,39 @@ def run_reference(args, wl):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_t * 1e3, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl),
            "corpus_gbs": wl["rows"] * 512 / full_t / 1e9,
+           "cpu_baseline": {"value": value, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_reference_kmeans(args, wl):
+    """C4 on the host cores: a bounded sample of points against all centroids per step (IndexFlatL2/IP.search(x, 1))."""
+    from oracle import oracle
+    cents = np.random.default_rng(777).standard_normal((wl["rows"], 128), dtype=np.float32)
+    fo = oracle.FaissFlatOracle(128, 1 if args.metric == "l2" else 0)
+    fo.add(cents)
+    total = args.steps + args.warmup
+    per_step_budget = max(1.0, min(10.0, 120.0 / max(total, 1)))
+    probe = host_queries(20_000)
+    t0 = time.perf_counter()
+    fo.search(probe, 1)
+    t_probe = time.perf_counter() - t0
+    ns = int(min(wl["nq"], 2_000_000, max(20_000, 20_000 * per_step_budget / max(t_probe, 1e-6))))
+    xs = host_queries(ns)
+    for _ in range(args.warmup):
+        fo.search(xs, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fo.search(xs, 1)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = ns / dt
+    sample = (f"each step: {ns} of {wl['nq']} points x all {wl['rows']} centroids ({dt:.2f}s); FAISS-1.6.3 restatement "
+              "(OpenBLAS sgemm + heap), not FAISS (faiss-cpu is not installable here)")
+    out = {"impl": "reference", "metric": "queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": wl["nq"] / value * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl["desc"], "name": args.workload, "points": wl["nq"], "centroids": wl["rows"], "d": 128, "k": 1, "metric": args.metric},
+           "corpus_gbs": value * 512 / 1e9,
            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -407,6 +445,161 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_kmeans_assign(args, wl):
+    """C4: the k = 1 assignment search of group_paras.py:45,51 — many points (query side) against few centroids (index side).
+    Points are sharded over ranks (data parallel, no exchange); a step is one assignment pass over all points."""
+    import torch
+    import torch.distributed as dist
+    import proqa_b200 as pq
+    from proqa_b200.sharded import shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; proqa_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_points, n_cent = wl["nq"], wl["rows"]
+    metric = pq.METRIC_L2 if args.metric == "l2" else pq.METRIC_INNER_PRODUCT
+    lo, hi = shard_bounds(n_points, world, rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(777)
+    cents = torch.randn((n_cent, 128), generator=g, device=dev, dtype=torch.float32)
+    pts = torch.empty((hi - lo, 128), device=dev, dtype=torch.float32)
+    for c in range(lo // CHUNK, (hi + CHUNK - 1) // CHUNK):  # same counter-based stream whatever the rank count
+        g.manual_seed(4321 + c)
+        rows = min(CHUNK, n_points - c * CHUNK)
+        x = torch.randn((rows, 128), generator=g, device=dev, dtype=torch.float32)
+        a, b = max(lo, c * CHUNK) - c * CHUNK, min(hi, c * CHUNK + rows) - c * CHUNK
+        pts[max(lo, c * CHUNK) - lo: max(lo, c * CHUNK) - lo + (b - a)] = x[a:b]
+        del x
+    ix = pq.IndexFlat(128, metric, local_rank)
+    if args.tier:
+        ix.set_tier(args.tier)
+    torch.cuda.synchronize()
+    ix.add_device(cents.data_ptr(), n_cent)
+    stream = torch.cuda.current_stream()
+    ix.set_stream(stream.cuda_stream)
+    n_loc = hi - lo
+    D = torch.empty((n_loc, 1), dtype=torch.float32, device=dev)
+    I = torch.empty((n_loc, 1), dtype=torch.int64, device=dev)
+
+    def step():
+        ix.search_device(pts.data_ptr(), n_loc, 1, D.data_ptr(), I.data_ptr())
+        return ix.last_stats[5]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step()
+    torch.cuda.synchronize()
+    nchk = min(n_loc, 4096)
+    p64, c64 = pts[:nchk].double(), cents.double()
+    S = p64 @ c64.T
+    if metric == pq.METRIC_L2:
+        dist2 = (p64 * p64).sum(1, keepdim=True) + (c64 * c64).sum(1)[None, :] - 2.0 * S
+        best, arg = dist2.min(1)
+    else:
+        best, arg = S.max(1)
+    got = D[:nchk, 0].double()
+    scale = torch.maximum(best.abs(), torch.full_like(best, 1e-3))
+    score_ok = bool(((got - best).abs() <= 1e-4 * scale + 1e-6).all())
+    frac_equal = float((I[:nchk, 0] == arg).double().mean())
+    parity_ok = score_ok and frac_equal > 0.995
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        launches += step()
+    ev1.record(stream)
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) / 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev = float(tt.item())
+
+    # end to end: every step copies a bounded slice of points from pinned host memory and reads the assignment back
+    e2e_n = min(n_loc, 2_000_000)
+    pts_host = pts[:e2e_n].cpu().pin_memory()
+    I_host = torch.empty((e2e_n, 1), dtype=torch.int64).pin_memory()
+    D_host = torch.empty((e2e_n, 1), dtype=torch.float32).pin_memory()
+    from proqa_b200 import _lib
+
+    def step_e2e():
+        rc = _lib.lib().pq_index_search(ix._h, e2e_n, ctypes.c_void_p(pts_host.data_ptr()), 1, ctypes.c_void_p(D_host.data_ptr()),
+                                       ctypes.c_void_p(I_host.data_ptr()))
+        _lib.check(rc, "search")
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        step_e2e()
+    barrier()
+    t_e2e = (time.perf_counter() - t0) / max(1, args.steps // 2)
+
+    ix.set_profile(True)
+    kern_us = []
+    for _ in range(2):
+        step()
+        kern_us.append(ix.last_stats[7])
+    ix.set_profile(False)
+    st = ix.last_stats
+    kernel_s = float(np.mean(kern_us)) * 1e-6
+    peaks = load_peaks()
+    flops = 2.0 * n_loc * n_cent * 128
+    long_run = t_dev > 1.0
+    peak = peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]
+    achieved = flops / kernel_s / 1e12 if kernel_s > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "pq_mma_filter_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": f"{peaks['source']} cuBLAS bf16 ({'sustained' if long_run else 'burst'})",
+                "algorithmic": "256 flop per (point,centroid) score", "launches_per_step": int(st[3]), "kernel_ms_per_step": kernel_s * 1e3}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        ns = 200_000
+        xs = pts[:ns].cpu().numpy()
+        fo = oracle.FaissFlatOracle(128, 1 if metric == pq.METRIC_L2 else 0)
+        fo.add(cents.cpu().numpy())
+        t0 = time.perf_counter()
+        fo.search(xs, 1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": ns / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {ns} of {n_points} points x all {n_cent} centroids in {dt:.2f}s; FAISS-1.6.3 restatement (OpenBLAS sgemm + heap), not FAISS"}
+    out = {"metric": "queries_per_sec", "value": (n_points * args.steps / t_dev) if parity_ok else None, "unit": "queries/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "bf16 filter + f32 rescoring", "data": "synthetic",
+           "config": {"workload": wl["desc"], "name": args.workload, "points": n_points, "centroids": n_cent, "d": 128, "k": 1,
+                      "metric": args.metric, "l2_flush": "points streamed per step (%.1f GB) exceed L2" % (n_loc * 512 / 1e9)},
+           "corpus_gbs": n_points * 512 * args.steps / t_dev / 1e9,
+           "e2e": {"value": e2e_n * world / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": e2e_n * 512, "d2h_bytes_per_step": e2e_n * 12,
+                   "sample": f"{e2e_n} points per step per rank through pq_index_search (pinned host in/out)"},
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+           "parity": {"points_checked": nchk, "ok": parity_ok, "ids_equal_frac": frac_equal, "against": "fp64 brute force (torch, checker only)",
+                      "fp32_rerun_queries_per_step": int(st[1])}}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def load_traffic(kernel):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
     try:
@@ -419,7 +612,7 @@ def load_traffic(kernel):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -428,6 +621,7 @@ def main():
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--tier", default=None, choices=[None, "auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--metric", default="l2", choices=["ip", "l2"], help="c4 only (group_paras.py default is L2; --spherical is IP)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     for key in ("rows", "nq", "k"):
@@ -436,6 +630,8 @@ def main():
             wl["desc"] += f" [{key}={wl[key]} override]"
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("kind") == "kmeans":
+        run_kmeans_assign(args, wl)
     else:
         run_ours(args, wl)
 

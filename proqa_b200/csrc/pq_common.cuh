@@ -218,6 +218,30 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// engine_dot computed by one warp: lane l holds dims 4l..4l+3 of both vectors.  Lanes 4j..4j+3 pass chain p_j from lane
+// to lane, then the eight p_j are tree-combined with three butterfly shuffles — the same bits as engine_dot above.
+// Every lane returns the result.
+__device__ __forceinline__ float warp_engine_dot(const float4 a, const float4 b, int lane) {
+    float acc = 0.f;
+#pragma unroll
+    for (int tstep = 0; tstep < 4; ++tstep) {
+        const float in = __shfl_up_sync(0xffffffffu, acc, 1);
+        if ((lane & 3) == tstep) {
+            float x = tstep == 0 ? 0.f : in;
+            x = fmaf(a.x, b.x, x);
+            x = fmaf(a.y, b.y, x);
+            x = fmaf(a.z, b.z, x);
+            x = fmaf(a.w, b.w, x);
+            acc = x;
+        }
+    }
+    acc = __shfl_sync(0xffffffffu, acc, lane | 3);  // p_j to all four lanes of group j
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    return acc;
+}
+
 // Bitonic sort of n (power of two) keys in shared memory by the whole CTA; ascending or descending.
 template <int kThreads>
 __device__ __forceinline__ void block_sort(uint64_t* a, int n, bool ascending) {

@@ -291,11 +291,11 @@ __global__ void pq_scatter_results_kernel(const float* __restrict__ Ds, const lo
 
 static bool tier_uses_mma(const pq_index* ix, int64_t nq, int64_t k) {
     if (ix->has_nonfinite) return false;
-    if (ix->metric != kMetricIP) return false;  // the bf16 filter scores inner products only (L2: fp32 scan)
     if (k > kMmaMaxK) return false;
     if (ix->tier == PQ_TIER_FP32) return false;
     if (ix->tier == PQ_TIER_BF16) return ix->ntotal >= 1;
-    return nq >= kMmaMinQueries && ix->ntotal >= kMmaMinRows;
+    // enough (query,row) pairs to pay for the epoch machinery: a big corpus, or the k-means shape (few centroids, millions of points)
+    return nq >= kMmaMinQueries && (ix->ntotal >= kMmaMinRows || nq * ix->ntotal >= kMmaMinPairs);
 }
 
 // Device-resident search: dq [nq,128] fp32 -> dD [nq,k], dI [nq,k]; all on ix->stream; leaves the stream drained.

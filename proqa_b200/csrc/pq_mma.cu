@@ -42,6 +42,7 @@ constexpr int kAccBufs = 4;         // TMEM accumulators of kSubN columns
 constexpr int kTmemACol = kAccBufs * kSubN;    // first TMEM column of the stationary query operand
 constexpr int kPanelBytes = 128 * 128;         // 128 rows x 128 B (64 bf16): one swizzle-128B K panel
 constexpr int kTileBytes = 2 * kPanelBytes;    // K = 128 -> two panels, 32 KB
+constexpr int kStageBytes = kTileBytes + 1024; // + the tile's 128 squared row norms (L2 only), padded to keep 1024-B alignment
 constexpr int kEpiWarps = 8;
 constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
 constexpr int kMaxMTiles = 4;       // 4 x 64 TMEM columns of bf16 queries + 4 x 64 columns of accumulators = 512
@@ -63,6 +64,7 @@ struct MmaParams {
     const uint16_t* q_bf16;  // [nq_pad][128] bf16 queries (rows beyond nq are zero)
     uint64_t* cand_keys;     // [nq_pad][n_sub][cap]
     uint32_t* cand_cnt;      // [nq_pad][n_sub], zeroed before the launch
+    const float* row_norms;  // [ntotal] squared row norms (L2 only)
     const float* thr;        // [nq_pad]
     const float* two_e;      // [nq_pad]
     long long row_begin;     // multiple of 128
@@ -116,6 +118,25 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r)
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (same mechanism as the tensor-map loads).
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// L2: turn 32 inner products into the engine's ranking score 2<q,x> - |x|^2 (larger = closer).
+__device__ __forceinline__ void mma_apply_l2_bias(float (&v)[32], const float4* norms) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 n = norms[c];
+        v[4 * c + 0] = fmaf(2.f, v[4 * c + 0], -n.x);
+        v[4 * c + 1] = fmaf(2.f, v[4 * c + 1], -n.y);
+        v[4 * c + 2] = fmaf(2.f, v[4 * c + 2], -n.z);
+        v[4 * c + 3] = fmaf(2.f, v[4 * c + 3], -n.w);
+    }
+}
+
 // Threshold filter over 32 accumulator columns held in registers (one thread = one query).
 __device__ __forceinline__ void mma_filter32(const float (&v)[32], float& thr, float two_e, int k1_adapt, uint32_t base_row, uint32_t row_end32,
                                              uint64_t* slab, uint32_t& cnt, uint32_t cap) {
@@ -126,13 +147,42 @@ __device__ __forceinline__ void mma_filter32(const float (&v)[32], float& thr, f
 #pragma unroll
     for (int g = 0; g < 8; ++g) g4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
     const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
+    // k = 1: a score more than 2E below any score already seen (this chunk's maximum included) cannot be the best row
+    if (k1_adapt && base_row + 32 <= row_end32) thr = fmaxf(thr, mx - two_e);
     const float th = thr;
-    if (k1_adapt && base_row + 32 <= row_end32) thr = fmaxf(th, mx - two_e);
     if (mx >= th) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             if (g4[g] >= th)
                 cnt = mma_insert_group4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], th, base_row + 4 * g, row_end32, slab, cnt, cap);
+        }
+    }
+}
+
+// k = 1 variant (k-means assignment: few rows per thread, so "rare" survivors are not rare).  The thread keeps a running
+// maximum; a score more than 2E below any score already seen cannot be the best row.  Survivors are recorded per group
+// of four rows (key = group maximum, first row of the group) with predicated stores — no call, no per-value loop; the
+// finalize kernel rescores the four rows of the few groups that end up within 2E of the overall maximum.
+__device__ __forceinline__ void mma_filter32_k1(float (&v)[32], float& thr, float two_e, uint32_t base_row, uint32_t row_end32, uint64_t* slab,
+                                                uint32_t& cnt, uint32_t cap) {
+    if (base_row + 32 > row_end32) {  // last tile: rows past the end (TMA zero fill, stale norms) must not look like scores
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (base_row + c >= row_end32) v[c] = -INFINITY;
+    }
+    float g4[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) g4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+    const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
+    thr = fmaxf(thr, mx - two_e);
+    const float th = thr;
+    if (mx >= th) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (g4[g] >= th) {
+                if (cnt < cap) slab[cnt] = make_key(g4[g], base_row + 4 * g);
+                ++cnt;
+            }
         }
     }
 }
@@ -143,12 +193,12 @@ __device__ __forceinline__ void mma_filter32(const float (&v)[32], float& thr, f
 // (buffer h*2 + (j & 1), use number j >> 1).  Every buffer is therefore produced and consumed in one fixed order by
 // one fixed set of warps — an mbarrier parity wait can only tell adjacent phases apart, so a consumer must never be
 // able to run two uses ahead of a buffer it shares with someone else.
-template <int M_TILES>
+template <int M_TILES, bool kL2, bool kK1>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* smem_b = smem;                                        // kStages x 32 KB
-    MmaCtrl* ctrl = reinterpret_cast<MmaCtrl*>(smem_b + (size_t)kStages * kTileBytes);
+    uint8_t* smem_b = smem;                                        // kStages x (32 KB tile + norms)
+    MmaCtrl* ctrl = reinterpret_cast<MmaCtrl*>(smem_b + (size_t)kStages * kStageBytes);
 
     // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role code below (barrier
     // addresses, descriptors, loop counters) in uniform registers — the tcgen05.mma issue path is a handful of uniform
@@ -186,7 +236,8 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) {
                 mbar_init(&ctrl->full[s], 1);
-                mbar_init(&ctrl->empty[s], 1);
+                // L2: the epilogue reads the stage's row norms, so the stage is only free once it has let go as well
+                mbar_init(&ctrl->empty[s], kL2 ? 1 + kEpiWarps : 1);
             }
             for (int b = 0; b < kAccBufs; ++b) {
                 mbar_init(&ctrl->tmem_full[b], 1);
@@ -237,11 +288,12 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
             const uint32_t ph = (uint32_t)(t / kStages) & 1u;
             mbar_wait(&ctrl->empty[s], ph ^ 1u);
             if (elect_one()) {
-                mbar_arrive_expect_tx(&ctrl->full[s], kTileBytes);
+                mbar_arrive_expect_tx(&ctrl->full[s], kTileBytes + (kL2 ? kBN * 4 : 0));
                 const int y = (int)(row0 + (long long)t * kBN);
 #pragma unroll
                 for (int pnl = 0; pnl < 2; ++pnl)
-                    tma_load_2d(smem_b + (size_t)s * kTileBytes + pnl * kPanelBytes, &tmap_c, pnl * 64, y, &ctrl->full[s]);
+                    tma_load_2d(smem_b + (size_t)s * kStageBytes + pnl * kPanelBytes, &tmap_c, pnl * 64, y, &ctrl->full[s]);
+                if (kL2) bulk_load_1d(smem_b + (size_t)s * kStageBytes + kTileBytes, p.row_norms + y, kBN * 4, &ctrl->full[s]);
             }
             __syncwarp();
         }
@@ -265,7 +317,7 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
                 tc_fence_after_sync();
                 if (elect_one()) {
                     const uint32_t a_tmem = (uint32_t)(kTmemACol + mi * 64);
-                    const uint32_t tile_addr = b_addr + (uint32_t)s * kTileBytes;
+                    const uint32_t tile_addr = b_addr + (uint32_t)s * kStageBytes;
                     // the two row halves accumulate into different TMEM buffers: interleaving them keeps two independent
                     // accumulation chains in the tensor pipe
 #pragma unroll
@@ -307,6 +359,9 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
             const uint32_t base_row = (uint32_t)(row0 + (long long)t * kBN + set * kSubN);
+            const int s = t % kStages;
+            const float4* norms = reinterpret_cast<const float4*>(smem_b + (size_t)s * kStageBytes + kTileBytes) + set * (kSubN / 4);
+            if (kL2) mbar_wait(&ctrl->full[s], (uint32_t)(t / kStages) & 1u);  // already complete (the MMAs needed it): acquire only
 #pragma unroll
             for (int mi = 0; mi < M_TILES; ++mi) {
                 if (mi < m) {
@@ -324,8 +379,21 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);
-                    mma_filter32(v0, thr[mi], two_e[mi], p.k1_adapt, base_row, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
-                    mma_filter32(v1, thr[mi], two_e[mi], p.k1_adapt, base_row + 32, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
+                    if (kL2) {
+                        mma_apply_l2_bias(v0, norms);
+                        mma_apply_l2_bias(v1, norms + 8);
+                        if (mi == m - 1) {  // last read of this stage's norms by this warp
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&ctrl->empty[s]);
+                        }
+                    }
+                    if (kK1) {
+                        mma_filter32_k1(v0, thr[mi], two_e[mi], base_row, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
+                        mma_filter32_k1(v1, thr[mi], two_e[mi], base_row + 32, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
+                    } else {
+                        mma_filter32(v0, thr[mi], two_e[mi], 0, base_row, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
+                        mma_filter32(v1, thr[mi], two_e[mi], 0, base_row + 32, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
+                    }
                 }
             }
         }
@@ -358,12 +426,14 @@ struct QState {
 };
 
 __global__ void pq_mma_init_state_kernel(QState st, const float* __restrict__ q_norm2, const uint8_t* __restrict__ q_bad, int nq,
-                                         int nq_pad, int kp, float max_norm2) {
+                                         int nq_pad, int kp, float max_norm2, int metric) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq_pad) return;
     const bool live = q < nq && !q_bad[q];
     // 2E with E = eps * |q| * max|c|; sqrt rounded up by the head-room in kEps
-    const float e2 = live ? 2.f * kEps * sqrtf(q_norm2[q]) * sqrtf(max_norm2) : 0.f;
+    float e2 = live ? 2.f * kEps * sqrtf(q_norm2[q]) * sqrtf(max_norm2) : 0.f;
+    // L2 ranks by 2<q,x> - |x|^2: twice the inner-product error, plus the fp32 rounding of that fmaf on both sides
+    if (metric == kMetricL2) e2 = 2.f * e2 + 4.8e-7f * (2.f * sqrtf(q_norm2[q]) * sqrtf(max_norm2) + max_norm2);
     st.two_e[q] = e2;
     st.thr[q] = live ? PQ_THR_FLOOR : INFINITY;
     st.dropmax[q] = -INFINITY;
@@ -540,6 +610,91 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k = 1 (k-means assignment, group_paras.py:45,51): one warp per query folds its slabs directly — no carry list,
+// no sort.  The slabs hold one record per group of four rows whose best bf16 score was within 2E of the best score its
+// thread had seen, so the exact best row sits in a group within 2E of the overall best bf16 score; the rows of those
+// (typically 1-3) groups are rescored with the engine's defined fp32 score by the whole warp (coalesced 512-B reads).
+// ------------------------------------------------------------------------------------------------
+struct K1Params {
+    const uint64_t* cand_keys;
+    const uint32_t* cand_cnt;
+    const float* two_e;
+    const float* queries;    // [nq][128] fp32
+    const float* rows;       // [ntotal][128] fp32
+    const float* row_norms;
+    const float* q_norms;
+    const uint8_t* q_bad;
+    int nq, n_sub, cap, metric;
+    long long n_rows;
+    long long id_base;
+    float* D;
+    long long* I;
+    uint8_t* fail;
+};
+
+__global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= p.nq) return;
+    const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
+    const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
+    bool fail = p.q_bad[q] != 0;
+    // pass 1: best bf16 score over all candidates
+    uint32_t best_hi = 0;
+    for (int s = 0; s < p.n_sub; ++s) {
+        const uint32_t c = cnts[s];
+        if (c > (uint32_t)p.cap) fail = true;
+        const int n = (int)min(c, (uint32_t)p.cap);
+        for (int i = lane; i < n; i += 32) best_hi = max(best_hi, (uint32_t)(keys[(size_t)s * p.cap + i] >> 32));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best_hi = max(best_hi, __shfl_xor_sync(0xffffffffu, best_hi, o));
+    uint64_t best = 0ull;
+    if (best_hi != 0 && !fail) {
+        const float bar = ordered_to_f32(best_hi) - p.two_e[q];
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
+        // pass 2: exact score of every candidate within 2E of the best
+        for (int s = 0; s < p.n_sub; ++s) {
+            const int n = (int)min(cnts[s], (uint32_t)p.cap);
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const uint64_t key = i < n ? keys[(size_t)s * p.cap + i] : 0ull;
+                unsigned live = __ballot_sync(0xffffffffu, key != 0ull && key_score(key) >= bar);
+                while (live) {
+                    const int src = __ffs(live) - 1;
+                    live &= live - 1;
+                    const uint32_t row0 = key_row(__shfl_sync(0xffffffffu, key, src));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t row = row0 + j;
+                        if ((long long)row >= p.n_rows) break;
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(p.rows + (size_t)row * kDim) + lane);
+                        float sc = warp_engine_dot(rv, qv, lane);
+                        if (p.metric == kMetricL2) sc = fmaf(2.f, sc, -__ldg(p.row_norms + row));
+                        if (sc >= PQ_THR_FLOOR) best = max(best, make_key(sc, row));
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        float d;
+        long long id;
+        if (best == 0ull) {
+            id = -1;
+            d = (p.metric == kMetricL2) ? FLT_MAX : -FLT_MAX;
+        } else {
+            id = (long long)key_row(best) + p.id_base;
+            const float sc = key_score(best);
+            d = (p.metric == kMetricL2) ? fmaxf(0.f, p.q_norms[q] - sc) : sc;
+        }
+        p.D[q] = d;
+        p.I[q] = id;
+        p.fail[q] = fail ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
 static int next_pow2i(int v) {
@@ -548,13 +703,23 @@ static int next_pow2i(int v) {
     return p;
 }
 
-template <int M>
+template <int M, bool L2, bool K1>
 static cudaError_t launch_filter(const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
-    const size_t smem = (size_t)kStages * kTileBytes + sizeof(MmaCtrl);
-    cudaError_t e = cudaFuncSetAttribute(pq_mma_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)kStages * kStageBytes + sizeof(MmaCtrl);
+    cudaError_t e = cudaFuncSetAttribute(pq_mma_filter_kernel<M, L2, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pq_mma_filter_kernel<M><<<n_ctas, kMmaThreads, smem, stream>>>(tc, p);
+    pq_mma_filter_kernel<M, L2, K1><<<n_ctas, kMmaThreads, smem, stream>>>(tc, p);
     return cudaGetLastError();
+}
+template <bool L2, bool K1>
+static cudaError_t launch_filter_m(int m_max, const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
+    if (m_max == 1) return launch_filter<1, L2, K1>(tc, p, n_ctas, stream);
+    if (m_max == 2) return launch_filter<2, L2, K1>(tc, p, n_ctas, stream);
+    return launch_filter<4, L2, K1>(tc, p, n_ctas, stream);
+}
+static cudaError_t launch_filter_any(int m_max, bool l2, bool k1, const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
+    if (l2) return k1 ? launch_filter_m<true, true>(m_max, tc, p, n_ctas, stream) : launch_filter_m<true, false>(m_max, tc, p, n_ctas, stream);
+    return k1 ? launch_filter_m<false, true>(m_max, tc, p, n_ctas, stream) : launch_filter_m<false, false>(m_max, tc, p, n_ctas, stream);
 }
 
 struct EpochPlan {
@@ -581,13 +746,16 @@ static void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n
         b = (long long)n_sms * g.base / n_mtiles;
         if (g.rem == 0) a = b;
     } else {
-        double best = 0.0;
+        // more groups than SMs: several waves.  Cost of c slices per group = waves x (row tiles per CTA + a fixed per-CTA
+        // cost — TMEM allocation, query staging, pipeline fill and drain — worth about 6 row tiles)
+        double best = 1e300;
         a = 1;
-        for (int c = 1; c <= 8; ++c) {
+        for (int c = 1; c <= 8 && c <= tiles; ++c) {
             const long long ctas = (long long)g.n_groups * c;
-            const double eff = (double)ctas / ((double)n_sms * (double)((ctas + n_sms - 1) / n_sms));
-            if (eff > best + 1e-9) {
-                best = eff;
+            const double waves = (double)((ctas + n_sms - 1) / n_sms);
+            const double cost = waves * ((double)((tiles + c - 1) / c) + 6.0);
+            if (cost < best - 1e-9) {
+                best = cost;
                 a = c;
             }
         }
@@ -604,7 +772,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
     const long long N = ix->ntotal;
     const int kp = carry_size_for_k(k);
     const bool k1 = (k == 1);
-    constexpr int kMaxBatch = 262144;  // queries per pass (bounds the candidate slabs)
+    const int kMaxBatch = k1 ? (1 << 20) : (1 << 18);  // queries per pass (bounds the candidate slabs)
 
     for (int qb = 0; qb < nq_total; qb += kMaxBatch) {
         const int nq = std::min(kMaxBatch, nq_total - qb);
@@ -628,7 +796,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             ep.begin = 0;
             ep.end = N;
             pick_slices(gs, n_mtiles, (N + kBN - 1) / kBN, ix->n_sms, &ep.s1, &ep.s0);
-            ep.cap = 128;
+            ep.cap = 64;  // a thread keeps only rows within 2E of its running maximum: a few dozen at most
             plan.push_back(ep);
         } else {
             const long long n0 = std::min<long long>(N, std::max(1024, next_pow2i(2 * kp)));
@@ -677,8 +845,8 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         st.overflow = (uint32_t*)w[3].p;
         st.carry = (uint64_t*)w[4].p;
 
-        PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
-        pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, dq_bad, nq, nq_pad, kp, ix->max_norm2);
+        if (!k1) PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
+        pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, dq_bad, nq, nq_pad, kp, ix->max_norm2, ix->metric);
         PQ_CUDA(cudaGetLastError());
         ix->stats[5] += 1;
 
@@ -688,6 +856,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.q_bf16 = dq_bf16;
             mp.cand_keys = (uint64_t*)w[5].p;
             mp.cand_cnt = (uint32_t*)w[6].p;
+            mp.row_norms = (const float*)ix->norms.p;
             mp.thr = st.thr;
             mp.two_e = st.two_e;
             mp.row_begin = ep.begin;
@@ -703,13 +872,37 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             const int n_ctas = gs.rem * ep.s1 + (gs.n_groups - gs.rem) * ep.s0;
             // slabs a CTA never touches (unequal slice counts, query tiles owned by the other warp set) must read as empty
             PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
-            cudaError_t e;
             ix->prof_begin();
-            if (gs.m_max == 1) e = launch_filter<1>(ix->tmap_bf16, mp, n_ctas, ix->stream);
-            else if (gs.m_max == 2) e = launch_filter<2>(ix->tmap_bf16, mp, n_ctas, ix->stream);
-            else e = launch_filter<4>(ix->tmap_bf16, mp, n_ctas, ix->stream);
+            const cudaError_t e = launch_filter_any(gs.m_max, ix->metric == kMetricL2, k1, ix->tmap_bf16, mp, n_ctas, ix->stream);
             ix->prof_end();
             PQ_CUDA(e);
+            ix->stats[3] += 1;
+            ix->stats[5] += 1;
+            if (k1) {  // single pass: fold the slabs straight into (D, I)
+                K1Params kp1;
+                kp1.cand_keys = mp.cand_keys;
+                kp1.cand_cnt = mp.cand_cnt;
+                kp1.two_e = st.two_e;
+                kp1.queries = dq;
+                kp1.rows = (const float*)ix->rows_f32.p;
+                kp1.row_norms = (const float*)ix->norms.p;
+                kp1.q_norms = dq_norm;
+                kp1.q_bad = dq_bad;
+                kp1.nq = nq;
+                kp1.n_sub = mp.n_sub;
+                kp1.cap = ep.cap;
+                kp1.metric = ix->metric;
+                kp1.n_rows = N;
+                kp1.id_base = ix->id_base;
+                kp1.D = dD_all + (size_t)qb;
+                kp1.I = dI_all + (size_t)qb;
+                kp1.fail = (uint8_t*)w[7].p;
+                pq_k1_finalize_kernel<<<(nq + 7) / 8, 256, 0, ix->stream>>>(kp1);
+                PQ_CUDA(cudaGetLastError());
+                ix->stats[4] += 1;
+                ix->stats[5] += 1;
+                continue;
+            }
 
             EpochSelParams sp;
             sp.st = st;
@@ -724,12 +917,12 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             PQ_CUDA(cudaFuncSetAttribute(pq_epoch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
             PQ_CUDA(cudaGetLastError());
-            ix->stats[3] += 1;
             ix->stats[4] += 1;
-            ix->stats[5] += 2;
+            ix->stats[5] += 1;
         }
 
         // ---- exact rescoring + certificate ------------------------------------------------------
+        if (!k1) {
         RescoreParams rp;
         rp.st = st;
         rp.queries = dq;
@@ -751,6 +944,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         PQ_CUDA(cudaGetLastError());
         ix->stats[4] += 1;
         ix->stats[5] += 1;
+        }
 
         std::vector<uint8_t> fail((size_t)nq);
         PQ_CUDA(cudaMemcpyAsync(fail.data(), w[7].p, (size_t)nq, cudaMemcpyDeviceToHost, ix->stream));

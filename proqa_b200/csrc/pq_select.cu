@@ -188,25 +188,7 @@ __global__ void __launch_bounds__(256) pq_prep_rows_kernel(const float* __restri
         *reinterpret_cast<uint2*>(rows_bf16 + row * kDim + lane * 4) = packed;
         // non-finite after rounding (covers inf/NaN inputs and fp32 values that overflow bf16)
         const float bx = __low2float(lo), by = __high2float(lo), bz = __low2float(hi), bw = __high2float(hi);
-        // squared norm = engine_dot(row, row): lanes 4j..4j+3 carry chain p_j (16 dims) from lane to lane, then the
-        // eight p_j are tree-combined with three butterfly shuffles (same bits as pq_common.cuh: engine_dot)
-        float acc = 0.f;
-#pragma unroll
-        for (int tstep = 0; tstep < 4; ++tstep) {
-            const float in = __shfl_up_sync(0xffffffffu, acc, 1);
-            if ((lane & 3) == tstep) {
-                float a = tstep == 0 ? 0.f : in;
-                a = fmaf(v.x, v.x, a);
-                a = fmaf(v.y, v.y, a);
-                a = fmaf(v.z, v.z, a);
-                a = fmaf(v.w, v.w, a);
-                acc = a;
-            }
-        }
-        acc = __shfl_sync(0xffffffffu, acc, lane | 3);  // p_j to all four lanes of group j
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        const float acc = warp_engine_dot(v, v, lane);  // squared norm = engine_dot(row, row)
         if (lane == 0) norms[row] = acc;
         bool row_is_bad = !(isfinite(bx) && isfinite(by) && isfinite(bz) && isfinite(bw));
         row_is_bad = __any_sync(0xffffffffu, row_is_bad) || !(acc <= FLT_MAX);  // inf or NaN norm

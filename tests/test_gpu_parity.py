@@ -53,6 +53,20 @@ def test_bf16_tier_bit_exact(nq, nb, k, kind):
     assert st[3] > 0, "tensor-core filter did not run"
 
 
+@pytest.mark.parametrize("nq,nb,k,kind", [(300, 40000, 10, "normal"), (1000, 20000, 1, "normal"), (130, 30000, 80, "skewed"),
+                                           (128, 50000, 100, "fp16"), (600, 16500, 1, "unit")])
+def test_bf16_tier_l2_bit_exact(nq, nb, k, kind):
+    """IndexFlatL2 (group_paras.py:38, the k-means default) on the tensor-core tier: ranking score 2<q,x> - |x|^2."""
+    xb, xq = data.corpus(nb, kind=kind), data.queries(nq, kind=kind)
+    ix = _index(1, xb, "bf16")
+    D, I = ix.search(xq, k)
+    Dr, Ir = oracle.engine_spec(xq, xb, k, 1)
+    _assert_bit_exact(D, I, Dr, Ir)
+    st = ix.last_stats
+    assert st[3] > 0, "tensor-core filter did not run"
+    assert not oracle.check_against_truth(D[:64], I[:64], xq[:64], xb, k, 1)
+
+
 def test_tiers_agree_and_match_truth():
     xb, xq = data.corpus(200000), data.queries(256)
     res = {}
@@ -169,10 +183,11 @@ def test_kmeans_assignment_shape_l2_and_ip():
     cents = data.corpus(1000, seed=7)
     pts = data.queries(20000, seed=8)
     for metric in (0, 1):
-        ix = _index(metric, cents, "auto")
-        D, I = ix.search(pts, 1)
         Dr, Ir = oracle.engine_spec(pts, cents, 1, metric)
-        _assert_bit_exact(D, I, Dr, Ir)
+        for tier in ("auto", "bf16"):
+            ix = _index(metric, cents, tier)
+            D, I = ix.search(pts, 1)
+            _assert_bit_exact(D, I, Dr, Ir)
 
 
 def test_id_base_offsets_ids():
