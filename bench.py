@@ -386,6 +386,26 @@ def run_ours(args, wl):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.item())
 
+    # ---- phase breakdown of one multi-GPU step (CUDA events on the launching stream; diagnostic) ----
+    phases = None
+    if world > 1:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = [0.0, 0.0, 0.0]
+        for _ in range(3):
+            barrier()
+            evs[0].record(stream)
+            ix.search_device(q.data_ptr(), nq, k, D_loc.data_ptr(), I_loc.data_ptr())
+            evs[1].record(stream)
+            dist.all_gather_into_tensor(D_all.view(world * nq, k), D_loc)
+            dist.all_gather_into_tensor(I_all.view(world * nq, k), I_loc)
+            evs[2].record(stream)
+            sh._merge_device(D_all, I_all, nq, k, D_out, I_out)
+            evs[3].record(stream)
+            torch.cuda.synchronize()
+            for j in range(3):
+                acc[j] += evs[j].elapsed_time(evs[j + 1]) / 3.0
+        phases = {"local_search_ms": acc[0], "all_gather_ms": acc[1], "merge_ms": acc[2]}
+
     # ---- dominant-kernel time (CUDA events around the kernel on its launching stream) --------------
     ix.set_profile(True)
     kern_us = []
@@ -437,6 +457,7 @@ def run_ours(args, wl):
         "parity": {"queries_checked": nchk, "ok": parity_ok, "ids_equal_frac": frac_equal, "against": "fp64 brute force (torch, checker only)",
                    "fp32_rerun_queries_per_step": rerun_q / max(1, args.steps)},
         "index_build_s": t_build,
+        "multi_gpu_phases": phases,
     }
     if not parity_ok:
         out["error"] = "parity gate failed: no speed reported"

@@ -96,6 +96,11 @@ int pq_index_last_stats(const pq_index* idx, int64_t* out, int n);
 int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists_dev,
                            const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev);
 
+/* Same, enqueued on the caller's CUDA stream (cudaStream_t as void*) without any device synchronisation: the all-gather
+ * that produced the lists and the consumer of the result are ordered by that stream. */
+int pq_merge_shard_results_async(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists_dev,
+                                 const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev, void* cuda_stream);
+
 const char* pq_last_error(void);
 /* "proqa_b200 <version> sm_100a" */
 const char* pq_version(void);

@@ -39,6 +39,8 @@ SIGNATURES = {
     "pq_index_last_stats": (ctypes.c_int, [_vp, _i64p, ctypes.c_int]),
     "pq_merge_shard_results": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp,
                                               _vp, _vp]),
+    "pq_merge_shard_results_async": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp,
+                                                    _vp, _vp, _vp]),
     "pq_last_error": (ctypes.c_char_p, []),
     "pq_version": (ctypes.c_char_p, []),
 }

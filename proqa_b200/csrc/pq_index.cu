@@ -98,6 +98,12 @@ void DevBuf::release() {
 }
 
 static int pick_device(int requested, int* out) {
+    // cudaGetDeviceProperties costs milliseconds: validate each ordinal once per process
+    static int validated[64];
+    if (requested >= 0 && requested < 64 && validated[requested]) {
+        *out = requested;
+        return PQ_OK;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -121,6 +127,7 @@ static int pick_device(int requested, int* out) {
     if (prop.major != 10)
         return set_error(PQ_ERR_NO_DEVICE, "device %d is sm_%d%d; proqa_b200 only runs on sm_100 (B200) and has no fallback", dev,
                          prop.major, prop.minor);
+    if (dev < 64) validated[dev] = 1;
     *out = dev;
     return PQ_OK;
 }
@@ -503,20 +510,28 @@ int pq_index_last_stats(const pq_index* ix, int64_t* out, int n) {
     return PQ_OK;
 }
 
-int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists, const int64_t* I_lists,
-                           float* D_out, int64_t* I_out) {
+static int merge_shard_results_impl(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists, const int64_t* I_lists,
+                                    float* D_out, int64_t* I_out, cudaStream_t stream, bool sync) {
     if (n_lists < 1 || nq < 0 || k < 1 || !D_lists || !I_lists || !D_out || !I_out)
         return set_error(PQ_ERR_INVALID, "merge_shard_results: bad arguments");
     if ((int64_t)n_lists * k > 16384) return set_error(PQ_ERR_UNSUPPORTED, "merge_shard_results: n_lists*k=%lld > 16384", (long long)(n_lists * k));
     int dev = -1;
     int rc = pick_device(device, &dev);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lock(g_device_mutex);
     PQ_CUDA(cudaSetDevice(dev));
-    PQ_CUDA(cudaDeviceSynchronize());
-    PQ_CUDA(merge_di_launch(D_lists, (const long long*)I_lists, n_lists, (int)nq, (int)k, metric, D_out, (long long*)I_out, 0));
-    PQ_CUDA(cudaDeviceSynchronize());
+    if (sync) PQ_CUDA(cudaDeviceSynchronize());
+    PQ_CUDA(merge_di_launch(D_lists, (const long long*)I_lists, n_lists, (int)nq, (int)k, metric, D_out, (long long*)I_out, stream));
+    if (sync) PQ_CUDA(cudaDeviceSynchronize());
     return PQ_OK;
+}
+
+int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists, const int64_t* I_lists,
+                           float* D_out, int64_t* I_out) {
+    return merge_shard_results_impl(device, metric, n_lists, nq, k, D_lists, I_lists, D_out, I_out, 0, true);
+}
+int pq_merge_shard_results_async(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists, const int64_t* I_lists,
+                                 float* D_out, int64_t* I_out, void* cuda_stream) {
+    return merge_shard_results_impl(device, metric, n_lists, nq, k, D_lists, I_lists, D_out, I_out, (cudaStream_t)cuda_stream, false);
 }
 
 const char* pq_last_error(void) { return g_err; }

@@ -121,9 +121,11 @@ class ShardedIndexFlat:
         return D_out, I_out
 
     def _merge_device(self, D_all, I_all, nq, k, D_out, I_out):
+        """Merge kernel on torch's current stream: ordered after the all-gather, no host synchronisation."""
         import torch
-        torch.cuda.current_stream().synchronize()
-        rc = _lib.lib().pq_merge_shard_results(D_all.device.index, self.metric_type, self.world, nq, k,
-                                               ctypes.c_void_p(D_all.data_ptr()), ctypes.c_void_p(I_all.data_ptr()),
-                                               ctypes.c_void_p(D_out.data_ptr()), ctypes.c_void_p(I_out.data_ptr()))
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _lib.lib().pq_merge_shard_results_async(D_all.device.index, self.metric_type, self.world, nq, k,
+                                                     ctypes.c_void_p(D_all.data_ptr()), ctypes.c_void_p(I_all.data_ptr()),
+                                                     ctypes.c_void_p(D_out.data_ptr()), ctypes.c_void_p(I_out.data_ptr()),
+                                                     ctypes.c_void_p(stream))
         _lib.check(rc, "merge_shard_results")
