@@ -101,6 +101,24 @@ int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int6
 int pq_merge_shard_results_async(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists_dev,
                                  const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev, void* cuda_stream);
 
+/* faiss.Clustering(d, k) ... clus.train(x, index)  — retrieval/group_paras.py:40-45 (FAISS 1.6.3 Clustering.cpp semantics).
+ * Fields mirror the ClusteringParameters the script sets (verbose :41, niter :42, max_points_per_centroid :43) plus the
+ * FAISS defaults it leaves alone.  `index` is the IndexFlatL2 / IndexFlatIP the script built (:35-38); on return it holds
+ * the final centroids (as after FAISS's last index.add).  centroids_out: [k*d] floats; obj_out (optional): one objective
+ * per iteration, at most obj_cap of them, *n_obj receives how many iterations ran. */
+typedef struct pq_kmeans_params {
+    int niter;                   /* 25   */
+    int nredo;                   /* 1    */
+    int verbose;                 /* 0    */
+    int spherical;               /* 0: centroids L2-normalised after each iteration when set */
+    int min_points_per_centroid; /* 39   */
+    int max_points_per_centroid; /* 256: above k*this many points the training set is subsampled */
+    int64_t seed;                /* 1234 */
+} pq_kmeans_params;
+void pq_kmeans_default_params(pq_kmeans_params* p);
+int pq_kmeans_train(pq_index* index, int64_t k, const pq_kmeans_params* params, int64_t n, const float* x_host, float* centroids_out,
+                    float* obj_out, int64_t obj_cap, int64_t* n_obj);
+
 const char* pq_last_error(void);
 /* "proqa_b200 <version> sm_100a" */
 const char* pq_version(void);

@@ -256,3 +256,147 @@ void engine_flat_search(const float* xq, int64_t nq, const float* xb, int64_t nb
     }
     free(nb2);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * faiss.Clustering.train restated (FAISS 1.6.3 Clustering.cpp / utils/random.cpp) [upstream-memory: the source is the
+ * un-vendored wheel; reference call site retrieval/group_paras.py:40-45].  Assignment = faiss_flat_search(x, 1) above.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint32_t mt[624];
+    int idx;
+} mt19937_t; /* std::mt19937 */
+static void mt_seed(mt19937_t* g, uint32_t seed) {
+    g->mt[0] = seed;
+    for (int i = 1; i < 624; ++i) g->mt[i] = 1812433253u * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + (uint32_t)i;
+    g->idx = 624;
+}
+static uint32_t mt_next(mt19937_t* g) {
+    if (g->idx >= 624) {
+        for (int i = 0; i < 624; ++i) {
+            const uint32_t y = (g->mt[i] & 0x80000000u) | (g->mt[(i + 1) % 624] & 0x7fffffffu);
+            g->mt[i] = g->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        g->idx = 0;
+    }
+    uint32_t y = g->mt[g->idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+/* RandomGenerator::rand_int(max) = mt() % max ; rand_float() = mt() / float(mt.max()) */
+static void faiss_rand_perm(int* perm, int64_t n, int64_t seed) {
+    mt19937_t g;
+    for (int64_t i = 0; i < n; ++i) perm[i] = (int)i;
+    mt_seed(&g, (uint32_t)seed);
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        const int64_t i2 = i + (int64_t)(mt_next(&g) % (uint32_t)(n - i));
+        const int t = perm[i];
+        perm[i] = perm[i2];
+        perm[i2] = t;
+    }
+}
+void faiss_rand_perm_export(int* perm, int64_t n, int64_t seed) { faiss_rand_perm(perm, n, seed); }
+
+static void renorm_l2(int d, int64_t k, float* c) {
+    for (int64_t i = 0; i < k; ++i) {
+        float nr = 0.f;
+        for (int j = 0; j < d; ++j) nr += c[i * d + j] * c[i * d + j];
+        if (nr > 0.f) {
+            const float inv = 1.0f / sqrtf(nr);
+            for (int j = 0; j < d; ++j) c[i * d + j] *= inv;
+        }
+    }
+}
+
+/* km_update_centroids: per-centroid sums in point order (fp32), mean, then void clusters split a populated one. */
+static int km_update_centroids(const float* x, float* centroids, const int64_t* assign, int d, int64_t k, int64_t n, int64_t* hassign) {
+    memset(centroids, 0, sizeof(float) * (size_t)(d * k));
+    memset(hassign, 0, sizeof(int64_t) * (size_t)k);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t ci = assign[i];
+        float* c = centroids + ci * d;
+        const float* xi = x + i * d;
+        hassign[ci]++;
+        for (int j = 0; j < d; ++j) c[j] += xi[j];
+    }
+    for (int64_t ci = 0; ci < k; ++ci) {
+        float* c = centroids + ci * d;
+        const float ni = (float)hassign[ci];
+        if (ni != 0)
+            for (int j = 0; j < d; ++j) c[j] /= ni;
+    }
+    int nsplit = 0;
+    const float EPS = 1.f / 1024.f;
+    mt19937_t rng;
+    mt_seed(&rng, 1234);
+    for (int64_t ci = 0; ci < k; ++ci) {
+        if (hassign[ci] != 0) continue;
+        int64_t cj;
+        for (cj = 0; 1; cj = (cj + 1) % k) {
+            const float p = (hassign[cj] - 1.0) / (float)(n - k);
+            const float r = mt_next(&rng) / 4294967296.0f; /* float(mt.max()) rounds to 2^32 */
+            if (r < p) break;
+        }
+        memcpy(centroids + ci * d, centroids + cj * d, sizeof(float) * (size_t)d);
+        for (int j = 0; j < d; ++j) {
+            if (j % 2 == 0) {
+                centroids[ci * d + j] *= 1 + EPS;
+                centroids[cj * d + j] *= 1 - EPS;
+            } else {
+                centroids[ci * d + j] *= 1 - EPS;
+                centroids[cj * d + j] *= 1 + EPS;
+            }
+        }
+        hassign[ci] = hassign[cj] / 2;
+        hassign[cj] -= hassign[ci];
+        nsplit++;
+    }
+    return nsplit;
+}
+
+/* Returns the number of iterations run; obj_out[it] = sum of the k=1 distances, nsplit_out[it] = clusters split. */
+int faiss_kmeans_train(const float* x_in, int64_t n_in, int d, int64_t k, int niter, int spherical, int max_points_per_centroid, int64_t seed,
+                       int metric, float* centroids, float* obj_out, int* nsplit_out, int64_t* assign_last) {
+    int64_t nx = n_in;
+    const float* x = x_in;
+    float* x_new = NULL;
+    if (n_in > k * (int64_t)max_points_per_centroid) {
+        int* perm = (int*)malloc(sizeof(int) * (size_t)n_in);
+        faiss_rand_perm(perm, n_in, seed);
+        nx = k * (int64_t)max_points_per_centroid;
+        x_new = (float*)malloc(sizeof(float) * (size_t)(nx * d));
+        for (int64_t i = 0; i < nx; ++i) memcpy(x_new + i * d, x_in + (int64_t)perm[i] * d, sizeof(float) * (size_t)d);
+        x = x_new;
+        free(perm);
+    }
+    if (nx == k) {
+        memcpy(centroids, x, sizeof(float) * (size_t)(k * d));
+        free(x_new);
+        return 0;
+    }
+    int64_t* assign = (int64_t*)malloc(sizeof(int64_t) * (size_t)nx);
+    float* dis = (float*)malloc(sizeof(float) * (size_t)nx);
+    int64_t* hassign = (int64_t*)malloc(sizeof(int64_t) * (size_t)k);
+    int* perm = (int*)malloc(sizeof(int) * (size_t)nx);
+    faiss_rand_perm(perm, nx, seed + 1);
+    for (int64_t i = 0; i < k; ++i) memcpy(centroids + i * d, x + (int64_t)perm[i] * d, sizeof(float) * (size_t)d);
+    if (spherical) renorm_l2(d, k, centroids);
+    for (int it = 0; it < niter; ++it) {
+        faiss_flat_search(x, nx, centroids, k, d, 1, metric, dis, assign);
+        float err = 0;
+        for (int64_t j = 0; j < nx; ++j) err += dis[j];
+        if (obj_out) obj_out[it] = err;
+        const int nsplit = km_update_centroids(x, centroids, assign, d, k, nx, hassign);
+        if (nsplit_out) nsplit_out[it] = nsplit;
+        if (spherical) renorm_l2(d, k, centroids);
+    }
+    if (assign_last) memcpy(assign_last, assign, sizeof(int64_t) * (size_t)(nx < n_in ? nx : n_in));
+    free(assign);
+    free(dis);
+    free(hassign);
+    free(perm);
+    free(x_new);
+    return niter;
+}

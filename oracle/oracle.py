@@ -68,6 +68,10 @@ def _lib():
         L.engine_flat_search.restype = None
         L.engine_chain_dot.argtypes = [f32p, f32p, i32]
         L.engine_chain_dot.restype = ctypes.c_float
+        L.faiss_kmeans_train.argtypes = [f32p, i64, i32, i64, i32, i32, i32, i64, i32, f32p, f32p, ctypes.POINTER(ctypes.c_int), i64p]
+        L.faiss_kmeans_train.restype = i32
+        L.faiss_rand_perm_export.argtypes = [ctypes.POINTER(ctypes.c_int), i64, i64]
+        L.faiss_rand_perm_export.restype = None
         _LIB = L
     return _LIB
 
@@ -174,6 +178,43 @@ def IndexFlatIP(d):
 
 def IndexFlatL2(d):
     return FaissFlatOracle(d, METRIC_L2)
+
+
+# ------------------------------------------------------------------------------------------------
+# faiss.Clustering restated (group_paras.py:40-47)
+# ------------------------------------------------------------------------------------------------
+def rand_perm(n, seed):
+    """faiss::rand_perm: Fisher-Yates driven by std::mt19937(seed) % (n - i)."""
+    perm = np.empty(n, dtype=np.int32)
+    _lib().faiss_rand_perm_export(_p(perm, ctypes.c_int), n, seed)
+    return perm
+
+
+class FaissClusteringOracle:
+    """faiss.Clustering(d, k) with the attributes group_paras.py sets; train(x, index) leaves the centroids in
+    ``centroids`` (flat, k*d) and in ``index`` (reset + add), the per-iteration objective in ``obj``."""
+
+    def __init__(self, d, k):
+        self.d, self.k = int(d), int(k)
+        self.niter, self.nredo, self.verbose, self.spherical = 25, 1, False, False
+        self.min_points_per_centroid, self.max_points_per_centroid, self.seed = 39, 256, 1234
+        self.centroids = np.zeros(0, np.float32)
+        self.obj = np.zeros(0, np.float32)
+        self.nsplit = np.zeros(0, np.int32)
+
+    def train(self, x, index):
+        x = _f32(x)
+        n, d = x.shape
+        assert d == self.d and n >= self.k
+        cent = np.empty(self.k * d, np.float32)
+        obj = np.zeros(max(1, self.niter), np.float32)
+        nsplit = np.zeros(max(1, self.niter), np.int32)
+        nit = _lib().faiss_kmeans_train(_p(x, ctypes.c_float), n, d, self.k, int(self.niter), int(bool(self.spherical)),
+                                        int(self.max_points_per_centroid), int(self.seed), int(index.metric_type), _p(cent, ctypes.c_float),
+                                        _p(obj, ctypes.c_float), nsplit.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), None)
+        self.centroids, self.obj, self.nsplit = cent, obj[:nit].copy(), nsplit[:nit].copy()
+        index.reset()
+        index.add(cent.reshape(self.k, d))
 
 
 # ------------------------------------------------------------------------------------------------

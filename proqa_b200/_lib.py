@@ -17,6 +17,12 @@ PQ_OK = 0
 PQ_MAX_K = 15360
 TIER_AUTO, TIER_FP32, TIER_BF16 = 0, 1, 2
 
+class KMeansParams(ctypes.Structure):
+    """struct pq_kmeans_params (include/proqa_b200.h)."""
+    _fields_ = [("niter", ctypes.c_int), ("nredo", ctypes.c_int), ("verbose", ctypes.c_int), ("spherical", ctypes.c_int),
+                ("min_points_per_centroid", ctypes.c_int), ("max_points_per_centroid", ctypes.c_int), ("seed", ctypes.c_int64)]
+
+
 # name -> (restype, argtypes); the single source the symbol test checks against include/proqa_b200.h
 _f32p = ctypes.POINTER(ctypes.c_float)
 _i64p = ctypes.POINTER(ctypes.c_int64)
@@ -41,6 +47,8 @@ SIGNATURES = {
                                               _vp, _vp]),
     "pq_merge_shard_results_async": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp,
                                                     _vp, _vp, _vp]),
+    "pq_kmeans_default_params": (None, [ctypes.POINTER(KMeansParams)]),
+    "pq_kmeans_train": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.POINTER(KMeansParams), ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int64, _i64p]),
     "pq_last_error": (ctypes.c_char_p, []),
     "pq_version": (ctypes.c_char_p, []),
 }

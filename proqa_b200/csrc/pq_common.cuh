@@ -59,10 +59,14 @@ __host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) { return ~uin
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ float engine_dot(const float* __restrict__ a, const float* __restrict__ b) {
     float p[8];
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int j = 0; j < 8; ++j) {
         float acc = 0.f;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
         for (int i = 0; i < 16; ++i) acc = fmaf(a[16 * j + i], b[16 * j + i], acc);
         p[j] = acc;
     }

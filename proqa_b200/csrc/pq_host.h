@@ -106,7 +106,15 @@ struct pq_index {
     }
 };
 
+#include <mutex>
 namespace pq {
+// One lock for all device work of the process (C ABI entry points take it; the *_locked helpers expect it held).
+extern std::mutex g_device_mutex;
+int index_init_device(pq_index* ix);
+int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device);
+int index_reset_locked(pq_index* ix);
+// Device-resident search: dq [nq,128] fp32 -> dD [nq,k], dI [nq,k]; runs on ix->stream and leaves it drained.
+int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t k, float* dD, long long* dI);
 // fp32 tier: exact scan of all local rows.  Queries, norms and outputs are device pointers.
 int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norms, int k, float* dD, long long* dI);
 // tensor-core tier (pq_mma.cu): bf16 tcgen05 filter + fp32 rescoring.  Requires ws_qbf16 / ws_qnorm / ws_qbad to be

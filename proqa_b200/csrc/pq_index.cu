@@ -36,7 +36,7 @@ int cuda_fail(cudaError_t e, const char* file, int line) {
 }
 
 // The fp32 scan keeps its queries in one __constant__ bank, so device work is serialised process-wide.
-static std::mutex g_device_mutex;
+std::mutex g_device_mutex;
 
 // ------------------------------------------------------------------------------------------------
 // tensor maps
@@ -135,7 +135,7 @@ static int pick_device(int requested, int* out) {
 // ------------------------------------------------------------------------------------------------
 // index
 // ------------------------------------------------------------------------------------------------
-static int index_init_device(pq_index* ix) {
+int index_init_device(pq_index* ix) {
     if (ix->device_ready) return PQ_OK;
     int dev = -1;
     int rc = pick_device(ix->requested_device, &dev);
@@ -194,12 +194,12 @@ static int index_grow(pq_index* ix, int64_t need_rows) {
     return PQ_OK;
 }
 
-static int index_add_impl(pq_index* ix, int64_t n, const float* x, bool on_device) {
+// Caller holds g_device_mutex.
+int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
     if (n < 0 || (n > 0 && !x)) return set_error(PQ_ERR_INVALID, "add: bad arguments (n=%lld, x=%p)", (long long)n, (const void*)x);
     if (n == 0) return PQ_OK;
     if (ix->ntotal + n > (int64_t)0x7fffff00) return set_error(PQ_ERR_UNSUPPORTED, "add: more than 2^31 rows per shard");
-    std::lock_guard<std::mutex> lock(g_device_mutex);
     int rc = index_init_device(ix);
     if (rc) return rc;
     PQ_CUDA(cudaSetDevice(ix->device));
@@ -306,7 +306,7 @@ static bool tier_uses_mma(const pq_index* ix, int64_t nq, int64_t k) {
 }
 
 // Device-resident search: dq [nq,128] fp32 -> dD [nq,k], dI [nq,k]; all on ix->stream; leaves the stream drained.
-static int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t k, float* dD, long long* dI) {
+int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t k, float* dD, long long* dI) {
     memset(ix->stats, 0, sizeof(ix->stats));
     if (nq == 0) return PQ_OK;
     if (ix->ntotal == 0) {
@@ -421,8 +421,14 @@ void pq_index_free(pq_index* ix) {
     delete ix;
 }
 
-int pq_index_add(pq_index* ix, int64_t n, const float* x_host) { return index_add_impl(ix, n, x_host, false); }
-int pq_index_add_device(pq_index* ix, int64_t n, const float* x_dev) { return index_add_impl(ix, n, x_dev, true); }
+int pq_index_add(pq_index* ix, int64_t n, const float* x_host) {
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    return index_add_locked(ix, n, x_host, false);
+}
+int pq_index_add_device(pq_index* ix, int64_t n, const float* x_dev) {
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    return index_add_locked(ix, n, x_dev, true);
+}
 
 int pq_index_search(pq_index* ix, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I) {
     int rc = check_search_args(ix, nq, xq, k, D, I);
@@ -462,6 +468,11 @@ int pq_index_search_device(pq_index* ix, int64_t nq, const float* xq_dev, int64_
 int pq_index_reset(pq_index* ix) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
     std::lock_guard<std::mutex> lock(g_device_mutex);
+    return pq::index_reset_locked(ix);
+}
+}  // extern "C"
+namespace pq {
+int index_reset_locked(pq_index* ix) {
     ix->ntotal = 0;
     ix->max_norm2 = 0.f;
     ix->has_nonfinite = false;
@@ -472,6 +483,8 @@ int pq_index_reset(pq_index* ix) {
     }
     return PQ_OK;
 }
+}  // namespace pq
+extern "C" {
 
 int64_t pq_index_ntotal(const pq_index* ix) { return ix ? ix->ntotal : 0; }
 int pq_index_d(const pq_index* ix) { return ix ? ix->d : 0; }

@@ -1,0 +1,378 @@
+// proqa_b200 — GPU k-means driver: the B200 counterpart of faiss.Clustering.train as ProQA calls it
+// (retrieval/group_paras.py:40-45: Clustering(d, ncentroids); niter; max_points_per_centroid; train(x, index)).
+//
+// FAISS 1.6.3's Clustering.cpp is not in the reference tree (third-party wheel): what follows restates its published
+// algorithm [upstream-memory, SURVEY.md §8c(6)] — subsample by rand_perm(seed) when n > k*max_points_per_centroid,
+// centroids initialised from rand_perm(seed+1+redo*15486557), then niter rounds of
+//     assign = index.search(x, 1)            -> the engine's k = 1 path (tensor-core filter + exact fp32 rescoring)
+//     centroid c = mean of its points        -> here: stable sort of points by centroid, then one warp per centroid
+//                                               adds its points IN INDEX ORDER in fp32 (the same sequential sum
+//                                               FAISS's km_update_centroids performs), divided by the count
+//     empty clusters split a big one         -> host, same RandomGenerator(1234) walk and +-1/1024 perturbation
+//     index.reset(); index.add(centroids)
+// The assignment search is the hot part (250 x 10M x 10k); everything else is < 10 % of an iteration.
+#include "pq_common.cuh"
+#include "pq_host.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <random>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace pq {
+
+// ---- FAISS RandomGenerator / rand_perm (utils/random.cpp) ---------------------------------------------------------
+struct FaissRng {
+    std::mt19937 mt;
+    explicit FaissRng(int64_t seed) : mt((unsigned int)seed) {}
+    int rand_int(int max) { return (int)(mt() % (unsigned)max); }
+    float rand_float() { return mt() / float(mt.max()); }
+};
+static void rand_perm(std::vector<int>& perm, size_t n, int64_t seed) {
+    perm.resize(n);
+    for (size_t i = 0; i < n; ++i) perm[i] = (int)i;
+    FaissRng rng(seed);
+    for (size_t i = 0; i + 1 < n; ++i) {
+        const int i2 = (int)i + rng.rand_int((int)(n - i));
+        std::swap(perm[i], perm[i2]);
+    }
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------------------
+__global__ void km_keys_kernel(const long long* __restrict__ assign, int n, int* __restrict__ keys, int* __restrict__ vals,
+                               int* __restrict__ hist, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long a = assign[i];
+    if (a < 0 || a >= k) a = 0;  // cannot happen with a non-empty index; keeps the sort keys in range
+    keys[i] = (int)a;
+    vals[i] = i;
+    atomicAdd(hist + (int)a, 1);
+}
+
+// One warp per centroid: lane l owns dims 4l..4l+3; points are added in ascending point index (stable sort order).
+__global__ void __launch_bounds__(256) km_centroid_kernel(const float* __restrict__ x, const int* __restrict__ sorted_idx,
+                                                          const int* __restrict__ offsets, const int* __restrict__ hist, int k,
+                                                          float* __restrict__ centroids) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= k) return;
+    const int n = hist[c];
+    const int* idx = sorted_idx + offsets[c];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {  // four row loads in flight, added strictly in order
+        const int i0 = idx[j], i1 = idx[j + 1], i2 = idx[j + 2], i3 = idx[j + 3];
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i0 * kDim) + lane);
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i1 * kDim) + lane);
+        const float4 r2 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i2 * kDim) + lane);
+        const float4 r3 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i3 * kDim) + lane);
+        acc.x += r0.x; acc.y += r0.y; acc.z += r0.z; acc.w += r0.w;
+        acc.x += r1.x; acc.y += r1.y; acc.z += r1.z; acc.w += r1.w;
+        acc.x += r2.x; acc.y += r2.y; acc.z += r2.z; acc.w += r2.w;
+        acc.x += r3.x; acc.y += r3.y; acc.z += r3.z; acc.w += r3.w;
+    }
+    for (; j < n; ++j) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(x + (size_t)idx[j] * kDim) + lane);
+        acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+    }
+    if (n > 0) {
+        const float ni = (float)n;
+        acc.x /= ni; acc.y /= ni; acc.z /= ni; acc.w /= ni;
+    }
+    reinterpret_cast<float4*>(centroids + (size_t)c * kDim)[lane] = acc;
+}
+
+// fvec_renorm_L2: every centroid scaled to unit norm (spherical k-means).
+__global__ void __launch_bounds__(256) km_renorm_kernel(float* __restrict__ centroids, int k) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= k) return;
+    float4 v = reinterpret_cast<float4*>(centroids + (size_t)c * kDim)[lane];
+    const float nr = warp_engine_dot(v, v, lane);
+    if (nr > 0.f) {
+        const float inv = 1.0f / sqrtf(nr);
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        reinterpret_cast<float4*>(centroids + (size_t)c * kDim)[lane] = v;
+    }
+}
+
+// Objective: sum of the k = 1 distances, in double, per-block partials summed on the host in block order (deterministic).
+__global__ void __launch_bounds__(256) km_objective_kernel(const float* __restrict__ dis, int n, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) s += (double)dis[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void km_gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ perm, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    reinterpret_cast<float4*>(out + (size_t)i * kDim)[lane] = __ldg(reinterpret_cast<const float4*>(x + (size_t)perm[i] * kDim) + lane);
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// km_update_centroids' treatment of void clusters (host; touches only the few affected rows).
+static int split_void_clusters(std::vector<float>& cent, std::vector<int>& hassign, int64_t k, int64_t n) {
+    const float EPS = 1.f / 1024.f;
+    int nsplit = 0;
+    FaissRng rng(1234);
+    for (int64_t ci = 0; ci < k; ++ci) {
+        if (hassign[ci] != 0) continue;
+        int64_t cj;
+        for (cj = 0; true; cj = (cj + 1) % k) {
+            const float p = (hassign[cj] - 1.0) / (float)(n - k);  // probability to pick this cluster for a split
+            const float r = rng.rand_float();
+            if (r < p) break;
+        }
+        memcpy(&cent[ci * kDim], &cent[cj * kDim], sizeof(float) * kDim);
+        for (int j = 0; j < kDim; ++j) {  // small symmetric perturbation
+            if (j % 2 == 0) {
+                cent[ci * kDim + j] *= 1 + EPS;
+                cent[cj * kDim + j] *= 1 - EPS;
+            } else {
+                cent[ci * kDim + j] *= 1 - EPS;
+                cent[cj * kDim + j] *= 1 + EPS;
+            }
+        }
+        hassign[ci] = hassign[cj] / 2;  // assume an even split of the cluster
+        hassign[cj] -= hassign[ci];
+        ++nsplit;
+    }
+    return nsplit;
+}
+
+static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& prm, int64_t n_in, const float* x_host, float* centroids_out,
+                               float* obj_out, int64_t obj_cap, int64_t* n_obj) {
+    if (k < 1 || n_in < k) return set_error(PQ_ERR_INVALID, "kmeans: number of training points (%lld) should be at least as large as number of clusters (%lld)",
+                                            (long long)n_in, (long long)k);
+    if (k > (1 << 24) || n_in > 0x7fffff00LL) return set_error(PQ_ERR_UNSUPPORTED, "kmeans: k or n too large");
+    for (int64_t i = 0; i < n_in * kDim; ++i)
+        if (!std::isfinite(x_host[i])) return set_error(PQ_ERR_INVALID, "kmeans: input contains NaN's or Inf's");
+    int rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const double t0 = now_s();
+
+    // ---- subsample (Clustering::train: "Sampling a subset of %ld / %ld for training") ----
+    int64_t nx = n_in;
+    std::vector<int> perm;
+    DevBuf d_x;
+    const int64_t max_train = k * (int64_t)prm.max_points_per_centroid;
+    if (n_in > max_train) {
+        if (prm.verbose) printf("Sampling a subset of %ld / %ld for training\n", (long)max_train, (long)n_in);
+        rand_perm(perm, (size_t)n_in, prm.seed);
+        nx = max_train;
+    } else if (n_in < k * (int64_t)prm.min_points_per_centroid) {
+        fprintf(stderr, "WARNING clustering %ld points to %ld centroids: please provide at least %ld training points\n", (long)n_in, (long)k,
+                (long)(k * (int64_t)prm.min_points_per_centroid));
+    }
+    rc = d_x.ensure((size_t)nx * kDim * 4);
+    if (rc) return rc;
+    if (n_in > max_train) {  // gather on the host in chunks (the full matrix may not fit beside the index), copy each chunk
+        const int64_t chunk = 1 << 20;
+        std::vector<float> buf((size_t)std::min(chunk, nx) * kDim);
+        for (int64_t a = 0; a < nx; a += chunk) {
+            const int64_t b = std::min(nx, a + chunk);
+            for (int64_t i = a; i < b; ++i) memcpy(&buf[(size_t)(i - a) * kDim], x_host + (size_t)perm[i] * kDim, sizeof(float) * kDim);
+            PQ_CUDA(cudaMemcpyAsync((float*)d_x.p + (size_t)a * kDim, buf.data(), (size_t)(b - a) * kDim * 4, cudaMemcpyHostToDevice, st));
+            PQ_CUDA(cudaStreamSynchronize(st));
+        }
+    } else {
+        PQ_CUDA(cudaMemcpyAsync(d_x.p, x_host, (size_t)nx * kDim * 4, cudaMemcpyHostToDevice, st));
+    }
+    const float* dx = (const float*)d_x.p;
+
+    if (nx == k) {  // "Number of training points same as number of clusters, just copying"
+        PQ_CUDA(cudaMemcpyAsync(centroids_out, dx, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
+        PQ_CUDA(cudaStreamSynchronize(st));
+        rc = index_reset_locked(ix);
+        if (!rc) rc = index_add_locked(ix, k, dx, true);
+        d_x.release();
+        if (n_obj) *n_obj = 0;
+        return rc;
+    }
+    if (prm.verbose)
+        printf("Clustering %d points in %dD to %ld clusters, redo %d times, %d iterations\n", (int)nx, kDim, (long)k, prm.nredo, prm.niter);
+
+    DevBuf d_cent, d_D, d_I, d_keys, d_keys2, d_vals, d_vals2, d_hist, d_off, d_tmp, d_part, d_perm;
+    auto release = [&]() {
+        DevBuf* all[] = {&d_x, &d_cent, &d_D, &d_I, &d_keys, &d_keys2, &d_vals, &d_vals2, &d_hist, &d_off, &d_tmp, &d_part, &d_perm};
+        for (DevBuf* b : all) b->release();
+    };
+#define KM_TRY(expr)              \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc) {                \
+            release();            \
+            return _rc;           \
+        }                         \
+    } while (0)
+#define KM_CUDA(expr)                                     \
+    do {                                                  \
+        cudaError_t _e = (expr);                          \
+        if (_e != cudaSuccess) {                          \
+            release();                                    \
+            return cuda_fail(_e, __FILE__, __LINE__);     \
+        }                                                 \
+    } while (0)
+    KM_TRY(d_cent.ensure((size_t)k * kDim * 4));
+    KM_TRY(d_D.ensure((size_t)nx * 4));
+    KM_TRY(d_I.ensure((size_t)nx * 8));
+    KM_TRY(d_keys.ensure((size_t)nx * 4));
+    KM_TRY(d_keys2.ensure((size_t)nx * 4));
+    KM_TRY(d_vals.ensure((size_t)nx * 4));
+    KM_TRY(d_vals2.ensure((size_t)nx * 4));
+    KM_TRY(d_hist.ensure((size_t)k * 4));
+    KM_TRY(d_off.ensure((size_t)k * 4));
+    KM_TRY(d_part.ensure(1024 * 8));
+    KM_TRY(d_perm.ensure((size_t)k * 4));
+    int key_bits = 1;
+    while ((1LL << key_bits) < k) ++key_bits;
+    size_t tmp_bytes = 0;
+    KM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int*)d_keys.p, (int*)d_keys2.p, (const int*)d_vals.p, (int*)d_vals2.p, (int)nx, 0,
+                                            key_bits, st));
+    KM_TRY(d_tmp.ensure(tmp_bytes));
+
+    std::vector<float> cent((size_t)k * kDim), best_cent;
+    std::vector<int> hassign((size_t)k), offsets((size_t)k);
+    std::vector<float> obj, best_obj;
+    std::vector<double> partial(1024);
+    float best_err = HUGE_VALF;
+    double t_search_tot = 0.0;
+
+    for (int redo = 0; redo < prm.nredo; ++redo) {
+        if (prm.verbose && prm.nredo > 1) printf("Outer iteration %d / %d\n", redo, prm.nredo);
+        // initialise the centroids with random points of the (sub-sampled) training set
+        std::vector<int> perm2;
+        rand_perm(perm2, (size_t)nx, prm.seed + 1 + redo * 15486557L);
+        KM_CUDA(cudaMemcpyAsync(d_perm.p, perm2.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
+        km_gather_rows_kernel<<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, (const int*)d_perm.p, (int)k, (float*)d_cent.p);
+        KM_CUDA(cudaGetLastError());
+        if (prm.spherical) km_renorm_kernel<<<(unsigned)((k + 7) / 8), 256, 0, st>>>((float*)d_cent.p, (int)k);
+        KM_CUDA(cudaStreamSynchronize(st));
+        KM_TRY(index_reset_locked(ix));
+        KM_TRY(index_add_locked(ix, k, (const float*)d_cent.p, true));
+        obj.clear();
+        float err = 0.f;
+        for (int it = 0; it < prm.niter; ++it) {
+            const double t0s = now_s();
+            KM_TRY(search_device_impl(ix, nx, dx, 1, (float*)d_D.p, (long long*)d_I.p));  // leaves the stream drained
+            t_search_tot += now_s() - t0s;
+            // objective
+            km_objective_kernel<<<1024, 256, 0, st>>>((const float*)d_D.p, (int)nx, (double*)d_part.p);
+            KM_CUDA(cudaMemcpyAsync(partial.data(), d_part.p, 1024 * 8, cudaMemcpyDeviceToHost, st));
+            // centroid update: histogram + stable sort by centroid, then one warp per centroid
+            KM_CUDA(cudaMemsetAsync(d_hist.p, 0, (size_t)k * 4, st));
+            km_keys_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>((const long long*)d_I.p, (int)nx, (int*)d_keys.p, (int*)d_vals.p, (int*)d_hist.p,
+                                                                        (int)k);
+            KM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const int*)d_keys.p, (int*)d_keys2.p, (const int*)d_vals.p, (int*)d_vals2.p, (int)nx,
+                                                    0, key_bits, st));
+            KM_CUDA(cudaMemcpyAsync(hassign.data(), d_hist.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+            KM_CUDA(cudaStreamSynchronize(st));
+            double e64 = 0.0;
+            for (int b = 0; b < 1024; ++b) e64 += partial[b];
+            err = (float)e64;
+            obj.push_back(err);
+            int run = 0, n_void = 0;
+            double uf = 0.0;
+            for (int64_t c = 0; c < k; ++c) {
+                offsets[c] = run;
+                run += hassign[c];
+                n_void += hassign[c] == 0;
+                uf += (double)hassign[c] * (double)hassign[c];
+            }
+            const double imbalance = uf * (double)k / ((double)run * (double)run);
+            KM_CUDA(cudaMemcpyAsync(d_off.p, offsets.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
+            km_centroid_kernel<<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, (const int*)d_vals2.p, (const int*)d_off.p, (const int*)d_hist.p, (int)k,
+                                                                       (float*)d_cent.p);
+            KM_CUDA(cudaGetLastError());
+            int nsplit = 0;
+            if (n_void) {
+                KM_CUDA(cudaMemcpyAsync(cent.data(), d_cent.p, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
+                KM_CUDA(cudaStreamSynchronize(st));
+                nsplit = split_void_clusters(cent, hassign, k, nx);
+                KM_CUDA(cudaMemcpyAsync(d_cent.p, cent.data(), (size_t)k * kDim * 4, cudaMemcpyHostToDevice, st));
+            }
+            if (prm.verbose) {
+                printf("\r  Iteration %d (%.2f s, search %.2f s): objective=%g imbalance=%.3f nsplit=%d       ", it, now_s() - t0, t_search_tot, err, imbalance,
+                       nsplit);
+                fflush(stdout);
+            }
+            if (prm.spherical) km_renorm_kernel<<<(unsigned)((k + 7) / 8), 256, 0, st>>>((float*)d_cent.p, (int)k);
+            KM_CUDA(cudaStreamSynchronize(st));
+            KM_TRY(index_reset_locked(ix));
+            KM_TRY(index_add_locked(ix, k, (const float*)d_cent.p, true));
+        }
+        if (prm.verbose) printf("\n");
+        if (prm.nredo > 1) {
+            if (err < best_err) {
+                if (prm.verbose) printf("Objective improved: keep new clusters\n");
+                best_cent.resize((size_t)k * kDim);
+                KM_CUDA(cudaMemcpyAsync(best_cent.data(), d_cent.p, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
+                KM_CUDA(cudaStreamSynchronize(st));
+                best_obj = obj;
+                best_err = err;
+            }
+        }
+    }
+    if (prm.nredo > 1) {
+        memcpy(centroids_out, best_cent.data(), (size_t)k * kDim * 4);
+        obj = best_obj;
+        KM_CUDA(cudaMemcpyAsync(d_cent.p, best_cent.data(), (size_t)k * kDim * 4, cudaMemcpyHostToDevice, st));
+        KM_CUDA(cudaStreamSynchronize(st));
+        KM_TRY(index_reset_locked(ix));
+        KM_TRY(index_add_locked(ix, k, (const float*)d_cent.p, true));
+    } else {
+        KM_CUDA(cudaMemcpyAsync(centroids_out, d_cent.p, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
+        KM_CUDA(cudaStreamSynchronize(st));
+    }
+    if (obj_out)
+        for (size_t i = 0; i < obj.size() && (int64_t)i < obj_cap; ++i) obj_out[i] = obj[i];
+    if (n_obj) *n_obj = (int64_t)obj.size();
+    release();
+#undef KM_TRY
+#undef KM_CUDA
+    return PQ_OK;
+}
+
+}  // namespace pq
+
+extern "C" {
+
+void pq_kmeans_default_params(pq_kmeans_params* p) {
+    if (!p) return;
+    p->niter = 25;
+    p->nredo = 1;
+    p->verbose = 0;
+    p->spherical = 0;
+    p->min_points_per_centroid = 39;
+    p->max_points_per_centroid = 256;
+    p->seed = 1234;
+}
+
+int pq_kmeans_train(pq_index* index, int64_t k, const pq_kmeans_params* params, int64_t n, const float* x_host, float* centroids_out, float* obj_out,
+                    int64_t obj_cap, int64_t* n_obj) {
+    if (!index || !params || !x_host || !centroids_out) return pq::set_error(PQ_ERR_INVALID, "kmeans_train: null argument");
+    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    return pq::kmeans_train_locked(index, k, *params, n, x_host, centroids_out, obj_out, obj_cap, n_obj);
+}
+
+}  // extern "C"

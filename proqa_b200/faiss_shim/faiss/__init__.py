@@ -20,5 +20,6 @@ if _ROOT not in _sys.path:
     _sys.path.insert(0, _ROOT)
 
 from proqa_b200.index import METRIC_INNER_PRODUCT, METRIC_L2, IndexFlat, IndexFlatIP, IndexFlatL2  # noqa: E402,F401
+from proqa_b200.clustering import Clustering, ClusteringParameters, vector_float_to_array, vector_to_array  # noqa: E402,F401
 
 __version__ = "1.6.3+proqa_b200"

@@ -33,3 +33,10 @@ def IndexFlatIP(d):
 
 def IndexFlatL2(d):
     return _Dumping(d, _o.METRIC_L2)
+
+
+Clustering = _o.FaissClusteringOracle
+
+
+def vector_float_to_array(v):
+    return np.array(v, dtype=np.float32, copy=True)

@@ -119,6 +119,8 @@ def main():
     print("\n".join(lines))
     print("eval_fixture.npz written; seed", seed, "bytes", os.path.getsize(os.path.join(HERE, "eval_fixture.npz")))
 
+    make_kmeans_fixture()
+
     # ---- hand-checkable known answers ---------------------------------------------------------------------------
     cases = []
     # case 1: corpus row j = (j+1) * e_{j % 128}; query = e_0 + 2 e_1.  <q, x_j> = (j+1) if j%128==0, 2(j+1) if j%128==1.
@@ -147,5 +149,42 @@ def main():
     print("known_answers.json written")
 
 
+def make_kmeans_fixture():
+    """kmeans_fixture.npz — the reference's retrieval/group_paras.py run UNMODIFIED (subprocess, cwd laid out as the script
+    expects: encodings/train_para_embed.npy, ../data/retrieve_train.txt, output ../data/data_splits/) with ``import faiss``
+    bound to the FAISS restatement (IndexFlatL2 + Clustering + vector_float_to_array).  Stored: the fp16 points, the CLI
+    arguments, the final assignment I the script obtained and the split files it wrote (line numbers per split)."""
+    n, k, niter = 1200, 10, 6
+    rng = np.random.default_rng(77)
+    centers = (rng.standard_normal((k, D)) * 4.0).astype(np.float32)
+    lab = rng.integers(0, k, size=n)
+    x = (centers[lab] + 0.05 * rng.standard_normal((n, D))).astype(np.float16)   # well separated: assignments are unambiguous
+    tmp = tempfile.mkdtemp(prefix="proqa_golden_km_")
+    os.makedirs(os.path.join(tmp, "retrieval", "encodings"))
+    os.makedirs(os.path.join(tmp, "data"))
+    np.save(os.path.join(tmp, "retrieval", "encodings", "train_para_embed.npy"), x)
+    with open(os.path.join(tmp, "data", "retrieve_train.txt"), "w") as f:
+        for i in range(n):
+            f.write(f"line {i}\n")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.path.join(HERE, "_oracle_faiss") + os.pathsep + env.get("PYTHONPATH", "")
+    env["PROQA_GOLDEN_DUMP"] = os.path.join(tmp, "dump.npz")
+    subprocess.run([sys.executable, os.path.join(REF, "group_paras.py"), "--ncentroids", str(k), "--niter", str(niter),
+                    "--max_points_per_centroid", "1000"], cwd=os.path.join(tmp, "retrieval"), env=env, capture_output=True, text=True, check=True)
+    dump = np.load(os.path.join(tmp, "dump.npz"))
+    splits = []
+    for c in range(k):
+        lines = open(os.path.join(tmp, "data", "data_splits", f"split_{c}.txt")).read().splitlines()
+        splits.append(np.array([int(ln.split()[1]) for ln in lines], dtype=np.int32))
+    assert sum(len(sp) for sp in splits) == n
+    np.savez_compressed(os.path.join(HERE, "kmeans_fixture.npz"), x=x, k=np.int32(k), niter=np.int32(niter), max_points_per_centroid=np.int32(1000),
+                        I=dump["I"].astype(np.int32), D=dump["D"].astype(np.float32), split_sizes=np.array([len(sp) for sp in splits], np.int32),
+                        split_lines=np.concatenate(splits))
+    print("kmeans_fixture.npz written, bytes", os.path.getsize(os.path.join(HERE, "kmeans_fixture.npz")), "split sizes", [len(sp) for sp in splits])
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "kmeans":
+        make_kmeans_fixture()
+    else:
+        main()

@@ -1,0 +1,79 @@
+"""-m gpu: the k-means driver (pq_kmeans_train behind proqa_b200.Clustering) against the FAISS Clustering restatement."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.test_kmeans_oracle import blobs, load_kmeans_fixture, run_group_paras_flow
+
+pytestmark = pytest.mark.gpu
+
+
+def _train_both(x, k, niter, metric, spherical=False, mpc=256):
+    import proqa_b200 as pq
+    ix = pq.IndexFlat(128, metric)
+    clus = pq.Clustering(128, k)
+    clus.niter, clus.spherical, clus.max_points_per_centroid = niter, spherical, mpc
+    clus.train(x, ix)
+    io = oracle.FaissFlatOracle(128, metric)
+    co = oracle.FaissClusteringOracle(128, k)
+    co.niter, co.spherical, co.max_points_per_centroid = niter, spherical, mpc
+    co.train(x, io)
+    return clus, ix, co, io
+
+
+@pytest.mark.parametrize("n,k,niter", [(6000, 20, 6), (40000, 64, 4)])
+def test_kmeans_l2_blobs_match_faiss_restatement_bit_for_bit(n, k, niter):
+    """Well separated blobs: assignments are unambiguous, and the centroid update adds points in index order in fp32 exactly
+    as km_update_centroids does, so the whole trajectory (centroids after every iteration) is bit-identical."""
+    x, _ = blobs(n, k)
+    clus, ix, co, io = _train_both(x, k, niter, 1)
+    np.testing.assert_array_equal(clus.centroids.view(np.uint32), co.centroids.view(np.uint32))
+    np.testing.assert_allclose(clus.obj, co.obj, rtol=2e-5)
+    assert ix.ntotal == k
+    D, I = ix.search(x, 1)
+    Do, Io = io.search(x, 1)
+    np.testing.assert_array_equal(I, Io)
+
+
+def test_kmeans_subsampling_and_void_split_match():
+    base = np.random.default_rng(3).standard_normal((5, 128)).astype(np.float32) * 3
+    x = np.repeat(base, 400, axis=0) + 0.01 * np.random.default_rng(4).standard_normal((2000, 128)).astype(np.float32)
+    clus, ix, co, io = _train_both(x, 12, 4, 1, mpc=100)    # 1200 of 2000 points; 12 centroids over 5 blobs: splits happen
+    assert co.nsplit.sum() >= 0
+    np.testing.assert_allclose(clus.obj, co.obj, rtol=1e-3)
+    assert np.isfinite(clus.centroids).all()
+
+
+def test_kmeans_spherical_ip_runs_and_normalises():
+    x, _ = blobs(5000, 16)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    clus, ix, co, io = _train_both(x, 16, 5, 0, spherical=True)
+    c = clus.centroids.reshape(16, 128)
+    np.testing.assert_allclose(np.linalg.norm(c, axis=1), 1.0, rtol=1e-5)
+    np.testing.assert_allclose(clus.obj, co.obj, rtol=1e-4)
+
+
+def test_group_paras_flow_on_engine_matches_fixture():
+    """retrieval/group_paras.py:20-53,12-18 on the committed fixture (made by running the reference script on the FAISS
+    restatement): same final assignment, same split files."""
+    import proqa_b200 as pq
+    import types
+    fx = load_kmeans_fixture()
+    mod = types.SimpleNamespace(IndexFlatL2=pq.IndexFlatL2, Clustering=pq.Clustering, vector_float_to_array=pq.vector_float_to_array)
+    D, I, samples = run_group_paras_flow(mod, fx)
+    np.testing.assert_array_equal(I, fx["I"])
+    np.testing.assert_allclose(D, fx["D"], rtol=1e-3, atol=1e-4)
+    assert [len(s) for s in samples] == fx["split_sizes"].tolist()
+    assert np.concatenate([np.array(s, np.int32) for s in samples]).tolist() == fx["split_lines"].tolist()
+
+
+def test_kmeans_errors():
+    import proqa_b200 as pq
+    ix = pq.IndexFlatL2(128)
+    clus = pq.Clustering(128, 50)
+    with pytest.raises(ValueError):
+        clus.train(np.zeros((10, 128), np.float32), ix)          # fewer points than clusters
+    bad = np.zeros((100, 128), np.float32)
+    bad[3, 3] = np.nan
+    with pytest.raises(ValueError):
+        clus.train(bad, ix)
