@@ -158,6 +158,10 @@ def make_kmeans_fixture():
     rng = np.random.default_rng(77)
     centers = (rng.standard_normal((k, D)) * 4.0).astype(np.float32)
     lab = rng.integers(0, k, size=n)
+    from oracle import oracle
+    # FAISS seeds the centroids with the first k entries of rand_perm(n, seed 1234 + 1): give each of them its own blob, so
+    # every blob owns exactly one centroid throughout and no assignment depends on fp32 rounding
+    lab[oracle.rand_perm(n, 1235)[:k]] = np.arange(k)
     x = (centers[lab] + 0.05 * rng.standard_normal((n, D))).astype(np.float16)   # well separated: assignments are unambiguous
     tmp = tempfile.mkdtemp(prefix="proqa_golden_km_")
     os.makedirs(os.path.join(tmp, "retrieval", "encodings"))

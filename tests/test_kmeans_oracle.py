@@ -5,11 +5,15 @@ from oracle import oracle
 from tests import data
 
 
-def blobs(n, k, seed=5, spread=0.05):
-    """k well-separated blobs: every assignment is unambiguous for any fp32 accumulation order."""
+def blobs(n, k, seed=5, spread=0.05, distinct_init=False):
+    """k well-separated blobs.  With distinct_init the k points FAISS picks as initial centroids (the first k entries of
+    rand_perm(n, seed 1234 + 1)) come from k different blobs, so every blob owns exactly one centroid from the first
+    iteration on and every assignment is unambiguous for any fp32 accumulation order."""
     rng = np.random.default_rng(seed)
     centers = rng.standard_normal((k, 128)).astype(np.float32) * 4.0
     lab = rng.integers(0, k, size=n)
+    if distinct_init:
+        lab[oracle.rand_perm(n, 1235)[:k]] = np.arange(k)
     x = centers[lab] + spread * rng.standard_normal((n, 128)).astype(np.float32)
     return np.ascontiguousarray(x, np.float32), lab
 
