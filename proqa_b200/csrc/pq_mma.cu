@@ -79,21 +79,6 @@ struct MmaParams {
     int k1_adapt;
 };
 
-// Rare path, deliberately out of line: the epilogue's hot loop must stay small enough for the
-// instruction cache (an earlier fully inlined version spent most of its time in "no instruction" stalls).
-__device__ __noinline__ uint32_t mma_insert_group4(float a, float b, float c, float d, float th, uint32_t row, uint32_t row_end,
-                                                   uint64_t* slab, uint32_t cnt, uint32_t cap) {
-    const float v[4] = {a, b, c, d};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (v[i] >= th && row + i < row_end) {
-            if (cnt < cap) slab[cnt] = make_key(v[i], row + i);
-            ++cnt;
-        }
-    }
-    return cnt;
-}
-
 // D[tmem] (+)= A[tmem] * B[smem desc]^T: the stationary operand (queries) is read from tensor memory, so shared
 // memory only has to feed the streamed corpus tile (64 B/clk instead of 128 B/clk for the SS form).
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -138,52 +123,67 @@ __device__ __forceinline__ void mma_apply_l2_bias(float (&v)[32], const float4* 
 }
 
 // Threshold filter over 32 accumulator columns held in registers (one thread = one query).
-__device__ __forceinline__ void mma_filter32(const float (&v)[32], float& thr, float two_e, int k1_adapt, uint32_t base_row, uint32_t row_end32,
-                                             uint64_t* slab, uint32_t& cnt, uint32_t cap) {
-    // Max tree over the 32 columns, keeping the 8 group-of-4 maxima: the rare survivor is then located by 8 cheap
-    // group tests.  Rows past row_end (TMA zero fill in the last tile) score 0 and are rejected inside
-    // mma_insert_group4.
-    float g4[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) g4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
-    const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
-    // k = 1: a score more than 2E below any score already seen (this chunk's maximum included) cannot be the best row
-    if (k1_adapt && base_row + 32 <= row_end32) thr = fmaxf(thr, mx - two_e);
-    const float th = thr;
-    if (mx >= th) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (g4[g] >= th)
-                cnt = mma_insert_group4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], th, base_row + 4 * g, row_end32, slab, cnt, cap);
-        }
-    }
+//
+// Control flow is kept WARP-UNIFORM: votes decide whether any lane of the warp has a survivor in the chunk, then in each
+// group of four columns, and the appends themselves are predicated stores — no divergent branch anywhere.  (Earlier
+// versions located survivors through per-lane nested branches, first out of line, then inline: in the early epochs,
+// where the threshold is still loose and nearly every chunk has a survivor in some lane, a third of all issued
+// instructions were BRA/BSSY/BSYNC and the tensor pipe sat at 5-20 %.)  A full slab keeps counting (overflow is detected
+// from the count) and overwrites its last slot.
+__device__ __forceinline__ void mma_append_if(bool hit, uint64_t* slab, uint32_t& cnt, uint32_t cap, float score, uint32_t row) {
+    const uint64_t key = make_key(score, row);
+    uint64_t* dst = slab + min(cnt, cap - 1);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "@p st.global.u64 [%1], %2;\n\t}"
+        ::"r"((uint32_t)hit), "l"(dst), "l"(key)
+        : "memory");
+    cnt += hit ? 1u : 0u;
 }
-
-// k = 1 variant (k-means assignment: few rows per thread, so "rare" survivors are not rare).  The thread keeps a running
-// maximum; a score more than 2E below any score already seen cannot be the best row.  Survivors are recorded per group
-// of four rows (key = group maximum, first row of the group) with predicated stores — no call, no per-value loop; the
-// finalize kernel rescores the four rows of the few groups that end up within 2E of the overall maximum.
-__device__ __forceinline__ void mma_filter32_k1(float (&v)[32], float& thr, float two_e, uint32_t base_row, uint32_t row_end32, uint64_t* slab,
-                                                uint32_t& cnt, uint32_t cap) {
-    if (base_row + 32 > row_end32) {  // last tile: rows past the end (TMA zero fill, stale norms) must not look like scores
+// rows past the end of the epoch (TMA zero fill in the last tile, stale norms) must not look like scores
+__device__ __forceinline__ void mma_mask_tail(float (&v)[32], uint32_t base_row, uint32_t row_end32) {
+    if (base_row + 32 > row_end32) {  // warp-uniform, last tile only
 #pragma unroll
         for (int c = 0; c < 32; ++c)
             if (base_row + c >= row_end32) v[c] = -INFINITY;
     }
+}
+
+__device__ __forceinline__ void mma_filter32(float (&v)[32], float th, uint32_t base_row, uint32_t row_end32, uint64_t* slab, uint32_t& cnt,
+                                             uint32_t cap) {
+    mma_mask_tail(v, base_row, row_end32);
+    float g4[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) g4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
+    const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
+    if (__any_sync(0xffffffffu, mx >= th)) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            if (__any_sync(0xffffffffu, g4[g] >= th)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_append_if(v[4 * g + i] >= th, slab, cnt, cap, v[4 * g + i], base_row + 4 * g + i);
+            }
+        }
+    }
+}
+
+// k = 1 variant (k-means assignment: few rows per thread, so survivors are common).  The thread keeps a running maximum;
+// a score more than 2E below any score already seen cannot be the best row.  Survivors are recorded per group of four
+// rows (key = group maximum, first row of the group) — 8 predicated appends per chunk; the finalize kernel rescores the
+// four rows of the few groups that end up within 2E of the overall maximum.
+__device__ __forceinline__ void mma_filter32_k1(float (&v)[32], float& thr, float two_e, uint32_t base_row, uint32_t row_end32, uint64_t* slab,
+                                                uint32_t& cnt, uint32_t cap) {
+    mma_mask_tail(v, base_row, row_end32);
     float g4[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) g4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
     const float mx = fmaxf(fmaxf(fmaxf(g4[0], g4[1]), fmaxf(g4[2], g4[3])), fmaxf(fmaxf(g4[4], g4[5]), fmaxf(g4[6], g4[7])));
     thr = fmaxf(thr, mx - two_e);
     const float th = thr;
-    if (mx >= th) {
+    if (__any_sync(0xffffffffu, mx >= th)) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (g4[g] >= th) {
-                if (cnt < cap) slab[cnt] = make_key(g4[g], base_row + 4 * g);
-                ++cnt;
-            }
-        }
+        for (int g = 0; g < 8; ++g) mma_append_if(g4[g] >= th, slab, cnt, cap, g4[g], base_row + 4 * g);
     }
 }
 
@@ -337,72 +337,72 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         }
     } else {
         // ===================== epilogue: threshold filter =====================
+        // per (query tile, thread) state in shared memory — threshold, 2E, slab fill — so the loop over query tiles
+        // below needs no unrolling (each thread reads and writes only its own slots: no synchronisation)
+        const int tid_e = (int)threadIdx.x - 64;
+        float* s_thr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctrl) + 256);
+        float* s_2e = s_thr + kMaxMTiles * kEpiWarps * 32;
+        uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_2e + kMaxMTiles * kEpiWarps * 32);
         const int lane_q = quarter * 32 + lane;
         const int sub = slice * 2 + set;
-        float thr[M_TILES], two_e[M_TILES];
-        uint32_t cnt[M_TILES];
-        uint64_t* slab[M_TILES];
-#pragma unroll
-        for (int mi = 0; mi < M_TILES; ++mi) {
-            cnt[mi] = 0;
-            thr[mi] = INFINITY;
-            two_e[mi] = 0.f;
-            slab[mi] = nullptr;
-            if (mi < m) {
-                const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
-                thr[mi] = p.thr[q];
-                two_e[mi] = p.two_e[q];
-                slab[mi] = p.cand_keys + (q * p.n_sub + sub) * (size_t)p.cap;
-            }
+        for (int mi = 0; mi < m; ++mi) {
+            const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
+            s_thr[mi * 256 + tid_e] = p.thr[q];
+            s_2e[mi * 256 + tid_e] = p.two_e[q];
+            s_cnt[mi * 256 + tid_e] = 0;
         }
         const uint32_t row_end32 = (uint32_t)p.row_end;
+        const uint32_t cap = (uint32_t)p.cap;
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
             const uint32_t base_row = (uint32_t)(row0 + (long long)t * kBN + set * kSubN);
             const int s = t % kStages;
             const float4* norms = reinterpret_cast<const float4*>(smem_b + (size_t)s * kStageBytes + kTileBytes) + set * (kSubN / 4);
             if (kL2) mbar_wait(&ctrl->full[s], (uint32_t)(t / kStages) & 1u);  // already complete (the MMAs needed it): acquire only
-#pragma unroll
-            for (int mi = 0; mi < M_TILES; ++mi) {
-                if (mi < m) {
-                    const int j = t * m + mi;
-                    const int b = set * 2 + (j & 1);
-                    const uint32_t aph = (uint32_t)(j >> 1) & 1u;
-                    mbar_wait(&ctrl->tmem_full[b], aph);
-                    tc_fence_after_sync();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kSubN);
-                    float v0[32], v1[32];
-                    tmem_ld_32x32(taddr, v0);
-                    tmem_ld_32x32(taddr + 32, v1);
-                    tmem_ld_wait();
-                    // The accumulator is in registers now: hand the TMEM buffer back before filtering.
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);
-                    if (kL2) {
-                        mma_apply_l2_bias(v0, norms);
-                        mma_apply_l2_bias(v1, norms + 8);
-                        if (mi == m - 1) {  // last read of this stage's norms by this warp
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&ctrl->empty[s]);
-                        }
-                    }
-                    if (kK1) {
-                        mma_filter32_k1(v0, thr[mi], two_e[mi], base_row, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
-                        mma_filter32_k1(v1, thr[mi], two_e[mi], base_row + 32, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
-                    } else {
-                        mma_filter32(v0, thr[mi], two_e[mi], 0, base_row, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
-                        mma_filter32(v1, thr[mi], two_e[mi], 0, base_row + 32, row_end32, slab[mi], cnt[mi], (uint32_t)p.cap);
+#pragma unroll 1
+            for (int mi = 0; mi < m; ++mi) {
+                const int j = t * m + mi;
+                const int b = set * 2 + (j & 1);
+                const uint32_t aph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(&ctrl->tmem_full[b], aph);
+                tc_fence_after_sync();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kSubN);
+                float v0[32], v1[32];
+                tmem_ld_32x32(taddr, v0);
+                tmem_ld_32x32(taddr + 32, v1);
+                tmem_ld_wait();
+                // The accumulator is in registers now: hand the TMEM buffer back before filtering.
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);
+                if (kL2) {
+                    mma_apply_l2_bias(v0, norms);
+                    mma_apply_l2_bias(v1, norms + 8);
+                    if (mi == m - 1) {  // last read of this stage's norms by this warp
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ctrl->empty[s]);
                     }
                 }
+                const int slot = mi * 256 + tid_e;
+                uint64_t* slab = p.cand_keys + (((size_t)(mt0 + mi) * kBM + lane_q) * p.n_sub + sub) * (size_t)cap;
+                uint32_t cnt = s_cnt[slot];
+                const uint32_t cnt_in = cnt;
+                float th = s_thr[slot];
+                if (kK1) {
+                    const float two_e = s_2e[slot];
+                    mma_filter32_k1(v0, th, two_e, base_row, row_end32, slab, cnt, cap);
+                    mma_filter32_k1(v1, th, two_e, base_row + 32, row_end32, slab, cnt, cap);
+                    s_thr[slot] = th;
+                } else {
+                    mma_filter32(v0, th, base_row, row_end32, slab, cnt, cap);
+                    mma_filter32(v1, th, base_row + 32, row_end32, slab, cnt, cap);
+                }
+                if (cnt != cnt_in) s_cnt[slot] = cnt;
             }
         }
-#pragma unroll
-        for (int mi = 0; mi < M_TILES; ++mi) {
-            if (mi < m) {
-                const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
-                p.cand_cnt[q * p.n_sub + sub] = cnt[mi];
-            }
+        for (int mi = 0; mi < m; ++mi) {
+            const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
+            p.cand_cnt[q * p.n_sub + sub] = s_cnt[mi * 256 + tid_e];
         }
     }
 
@@ -448,80 +448,179 @@ struct EpochSelParams {
 };
 
 // One CTA per query: carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
-// The carry list is kept sorted, so only the new candidates are sorted (ascending) and one bitonic
-// merge of [carry desc | new asc] finishes the job: ~10x less work than re-sorting everything.
+// Slab counts are staged and prefix-summed in shared memory, candidates gathered coalesced (one warp per slab) into a
+// pool next to the old carry; when the pool exceeds K' an MSB-first radix select over the 64-bit keys (8-bit digits, bytes
+// common to all keys skipped) finds the K'-th largest key and the survivors are compacted — no sort of the pool.  Only the
+// K' survivors are sorted at the end (the next epoch and the rescoring kernel read the k-th entry).
+__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* pool, int n, int want, int* hist, uint64_t* s_u64, int* s_int) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // bytes on which all keys agree need no pass
+    uint64_t a = ~0ull, o = 0ull;
+    for (int i = t; i < n; i += 256) {
+        const uint64_t k = pool[i];
+        a &= k;
+        o |= k;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        a &= __shfl_xor_sync(0xffffffffu, a, s);
+        o |= __shfl_xor_sync(0xffffffffu, o, s);
+    }
+    if (lane == 0) {
+        s_u64[warp] = a;
+        s_u64[8 + warp] = o;
+    }
+    __syncthreads();
+    a = s_u64[0];
+    o = s_u64[8];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+        a &= s_u64[w];
+        o |= s_u64[8 + w];
+    }
+    const uint64_t differ = a ^ o;  // bit set = keys disagree there
+    uint64_t prefix = a & ~differ, mask = ~differ;  // agreed bits are part of the prefix already
+    __syncthreads();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (((differ >> shift) & 0xffull) == 0) continue;  // block-uniform
+        const uint64_t dmask = (differ >> shift) & 0xffull;  // only the disagreeing bits of this byte vary
+        hist[t] = 0;
+        __syncthreads();
+        for (int i = t; i < n; i += 256) {
+            const uint64_t k = pool[i];
+            if (((k ^ prefix) & mask) == 0) atomicAdd(&hist[(int)((k >> shift) & dmask)], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {  // largest digit d with count(digit >= d) >= want
+            int loc = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) loc += hist[lane * 8 + b];
+            int suf = loc;  // suffix sum over lanes (lane 31 = highest digits)
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, s);
+                if (lane + s < 32) suf += v;
+            }
+            const unsigned ok = __ballot_sync(0xffffffffu, suf >= want);
+            const int L = 31 - __clz((int)ok);
+            if (lane == L) {
+                int above = suf - loc;
+                int d = lane * 8 + 7;
+                for (; d > lane * 8; --d) {
+                    if (above + hist[d] >= want) break;
+                    above += hist[d];
+                }
+                s_int[0] = d;
+                s_int[1] = want - above;
+            }
+        }
+        __syncthreads();
+        prefix |= (uint64_t)s_int[0] << shift;
+        mask |= dmask << shift;
+        want = s_int[1];
+        __syncthreads();
+    }
+    return prefix;  // keys are unique: exactly `want_initial` keys are >= prefix
+}
+
 __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
-    __shared__ int s_fill, s_total, s_ovf, s_next, s_L;
-    __shared__ float s_drop;
+    uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw);                      // lmax keys: old carry + gathered candidates
+    uint64_t* out = pool + p.lmax;                                               // kp keys: survivors
+    int* s_cnt = reinterpret_cast<int*>(out + p.kp);                             // n_sub
+    int* s_off = s_cnt + p.n_sub;                                                // n_sub
+    __shared__ int hist[256];
+    __shared__ uint64_t s_u64[16];
+    __shared__ int s_int[2];
+    __shared__ int s_total, s_ovf, s_nc, s_slot;
+    __shared__ unsigned long long s_dropkey;
     const int q = blockIdx.x;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     uint64_t* carry = p.st.carry + (size_t)q * p.kp;
     const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
     const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
     if (t == 0) {
-        s_fill = 0;
-        s_total = 0;
         s_ovf = 0;
-        s_drop = -INFINITY;
+        s_nc = 0;
+        s_dropkey = 0ull;
     }
     __syncthreads();
-    int local = 0;
     for (int s = t; s < p.n_sub; s += 256) {
         const uint32_t c = cnts[s];
         if (c > (uint32_t)p.cap) s_ovf = 1;
-        local += (int)min(c, (uint32_t)p.cap);
+        s_cnt[s] = (int)min(c, (uint32_t)p.cap);
     }
-    if (local) atomicAdd(&s_total, local);
-    __syncthreads();
-    if (t == 0) {
-        int L = p.kp;
-        while (L < s_total && L < p.lmax) L <<= 1;
-        s_L = L;
+    for (int i = t; i < p.kp; i += 256) {  // the carry is sorted: its non-empty entries form a prefix
+        const uint64_t k = carry[i];
+        pool[i] = k;
+        if (k != 0ull) atomicMax(&s_nc, i + 1);
     }
     __syncthreads();
-    const int L = s_L;
-    for (int i = t; i < L; i += 256) work[i] = (i < p.kp) ? carry[i] : 0ull;
-    int s0 = 0;
-    while (s0 < p.n_sub) {
-        if (t == 0) {  // largest run of slabs whose entries fit one chunk of L
-            int s1 = s0, acc = 0;
-            while (s1 < p.n_sub) {
-                const int c = (int)min(cnts[s1], (uint32_t)p.cap);
-                if (acc + c > L) break;
-                acc += c;
-                ++s1;
+    if (warp == 0) {  // exclusive prefix sum of the slab counts: lane owns a contiguous run, warp scan across lanes
+        const int per = (p.n_sub + 31) / 32;
+        const int a = lane * per, b = min(p.n_sub, a + per);
+        int run = 0;
+        for (int s = a; s < b; ++s) run += s_cnt[s];
+        int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int base = incl - run;
+        for (int s = a; s < b; ++s) {
+            s_off[s] = base;
+            base += s_cnt[s];
+        }
+        if (lane == 31) s_total = incl;
+    }
+    __syncthreads();
+    const int total = s_total;
+    int nc = s_nc;
+    for (int c0 = 0; c0 < total;) {  // almost always a single chunk
+        const int chunk = min(total - c0, p.lmax - nc);
+        for (int s = warp; s < p.n_sub; s += 8) {
+            const int base = s_off[s] - c0, n = s_cnt[s];
+            if (base + n <= 0 || base >= chunk) continue;
+            const uint64_t* src = keys + (size_t)s * p.cap;
+            for (int pos = lane; pos < n; pos += 32) {
+                const int f = base + pos;
+                if (f >= 0 && f < chunk) pool[nc + f] = src[pos];
             }
-            s_next = s1;
-            s_fill = 0;
         }
         __syncthreads();
-        const int s1 = s_next;
-        for (int idx = s0 * p.cap + t; idx < s1 * p.cap; idx += 256) {
-            const int sub = idx / p.cap, pos = idx - sub * p.cap;
-            if ((uint32_t)pos < cnts[sub]) work[L + atomicAdd(&s_fill, 1)] = keys[idx];
+        const int n = nc + chunk;
+        if (n > p.kp) {
+            const uint64_t pivot = block_radix_select(pool, n, p.kp, hist, s_u64, s_int);
+            if (t == 0) s_slot = 0;
+            __syncthreads();
+            uint64_t dropped = 0ull;
+            for (int i = t; i < n; i += 256) {
+                const uint64_t k = pool[i];
+                if (k >= pivot) out[atomicAdd(&s_slot, 1)] = k;
+                else dropped = max(dropped, k);
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) dropped = max(dropped, __shfl_xor_sync(0xffffffffu, dropped, s));
+            if (lane == 0 && dropped) atomicMax(&s_dropkey, (unsigned long long)dropped);
+            __syncthreads();
+            for (int i = t; i < p.kp; i += 256) pool[i] = out[i];
+            nc = p.kp;
+            __syncthreads();
+        } else {
+            nc = n;
         }
-        __syncthreads();
-        const int fill = s_fill;
-        if (fill > 0) {
-            for (int i = fill + t; i < L; i += 256) work[L + i] = 0ull;
-            __syncthreads();
-            block_sort<256>(work + L, L, /*ascending=*/true);
-            block_bitonic_merge_desc<256>(work, 2 * L);
-            if (t == 0 && work[p.kp] != 0ull) s_drop = fmaxf(s_drop, key_score(work[p.kp]));
-            __syncthreads();
-            for (int i = p.kp + t; i < L; i += 256) work[i] = 0ull;  // truncate the carry back to K'
-            __syncthreads();
-        }
-        s0 = s1;
+        c0 += chunk;
     }
+    // sort the (at most K') survivors, best first
+    for (int i = nc + t; i < p.kp; i += 256) pool[i] = 0ull;
     __syncthreads();
-    for (int i = t; i < p.kp; i += 256) carry[i] = work[i];
+    block_sort_desc<256>(pool, p.kp);
+    for (int i = t; i < p.kp; i += 256) carry[i] = pool[i];
     if (t == 0) {
-        if (s_drop > -INFINITY) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], s_drop);
+        if (s_dropkey != 0ull) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], key_score((uint64_t)s_dropkey));
         if (s_ovf) p.st.overflow[q] = 1u;
-        const uint64_t kth = work[p.k - 1];
+        const uint64_t kth = pool[p.k - 1];
         if (kth != 0ull) p.st.thr[q] = fmaxf(p.st.thr[q], key_score(kth) - p.st.two_e[q]);
     }
 }
@@ -705,7 +804,7 @@ static int next_pow2i(int v) {
 
 template <int M, bool L2, bool K1>
 static cudaError_t launch_filter(const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
-    const size_t smem = (size_t)kStages * kStageBytes + sizeof(MmaCtrl);
+    const size_t smem = (size_t)kStages * kStageBytes + 256 + (size_t)kMaxMTiles * kEpiWarps * 32 * 12;  // ring + control + epilogue state
     cudaError_t e = cudaFuncSetAttribute(pq_mma_filter_kernel<M, L2, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pq_mma_filter_kernel<M, L2, K1><<<n_ctas, kMmaThreads, smem, stream>>>(tc, p);
@@ -912,8 +1011,8 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.cap = ep.cap;
             sp.kp = kp;
             sp.k = k;
-            sp.lmax = std::max(std::max(kp, next_pow2i(ep.cap)), 1024);
-            const size_t smem = (size_t)sp.lmax * 2 * 8;
+            sp.lmax = std::max(2 * kp, 4096);  // pool: old carry + one chunk of candidates
+            const size_t smem = ((size_t)sp.lmax + kp) * 8 + (size_t)sp.n_sub * 8;
             PQ_CUDA(cudaFuncSetAttribute(pq_epoch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
             PQ_CUDA(cudaGetLastError());
