@@ -30,7 +30,7 @@ int make_row_tensor_map(CUtensorMap* out, const void* base, long long rows, int 
 
 // Tensor-core tier limits
 constexpr int kMmaMaxK = 1024;          // carry list K' <= 4096 entries
-constexpr int kMmaMinQueries = 9;       // below this the fp32 scan is HBM-bound anyway
+constexpr int kMmaMinQueries = 5;       // nq <= 4: the fp32 scan streams the corpus at the HBM roofline (measured 1.0 of peak)
 constexpr int kMmaMinRows = 16384;      // below this the epoch machinery is pure overhead ...
 constexpr long long kMmaMinPairs = 1LL << 24;  // ... unless the query side is large (k-means assignment: 10k centroids x millions of points)
 
