@@ -310,29 +310,28 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
             tc_fence_after_sync();
             for (int mi = 0; mi < m; ++mi) {
                 const int j = t * m + mi;
-                const int b0 = (j & 1), b1 = 2 + (j & 1);
                 const uint32_t aph = (uint32_t)(j >> 1) & 1u;
-                mbar_wait(&ctrl->tmem_empty[b0], aph ^ 1u);
-                mbar_wait(&ctrl->tmem_empty[b1], aph ^ 1u);
-                tc_fence_after_sync();
-                if (elect_one()) {
-                    const uint32_t a_tmem = (uint32_t)(kTmemACol + mi * 64);
-                    const uint32_t tile_addr = b_addr + (uint32_t)s * kStageBytes;
-                    // the two row halves accumulate into different TMEM buffers: interleaving them keeps two independent
-                    // accumulation chains in the tensor pipe
+                const uint32_t a_tmem = (uint32_t)(kTmemACol + mi * 64);
+                const uint32_t tile_addr = b_addr + (uint32_t)s * kStageBytes;
+                // the two row halves go to the buffers of the two epilogue sets, one after the other: set 0 starts draining
+                // its accumulator while the tensor core works on set 1's, and each buffer is waited for as late as possible
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        // K step ks is 32 B into the 128-B row of panel ks>>2; rows 64.. of the tile start 64*128 B into each panel
-                        const uint32_t koff = (uint32_t)(ks >> 2) * kPanelBytes + (uint32_t)(ks & 3) * 32u;
-                        umma_bf16_ts((uint32_t)(b0 * kSubN), a_tmem + (uint32_t)ks * 8u, umma_desc_k128(tile_addr + koff), idesc, ks > 0 ? 1u : 0u);
-                        umma_bf16_ts((uint32_t)(b1 * kSubN), a_tmem + (uint32_t)ks * 8u, umma_desc_k128(tile_addr + koff + kSubN * 128), idesc,
-                                     ks > 0 ? 1u : 0u);
+                for (int h = 0; h < 2; ++h) {
+                    const int b = h * 2 + (j & 1);
+                    mbar_wait(&ctrl->tmem_empty[b], aph ^ 1u);
+                    tc_fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            // K step ks is 32 B into the 128-B row of panel ks>>2; rows 64.. of the tile start 64*128 B into each panel
+                            const uint32_t koff = (uint32_t)(ks >> 2) * kPanelBytes + (uint32_t)(ks & 3) * 32u + (uint32_t)h * (kSubN * 128);
+                            umma_bf16_ts((uint32_t)(b * kSubN), a_tmem + (uint32_t)ks * 8u, umma_desc_k128(tile_addr + koff), idesc, ks > 0 ? 1u : 0u);
+                        }
+                        umma_commit(&ctrl->tmem_full[b]);
+                        if (h == 1 && mi == m - 1) umma_commit(&ctrl->empty[s]);
                     }
-                    umma_commit(&ctrl->tmem_full[b0]);
-                    umma_commit(&ctrl->tmem_full[b1]);
-                    if (mi == m - 1) umma_commit(&ctrl->empty[s]);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -649,11 +648,14 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) 
     const uint64_t* carry = p.st.carry + (size_t)q * p.kp;
     if (t < kDim) s_q[t] = p.queries[(size_t)q * kDim + t];
     __syncthreads();
+    // a carry entry whose bf16 score is more than 2E below the k-th best bf16 score cannot be in the exact top-k: skip it
+    const uint64_t kth_key = carry[p.k - 1];
+    const float bar = kth_key != 0ull ? key_score(kth_key) - p.st.two_e[q] : -INFINITY;
     for (int i = t; i < p.work; i += 256) {
         uint64_t out = 0ull;
         if (i < p.kp) {
             const uint64_t key = carry[i];
-            if (key != 0ull) {
+            if (key != 0ull && key_score(key) >= bar) {
                 const uint32_t row = key_row(key);
                 // the engine's defined score (pq_common.cuh: engine_dot): 8 chains of 16 dims, tree-combined
                 const float4* r4 = reinterpret_cast<const float4*>(p.rows + (size_t)row * kDim);
