@@ -440,6 +440,24 @@ def run_ours(args, wl):
         if world > 1:
             dist.destroy_process_group()
         return
+    # ---- index load path: index.add() of a pageable host array (eval_retrieval.py:100,103), GB/s -------------------
+    add_info = None
+    if world == 1:
+        rows_add = 2_000_000
+        xh = host_corpus_sample(rows_add)
+        scratch = pq.IndexFlatIP(128, local_rank)
+        scratch.add(xh[:1000])          # device init, allocations
+        scratch.reset()
+        best = None
+        for _ in range(2):
+            scratch.reset()
+            t0 = time.perf_counter()
+            scratch.add(xh)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        add_info = {"rows": rows_add, "seconds": best, "host_gbs": rows_add * 512 / best / 1e9,
+                    "note": "pageable numpy array -> pinned double-buffered H2D + norms/bf16 preparation, per index.add call"}
+        del scratch, xh
     cpu = cpu_baseline(wl) if (world == 1 and not args.no_cpu_baseline) else None
     ms = t_dev / args.steps * 1e3
     out = {
@@ -457,6 +475,7 @@ def run_ours(args, wl):
         "parity": {"queries_checked": nchk, "ok": parity_ok, "ids_equal_frac": frac_equal, "against": "fp64 brute force (torch, checker only)",
                    "fp32_rerun_queries_per_step": rerun_q / max(1, args.steps)},
         "index_build_s": t_build,
+        "index_add": add_info,
         "multi_gpu_phases": phases,
     }
     if not parity_ok:

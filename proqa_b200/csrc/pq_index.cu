@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace pq {
@@ -35,7 +36,9 @@ int cuda_fail(cudaError_t e, const char* file, int line) {
     return set_error(code, "CUDA error %s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
 }
 
-// The fp32 scan keeps its queries in one __constant__ bank, so device work is serialised process-wide.
+static int cuda_ok_or_fail(cudaError_t e) { return e == cudaSuccess ? PQ_OK : cuda_fail(e, __FILE__, __LINE__); }
+
+// Device work is serialised process-wide (shared staging buffers, one stream per index).
 std::mutex g_device_mutex;
 
 // ------------------------------------------------------------------------------------------------
@@ -194,6 +197,67 @@ static int index_grow(pq_index* ix, int64_t need_rows) {
     return PQ_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Index load path: host rows -> device.  The reference hands add() a pageable numpy array
+// (eval_retrieval.py:100,103: np.load(...).astype('float32'), 10.75 GB for the 21M-row index).  A plain cudaMemcpy from
+// pageable memory is staged by the driver through one small bounce buffer; here the copy is pipelined explicitly:
+// host threads fill one of two pinned 64 MB buffers while the other is in flight over PCIe and the row-preparation kernel
+// (norms, bf16 copy) of the previous chunk runs on the same stream.
+// ------------------------------------------------------------------------------------------------
+struct StagingBuffers {
+    static constexpr size_t kBytes = 64u << 20;
+    void* buf[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaMallocHost(&buf[i], kBytes) != cudaSuccess || cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+        }
+        ok = true;
+        return true;
+    }
+};
+static StagingBuffers g_staging;  // guarded by g_device_mutex
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const int n_threads = 4;
+    const size_t per = (bytes / n_threads + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_threads; ++i) {
+        const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
+        if (b > a) th.emplace_back([=] { memcpy((char*)dst + a, (const char*)src + a, b - a); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (std::thread& t : th) t.join();
+}
+
+// Copies n rows from pageable host memory to dst_dev and launches the row preparation chunk by chunk on `stream`.
+static int staged_add_rows(pq_index* ix, float* dst_dev, const float* x_host, int64_t n, int64_t first_row) {
+    uint32_t* sc = (uint32_t*)ix->scalars.p;
+    const int64_t rows_per_chunk = (int64_t)(StagingBuffers::kBytes / (kDim * 4));
+    if (n * kDim * 4 < (int64_t)(8u << 20) || !g_staging.init()) {  // small (k-means centroids, tests): one plain copy
+        PQ_CUDA(cudaMemcpyAsync(dst_dev, x_host, (size_t)n * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
+        return cuda_ok_or_fail(prep_rows_launch(dst_dev, n, (uint16_t*)ix->rows_bf16.p + (size_t)first_row * kDim, (float*)ix->norms.p + first_row,
+                                                sc + 0, sc + 1, nullptr, ix->stream));
+    }
+    int which = 0;
+    for (int64_t a = 0; a < n; a += rows_per_chunk, which ^= 1) {
+        const int64_t rows = std::min(rows_per_chunk, n - a);
+        PQ_CUDA(cudaEventSynchronize(g_staging.done[which]));  // the H2D that last used this buffer has finished
+        parallel_memcpy(g_staging.buf[which], x_host + (size_t)a * kDim, (size_t)rows * kDim * 4);
+        float* d = dst_dev + (size_t)a * kDim;
+        PQ_CUDA(cudaMemcpyAsync(d, g_staging.buf[which], (size_t)rows * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
+        PQ_CUDA(cudaEventRecord(g_staging.done[which], ix->stream));
+        PQ_CUDA(prep_rows_launch(d, rows, (uint16_t*)ix->rows_bf16.p + (size_t)(first_row + a) * kDim, (float*)ix->norms.p + first_row + a, sc + 0,
+                                 sc + 1, nullptr, ix->stream));
+    }
+    return PQ_OK;
+}
+
 // Caller holds g_device_mutex.
 int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
@@ -206,10 +270,15 @@ int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device) {
     rc = index_grow(ix, ix->ntotal + n);
     if (rc) return rc;
     float* dst = (float*)ix->rows_f32.p + (size_t)ix->ntotal * kDim;
-    PQ_CUDA(cudaMemcpyAsync(dst, x, (size_t)n * kDim * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ix->stream));
     uint32_t* sc = (uint32_t*)ix->scalars.p;
-    PQ_CUDA(prep_rows_launch(dst, n, (uint16_t*)ix->rows_bf16.p + (size_t)ix->ntotal * kDim, (float*)ix->norms.p + ix->ntotal, sc + 0,
-                             sc + 1, nullptr, ix->stream));
+    if (on_device) {
+        PQ_CUDA(cudaMemcpyAsync(dst, x, (size_t)n * kDim * 4, cudaMemcpyDeviceToDevice, ix->stream));
+        PQ_CUDA(prep_rows_launch(dst, n, (uint16_t*)ix->rows_bf16.p + (size_t)ix->ntotal * kDim, (float*)ix->norms.p + ix->ntotal, sc + 0,
+                                 sc + 1, nullptr, ix->stream));
+    } else {
+        rc = staged_add_rows(ix, dst, x, n, ix->ntotal);
+        if (rc) return rc;
+    }
     uint32_t host_sc[2];
     PQ_CUDA(cudaMemcpyAsync(host_sc, sc, 8, cudaMemcpyDeviceToHost, ix->stream));
     PQ_CUDA(cudaStreamSynchronize(ix->stream));
