@@ -5,18 +5,21 @@
 // GEMM with K = 128.  This file runs it on the 5th-generation tensor cores and never writes the
 // score matrix:
 //
-//   pq_mma_filter_kernel  (one CTA per SM, warp-specialised)
-//     warp 0      TMA producer: query tiles once, then corpus tiles (128 rows x 256 B bf16) through a
-//                 4-stage shared-memory ring, SWIZZLE_128B, mbarrier completion
-//     warp 1      one elected thread issues tcgen05.mma (M=128 queries x N=128 rows x K=16, bf16 -> fp32)
-//                 into 4 rotating TMEM accumulators (4 x 128 columns = all 512)
-//     warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers; one thread owns one query
-//                 (a TMEM lane), so the admission threshold is a register compare; survivors (rare)
-//                 are appended to the query's private candidate slab in global memory
-//   pq_epoch_select_kernel  folds the slabs of one epoch into a per-query carry list (top-K' by bf16
-//                 score) and raises the query's admission threshold to  A_k - 2E
-//   pq_rescore_kernel       recomputes the carry list's scores with the engine's defined fp32 chain,
-//                 sorts, emits (D, I) and evaluates the exactness certificate.
+//   pq_mma_filter_kernel  (one CTA per SM, warp-specialised, 320 threads)
+//     warp 0      TMA producer: corpus tiles (128 rows x 256 B bf16, SWIZZLE_128B; L2 also the tile's 128 row norms)
+//                 through a 6-stage shared-memory ring, mbarrier completion
+//     warp 1      issues tcgen05.mma in the TS form: the stationary operand — up to 4 query tiles of 128 queries, written
+//                 once per CTA into tensor memory with tcgen05.st — times the streamed corpus tile from shared memory;
+//                 M=128 queries x N=64 rows x K=16, bf16 -> fp32, into four 64-column TMEM accumulators
+//     warps 2-9   epilogue, two sets of four warps (one warp per TMEM lane quarter): set h drains the accumulators of row
+//                 half h through its own two buffers (tcgen05.ld 32 lanes x 32 columns -> registers); one thread owns one
+//                 query (a TMEM lane), so the admission threshold is a register compare; survivors are appended to the
+//                 query's private candidate slab in global memory (warp-uniform votes + predicated stores)
+//   pq_epoch_select_kernel  folds the slabs of one epoch into a per-query carry list (top-K' by bf16 score, radix select)
+//                 and raises the query's admission threshold to  A_k - 2E
+//   pq_rescore_kernel       recomputes the carry list's scores with the engine's defined fp32 score, sorts, emits (D, I)
+//                 and evaluates the exactness certificate
+//   pq_k1_finalize_kernel   k = 1 (k-means assignment): one warp per query rescoring the few groups within 2E of the best
 //
 // Exactness: |bf16 score - fp32 score| <= E_q = eps * |q| * max|c|.  Every row of the
 // true top-k has approximate score >= A_k - 2E (A_k = k-th best approximate score), so filtering at
