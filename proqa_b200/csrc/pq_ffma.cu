@@ -88,8 +88,10 @@ __device__ __forceinline__ void ffma_fold(const float (&v)[N], float (&out)[(N >
 // 16 rows, the CTA's 8 warps the 128 rows of the tile.  Row and query operands both come from shared memory as
 // LDS.128: per 16*QT FFMAs a thread issues 4 + QT loads, all bank-conflict free (rows through TMA's 128-byte
 // swizzle, queries through the [q][step][kq] layout).
+// Returns true if one of this thread's appends pushed a query's buffer past its refill mark (the caller ORs the flags of
+// all threads at the tile barrier: a shared flag read after that barrier raced with the next tile's writers).
 template <int QT>
-__device__ __forceinline__ void ffma_tile(const uint8_t* stage, const float4* qsm, long long tile_row0, uint64_t* bufs, FfmaCtrl* ctrl,
+__device__ __forceinline__ bool ffma_tile(const uint8_t* stage, const float4* qsm, long long tile_row0, uint64_t* bufs, FfmaCtrl* ctrl,
                                           const FfmaParams& p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rg = lane & 3, kq = lane >> 2;
@@ -133,7 +135,8 @@ __device__ __forceinline__ void ffma_tile(const uint8_t* stage, const float4* qs
     bool owner = true;
     if constexpr (N2 > 1) a0 += b2 ? N / 8 : 0;
     else owner = !b2;  // N == 4: both partners of the last step hold the same value, one reports it
-    if (!owner) return;
+    bool want_compact = false;
+    if (!owner) return false;
 #pragma unroll
     for (int i = 0; i < N3; ++i) {
         const int a = a0 + i;
@@ -145,10 +148,11 @@ __device__ __forceinline__ void ffma_tile(const uint8_t* stage, const float4* qs
             if (s >= ctrl->thr[q]) {
                 const int slot = atomicAdd(&ctrl->cnt[q], 1);
                 bufs[(size_t)q * p.cap + slot] = make_key(s, (uint32_t)row);
-                if (slot + 1 > p.cap - kFfmaTileRows) ctrl->need_compact = 1;
+                if (slot + 1 > p.cap - kFfmaTileRows) want_compact = true;
             }
         }
     }
+    return want_compact;
 }
 
 template <int QT>
@@ -170,7 +174,6 @@ pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p
         tma_prefetch_desc(&tmap);
         for (int s = 0; s < p.n_stages; ++s) mbar_init(&ctrl->full[s], 1);
         fence_mbar_init();
-        ctrl->need_compact = 0;
     }
     if (t < kFfmaMaxQ) {
         ctrl->cnt[t] = 0;
@@ -202,14 +205,13 @@ pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p
         if (t == 0 && it + p.n_stages - 1 < ntiles) issue(it + p.n_stages - 1);
         const int s = it % p.n_stages;
         mbar_wait(&ctrl->full[s], (uint32_t)((it / p.n_stages) & 1));
-        ffma_tile<QT>(stages + (size_t)s * kFfmaStageBytes, qsm, (long long)(tile0 + it) * kFfmaTileRows, bufs, ctrl, p);
-        __syncthreads();
+        const bool want = ffma_tile<QT>(stages + (size_t)s * kFfmaStageBytes, qsm, (long long)(tile0 + it) * kFfmaTileRows, bufs, ctrl, p);
+        const int need_compact = __syncthreads_or(want ? 1 : 0);  // also the barrier that frees the stage for the next TMA
         const bool refresh = ((it & 15) == 15);
-        if (ctrl->need_compact) {  // block-uniform: written before the barrier above
+        if (need_compact) {  // block-uniform
             for (int q = 0; q < p.nq; ++q) {
                 if (ctrl->cnt[q] > p.cap - kFfmaTileRows) ffma_compact(bufs + (size_t)q * p.cap, ctrl, q, p);
             }
-            if (t == 0) ctrl->need_compact = 0;
             __syncthreads();
         } else if (refresh) {
             if (t < p.nq) ctrl->thr[t] = fmaxf(ctrl->thr[t], ordered_to_f32(ld_volatile_u32(p.gthr + t)));
