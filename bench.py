@@ -202,7 +202,12 @@ def run_reference_kmeans(args, wl):
 
 
 def workload_config(args, wl):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from proqa_b200.sharded import auto_row_shards
+    rs = getattr(args, "row_shards", None)
+    R = auto_row_shards(world, wl["rows"]) if rs == "auto" else (world if rs in (None, "rows") else int(rs))
     return {"workload": wl["desc"], "name": args.workload, "nq": wl["nq"], "rows": wl["rows"], "d": 128, "k": wl["k"],
+            "parallelism": f"{R} row shards x {world // R} query groups" if world > 1 else "1 GPU",
             "l2_flush": "inputs larger than L2 (bf16 corpus copy %.1f GB per step)" % (wl["rows"] * 256 / 1e9)}
 
 
@@ -284,8 +289,11 @@ def run_ours(args, wl):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     nq, N, k = wl["nq"], wl["rows"], wl["k"]
-    lo, hi = shard_bounds(N, world, rank)
-    sh = ShardedIndexFlat(128, pq.METRIC_INNER_PRODUCT, device=local_rank)
+    from proqa_b200.sharded import auto_row_shards
+    R = auto_row_shards(world, N) if args.row_shards == "auto" else (world if args.row_shards in (None, "rows") else int(args.row_shards))
+    sh = ShardedIndexFlat(128, pq.METRIC_INNER_PRODUCT, device=local_rank, row_shards=R)
+    lo, hi = sh.row_bounds(N)
+    qlo, qhi = sh.query_bounds(nq)
     ix = sh.local
     if args.tier:
         ix.set_tier(args.tier)
@@ -340,10 +348,11 @@ def run_ours(args, wl):
     if world > 1:
         Dt_all = torch.empty((world, nchk, k), dtype=torch.float64, device=dev)
         It_all = torch.empty((world, nchk, k), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(Dt_all, Dt.contiguous())
-        dist.all_gather_into_tensor(It_all, It.contiguous())
-        cat_d = Dt_all.permute(1, 0, 2).reshape(nchk, -1)
-        cat_i = It_all.permute(1, 0, 2).reshape(nchk, -1)
+        dist.all_gather_into_tensor(Dt_all.view(world * nchk, k), Dt.contiguous())
+        dist.all_gather_into_tensor(It_all.view(world * nchk, k), It.contiguous())
+        # ranks 0..R-1 (query group 0) together hold every row shard exactly once
+        cat_d = Dt_all[:sh.R].permute(1, 0, 2).reshape(nchk, -1)
+        cat_i = It_all[:sh.R].permute(1, 0, 2).reshape(nchk, -1)
         top = torch.topk(cat_d, k, dim=1)
         Dt, It = top.values, torch.gather(cat_i, 1, top.indices)
     parity_ok, frac_equal = parity_gate(D_out[:nchk], I_out[:nchk], Dt, It)
@@ -388,7 +397,7 @@ def run_ours(args, wl):
 
     # ---- phase breakdown of one multi-GPU step (CUDA events on the launching stream; diagnostic) ----
     phases = None
-    if world > 1:
+    if world > 1 and sh.Q == 1:
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         acc = [0.0, 0.0, 0.0]
         for _ in range(3):
@@ -419,7 +428,7 @@ def run_ours(args, wl):
     local_rows = hi - lo
     tensor_path = st[3] > 0
     if tensor_path:
-        flops = 2.0 * nq * local_rows * 128
+        flops = 2.0 * (qhi - qlo) * local_rows * 128
         long_run = t_dev > 1.0
         peak = peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]
         achieved = flops / kernel_s / 1e12 if kernel_s > 0 else 0.0
@@ -661,6 +670,8 @@ def main():
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--tier", default=None, choices=[None, "auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--row-shards", default=None,
+                    help="multi-GPU layout: number of corpus row shards R (world = R x query groups); 'rows' (default) = world, 'auto' = fewest shards that fit")
     ap.add_argument("--metric", default="l2", choices=["ip", "l2"], help="c4 only (group_paras.py default is L2; --spherical is IP)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

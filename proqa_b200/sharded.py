@@ -1,17 +1,24 @@
-"""Multi-GPU layer: the corpus row-sharded over the ranks of a torch.distributed group (one process per GPU).
+"""Multi-GPU layer: one process per GPU (torch.distributed), the corpus row-sharded over the ranks.
 
-The reference's search path has no collective at all (single host process); sharding the
-rows of ``IndexFlatIP`` (retrieval/eval_retrieval.py:102-104) adds exactly one exchange step:
+The reference's search path has no collective at all (single host process); sharding the rows of
+``IndexFlatIP`` (retrieval/eval_retrieval.py:102-104) adds exactly one exchange step:
 
     rank r owns the contiguous global rows [lo_r, hi_r)   (ids reported as local row + lo_r)
     queries are replicated (broadcast from rank 0 when asked)
     every rank searches its shard              -> local (D, I) [nq, k], best-first, global ids
-    all_gather of the G lists (NCCL over NVLink: 12 B per entry, tiny next to the scan)
+    all_gather of the R lists (NCCL over NVLink: 12 B per entry, tiny next to the scan)
     merge kernel (pq_merge_shard_results)      -> final (D, I) on every rank
 
-``local_factory`` / ``merge_fn`` exist so that the host-side logic (shard bounds, id bases, gather layout)
-can be exercised on CPU with the gloo backend and test doubles; the defaults are the CUDA engine and there is
-no CPU fallback in the product.
+Layout.  ``row_shards = R`` (default: the world size W, i.e. pure row sharding) arranges the W ranks as Q = W / R *query
+groups* of R *row shards*: rank r holds row shard ``r % R`` and answers query slice ``r // R`` of Q.  Per-query work that
+does not shrink with the shard (threshold epochs, selection, rescoring) is then divided by Q; the price is Q copies of the
+corpus across the box (21M x 128 is 16 GB per copy, a B200 has 180).  The exchange becomes: all_gather + merge inside a
+row group (R ranks), then one all_gather of the finished slices across the Q groups.  R = 1 is pure query sharding (no
+merge at all); R = W is the layout above.
+
+``local_factory`` / ``merge_fn`` exist so that the host-side logic (shard bounds, id bases, gather layout) can be
+exercised on CPU with the gloo backend and test doubles; the defaults are the CUDA engine and there is no CPU fallback in
+the product.
 """
 from __future__ import annotations
 
@@ -24,32 +31,63 @@ from .index import METRIC_INNER_PRODUCT, IndexFlat
 
 
 def shard_bounds(n, world, rank):
-    """Contiguous, ascending, near-equal row ranges: rank r owns [lo, hi)."""
+    """Contiguous, ascending, near-equal ranges: part ``rank`` of ``world`` owns [lo, hi)."""
     per = (n + world - 1) // world
     lo = min(n, rank * per)
     return lo, min(n, lo + per)
 
 
+def auto_row_shards(world, n_rows, bytes_per_row=772, budget_bytes=48e9):
+    """Fewest row shards (a divisor of ``world``) whose shard — fp32 rows + bf16 copy + norms — stays under the budget."""
+    for r in range(1, world + 1):
+        if world % r == 0 and (n_rows / r) * bytes_per_row <= budget_bytes:
+            return r
+    return world
+
+
 class ShardedIndexFlat:
-    def __init__(self, d, metric=METRIC_INNER_PRODUCT, group=None, device=None, local_factory=None, merge_fn=None):
+    def __init__(self, d, metric=METRIC_INNER_PRODUCT, group=None, device=None, local_factory=None, merge_fn=None, row_shards=None):
         import torch.distributed as dist
         self._dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.R = int(row_shards) if row_shards else self.world
+        assert self.world % self.R == 0, f"row_shards={self.R} must divide the world size {self.world}"
+        self.Q = self.world // self.R
+        self.rr, self.rq = self.rank % self.R, self.rank // self.R   # my row shard, my query group
         self.d, self.metric_type, self.is_trained = int(d), int(metric), True
         self.device = device
         self._local = (local_factory or (lambda: IndexFlat(d, metric, -1 if device is None else device)))()
         self._merge_fn = merge_fn
         self.ntotal = 0
         self._first_add = True
+        # process groups: every rank creates every group, in the same order (new_group is collective)
+        self.row_group = group
+        self.col_group = None
+        if self.world > 1 and self.Q > 1:
+            base = list(range(self.world)) if group is None else dist.get_process_group_ranks(group)
+            for q in range(self.Q):
+                g = dist.new_group([base[q * self.R + i] for i in range(self.R)]) if self.R > 1 else None
+                if q == self.rq:
+                    self.row_group = g
+            for r in range(self.R):
+                g = dist.new_group([base[q * self.R + r] for q in range(self.Q)])
+                if r == self.rr:
+                    self.col_group = g
 
     # ---- build ----------------------------------------------------------------------------------
+    def row_bounds(self, n):
+        return shard_bounds(n, self.R, self.rr)
+
+    def query_bounds(self, nq):
+        return shard_bounds(nq, self.Q, self.rq)
+
     def add(self, x):
-        """Every rank passes the same global array; each keeps its contiguous slice."""
+        """Every rank passes the same global array; each keeps the contiguous slice of its row shard."""
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2 and x.shape[1] == self.d
-        lo, hi = shard_bounds(x.shape[0], self.world, self.rank)
+        lo, hi = self.row_bounds(x.shape[0])
         self.add_shard(x[lo:hi], self.ntotal + lo, x.shape[0])
 
     def add_shard(self, x_local, id_base, n_global):
@@ -81,50 +119,92 @@ class ShardedIndexFlat:
 
     # ---- search ---------------------------------------------------------------------------------
     def search(self, xq, k):
-        """Host API (numpy in, numpy out), same on every rank."""
+        """Host API (numpy in, numpy out), same result on every rank."""
         import torch
         xq = np.ascontiguousarray(xq, dtype=np.float32)
         k = int(k)
-        D, I = self._local.search(xq, k)
+        nq = xq.shape[0]
+        qlo, qhi = self.query_bounds(nq)
+        D, I = self._local.search(xq[qlo:qhi], k)
         if self.world == 1:
             return D, I
         on_gpu = self._merge_fn is None
         dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
         Dl, Il = torch.from_numpy(D).to(dev), torch.from_numpy(I).to(dev)
-        Dg, Ig = self.gather_merge(Dl, Il, k)
-        return Dg.cpu().numpy(), Ig.cpu().numpy()
+        if self.R > 1:
+            Dl, Il = self.gather_merge(Dl, Il, k)
+        if self.Q > 1:
+            Dl, Il = self._gather_slices(Dl, Il, nq, k)
+        return Dl.cpu().numpy(), Il.cpu().numpy()
 
     def search_device(self, q, k, D_local, I_local, D_all, I_all, D_out, I_out):
-        """Device API on torch tensors (all preallocated): local search, all_gather, merge kernel."""
+        """Device API on torch tensors (all preallocated for the full batch): local search of this rank's query slice,
+        all_gather + merge kernel inside the row group, all_gather of the slices across query groups."""
         nq = q.shape[0]
-        self._local.search_device(q.data_ptr(), nq, k, D_local.data_ptr(), I_local.data_ptr())
+        qlo, qhi = self.query_bounds(nq)
+        n_loc = qhi - qlo
+        per = (nq + self.Q - 1) // self.Q   # padded slice length (all_gather needs equal pieces)
+        Dl, Il = D_local[:n_loc], I_local[:n_loc]
+        if n_loc:
+            self._local.search_device(q[qlo:qhi].data_ptr(), n_loc, k, Dl.data_ptr(), Il.data_ptr())
         if self.world == 1:
             D_out.copy_(D_local)
             I_out.copy_(I_local)
             return
-        # rank-major concatenation along dim 0: [G*nq, k] is the layout every backend accepts for the output
-        self._dist.all_gather_into_tensor(D_all.view(self.world * nq, k), D_local, group=self.group)
-        self._dist.all_gather_into_tensor(I_all.view(self.world * nq, k), I_local, group=self.group)
-        self._merge_device(D_all, I_all, nq, k, D_out, I_out)
+        if self.R > 1:
+            # rank-major concatenation along dim 0: [R*n_loc, k] is the layout every backend accepts for the output
+            Da, Ia = D_all.view(-1)[: self.R * n_loc * k].view(self.R * n_loc, k), I_all.view(-1)[: self.R * n_loc * k].view(self.R * n_loc, k)
+            self._dist.all_gather_into_tensor(Da, Dl, group=self.row_group)
+            self._dist.all_gather_into_tensor(Ia, Il, group=self.row_group)
+            if self.Q == 1:
+                self._merge_device(Da, Ia, n_loc, k, D_out, I_out)
+                return
+            self._merge_device(Da, Ia, n_loc, k, Dl, Il)   # slice result back into the local buffers
+        if self.Q > 1:
+            if per * self.Q == nq:
+                self._dist.all_gather_into_tensor(D_out, D_local[:per], group=self.col_group)
+                self._dist.all_gather_into_tensor(I_out, I_local[:per], group=self.col_group)
+            else:  # ragged last slice: gather padded pieces, then trim
+                Dp, Ip = self._gather_slices(D_local[:per], I_local[:per], nq, k, padded=True)
+                D_out.copy_(Dp[:nq])
+                I_out.copy_(Ip[:nq])
 
     def gather_merge(self, Dl, Il, k):
+        """all_gather of the R per-shard lists of this row group + merge."""
         import torch
         nq = Dl.shape[0]
-        D_all = torch.empty((self.world,) + tuple(Dl.shape), dtype=Dl.dtype, device=Dl.device)
-        I_all = torch.empty((self.world,) + tuple(Il.shape), dtype=Il.dtype, device=Il.device)
-        self._dist.all_gather_into_tensor(D_all.view(self.world * nq, k), Dl.contiguous(), group=self.group)
-        self._dist.all_gather_into_tensor(I_all.view(self.world * nq, k), Il.contiguous(), group=self.group)
+        D_all = torch.empty((self.R,) + tuple(Dl.shape), dtype=Dl.dtype, device=Dl.device)
+        I_all = torch.empty((self.R,) + tuple(Il.shape), dtype=Il.dtype, device=Il.device)
+        self._dist.all_gather_into_tensor(D_all.view(self.R * nq, k), Dl.contiguous(), group=self.row_group)
+        self._dist.all_gather_into_tensor(I_all.view(self.R * nq, k), Il.contiguous(), group=self.row_group)
         if self._merge_fn is not None:
             return self._merge_fn(D_all, I_all, k, self.metric_type)
         D_out, I_out = torch.empty_like(Dl), torch.empty_like(Il)
-        self._merge_device(D_all, I_all, nq, k, D_out, I_out)
+        self._merge_device(D_all.view(self.R * nq, k), I_all.view(self.R * nq, k), nq, k, D_out, I_out)
         return D_out, I_out
+
+    def _gather_slices(self, Dl, Il, nq, k, padded=False):
+        """Finished query slices of the Q groups -> the full [nq, k] result on every rank."""
+        import torch
+        per = (nq + self.Q - 1) // self.Q
+        if not padded:
+            Dp = torch.zeros((per, k), dtype=Dl.dtype, device=Dl.device)
+            Ip = torch.full((per, k), -1, dtype=Il.dtype, device=Il.device)
+            Dp[: Dl.shape[0]] = Dl
+            Ip[: Il.shape[0]] = Il
+        else:
+            Dp, Ip = Dl, Il
+        D_all = torch.empty((self.Q * per, k), dtype=Dl.dtype, device=Dl.device)
+        I_all = torch.empty((self.Q * per, k), dtype=Il.dtype, device=Il.device)
+        self._dist.all_gather_into_tensor(D_all, Dp.contiguous(), group=self.col_group)
+        self._dist.all_gather_into_tensor(I_all, Ip.contiguous(), group=self.col_group)
+        return (D_all, I_all) if padded else (D_all[:nq], I_all[:nq])
 
     def _merge_device(self, D_all, I_all, nq, k, D_out, I_out):
         """Merge kernel on torch's current stream: ordered after the all-gather, no host synchronisation."""
         import torch
         stream = torch.cuda.current_stream().cuda_stream
-        rc = _lib.lib().pq_merge_shard_results_async(D_all.device.index, self.metric_type, self.world, nq, k,
+        rc = _lib.lib().pq_merge_shard_results_async(D_all.device.index, self.metric_type, self.R, nq, k,
                                                      ctypes.c_void_p(D_all.data_ptr()), ctypes.c_void_p(I_all.data_ptr()),
                                                      ctypes.c_void_p(D_out.data_ptr()), ctypes.c_void_p(I_out.data_ptr()),
                                                      ctypes.c_void_p(stream))

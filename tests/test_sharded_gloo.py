@@ -48,15 +48,16 @@ def _merge_double(D_all, I_all, k, metric):
     return torch.from_numpy(Do), torch.from_numpy(Io)
 
 
-def _worker(rank, world, port, metric, n, nq, k, out):
+def _worker(rank, world, port, metric, n, nq, k, out, row_shards=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from proqa_b200.sharded import ShardedIndexFlat, shard_bounds
         xb, xq = data.corpus(n), data.queries(nq)
-        sh = ShardedIndexFlat(128, metric, local_factory=lambda: _OracleLocal(metric), merge_fn=_merge_double)
+        sh = ShardedIndexFlat(128, metric, local_factory=lambda: _OracleLocal(metric), merge_fn=_merge_double, row_shards=row_shards)
         sh.add(xb)
-        lo, hi = shard_bounds(n, world, rank)
+        R = row_shards or world
+        lo, hi = shard_bounds(n, R, rank % R)
         assert sh.local.base == lo and len(sh.local.xb) == hi - lo and sh.ntotal == n
         D, I = sh.search(xq, k)
         np.savez(out + f".{rank}.npz", D=D, I=I)
@@ -82,6 +83,28 @@ def test_sharded_search_equals_single_index(tmp_path, metric, n, nq, k):
         z = np.load(out + f".{rank}.npz")
         np.testing.assert_array_equal(z["I"], Ir)
         np.testing.assert_array_equal(z["D"].view(np.uint32), Dr.view(np.uint32))
+
+
+@pytest.mark.parametrize("world,row_shards,nq", [(2, 1, 7), (2, 1, 8), (4, 2, 9), (4, 1, 5)])
+def test_query_groups_times_row_shards_equals_single_index(tmp_path, world, row_shards, nq):
+    """2-D layout: W ranks = Q query groups x R row shards (R = 1 is pure query sharding, ragged slices included)."""
+    from oracle import oracle
+    out = str(tmp_path / "res")
+    n, k = 1500, 12
+    mp.spawn(_worker, args=(world, _free_port(), 0, n, nq, k, out, row_shards), nprocs=world, join=True)
+    Dr, Ir = oracle.engine_spec(data.queries(nq), data.corpus(n), k, 0)
+    for rank in range(world):
+        z = np.load(out + f".{rank}.npz")
+        np.testing.assert_array_equal(z["I"], Ir)
+        np.testing.assert_array_equal(z["D"].view(np.uint32), Dr.view(np.uint32))
+
+
+def test_auto_row_shards():
+    from proqa_b200.sharded import auto_row_shards
+    assert auto_row_shards(8, 21_000_000) == 1            # 16 GB per copy: every GPU can hold the corpus
+    assert auto_row_shards(8, 100_000_000) == 2           # 77 GB: two shards
+    assert auto_row_shards(8, 1_000_000_000) == 8
+    assert auto_row_shards(1, 10**9) == 1
 
 
 def test_shard_bounds_cover_and_are_contiguous():
