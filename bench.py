@@ -205,7 +205,7 @@ def workload_config(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from proqa_b200.sharded import auto_row_shards
     rs = getattr(args, "row_shards", None)
-    R = auto_row_shards(world, wl["rows"]) if rs == "auto" else (world if rs in (None, "rows") else int(rs))
+    R = auto_row_shards(world, wl["rows"]) if rs in (None, "auto") else (world if rs == "rows" else int(rs))
     return {"workload": wl["desc"], "name": args.workload, "nq": wl["nq"], "rows": wl["rows"], "d": 128, "k": wl["k"],
             "parallelism": f"{R} row shards x {world // R} query groups" if world > 1 else "1 GPU",
             "l2_flush": "inputs larger than L2 (bf16 corpus copy %.1f GB per step)" % (wl["rows"] * 256 / 1e9)}
@@ -290,7 +290,7 @@ def run_ours(args, wl):
 
     nq, N, k = wl["nq"], wl["rows"], wl["k"]
     from proqa_b200.sharded import auto_row_shards
-    R = auto_row_shards(world, N) if args.row_shards == "auto" else (world if args.row_shards in (None, "rows") else int(args.row_shards))
+    R = auto_row_shards(world, N) if args.row_shards in (None, "auto") else (world if args.row_shards == "rows" else int(args.row_shards))
     sh = ShardedIndexFlat(128, pq.METRIC_INNER_PRODUCT, device=local_rank, row_shards=R)
     lo, hi = sh.row_bounds(N)
     qlo, qhi = sh.query_bounds(nq)
@@ -671,7 +671,8 @@ def main():
     ap.add_argument("--tier", default=None, choices=[None, "auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--row-shards", default=None,
-                    help="multi-GPU layout: number of corpus row shards R (world = R x query groups); 'rows' (default) = world, 'auto' = fewest shards that fit")
+                    help="multi-GPU layout: number of corpus row shards R (world = R x query groups); 'auto' (default) = fewest shards whose "
+                         "slice of the corpus fits the per-GPU budget, 'rows' = one shard per GPU (pure row sharding + NCCL merge)")
     ap.add_argument("--metric", default="l2", choices=["ip", "l2"], help="c4 only (group_paras.py default is L2; --spherical is IP)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
