@@ -36,43 +36,59 @@ __device__ __forceinline__ void emit_result(const MergeLaunch& a, int q, int i, 
     if (a.out_keys) a.out_keys[(size_t)q * a.k + i] = key;
 }
 
+// Candidates are examined 1024 at a time (4 per thread); accepted ones (non-empty, not below the running k-th key) are
+// appended to the shared work array, which is sorted back to its best k only when it is about to overflow — so the number
+// of sorts follows the number of ACCEPTED candidates, not the number examined (148 lists x k = 5000 used to cost a sort
+// per round).  After every sort the k-th key becomes the new admission bar.
 __global__ void __launch_bounds__(kSelThreads) pq_merge_lists_kernel(const MergeParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ int s_fill;
+    __shared__ unsigned long long s_bar;
     const MergeLaunch& a = p.a;
     const int q = blockIdx.x;
     const int t = threadIdx.x;
-    const uint32_t thr = a.gthr ? a.gthr[q] : 0u;
     const uint64_t* base = a.keys + (size_t)q * a.q_stride;
     const long long total = (long long)a.n_lists * a.list_len;
-    const int round = p.work - a.k;  // candidates examined between two compaction checks
+    constexpr int kPer = 4, kStep = kSelThreads * kPer;
 
-    if (t == 0) s_fill = 0;
+    if (t == 0) {
+        s_fill = 0;
+        s_bar = a.gthr ? ((unsigned long long)a.gthr[q] << 32) : 0ull;
+    }
     __syncthreads();
-    for (long long r0 = 0; r0 < total; r0 += round) {
-        const long long r1 = (r0 + round < total) ? r0 + round : total;
-        for (long long idx = r0 + t; idx < r1; idx += kSelThreads) {
-            const int list = (int)(idx / a.list_len);
-            const int pos = (int)(idx - (long long)list * a.list_len);
-            if (a.counts && pos >= (int)a.counts[(size_t)q * a.cnt_q_stride + list]) continue;
-            const uint64_t key = base[(size_t)list * a.list_stride + pos];
-            if (key != 0ull && uint32_t(key >> 32) >= thr) work[atomicAdd(&s_fill, 1)] = key;
+    for (long long r0 = 0; r0 < total; r0 += kStep) {
+        const unsigned long long bar = s_bar;
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const long long idx = r0 + u * kSelThreads + t;
+            if (idx < total) {
+                const int list = (int)(idx / a.list_len);
+                const int pos = (int)(idx - (long long)list * a.list_len);
+                if (!a.counts || pos < (int)a.counts[(size_t)q * a.cnt_q_stride + list]) {
+                    const uint64_t key = base[(size_t)list * a.list_stride + pos];
+                    if (key != 0ull && key >= bar) work[atomicAdd(&s_fill, 1)] = key;
+                }
+            }
         }
         __syncthreads();
         const int fill = s_fill;
-        const bool last = (r1 == total);
-        if (last || fill + round > p.work) {
+        if (fill + kStep > p.work) {  // the next batch might not fit: keep the best k
             for (int i = fill + t; i < p.work; i += kSelThreads) work[i] = 0ull;
             __syncthreads();
             block_sort_desc<kSelThreads>(work, p.work);
-            if (t == 0) s_fill = fill < a.k ? fill : a.k;
+            if (t == 0) {
+                s_fill = fill < a.k ? fill : a.k;
+                if (fill >= a.k && work[a.k - 1] > s_bar) s_bar = work[a.k - 1];
+            }
             __syncthreads();
         }
     }
-    if (total == 0) {
-        for (int i = t; i < p.work; i += kSelThreads) work[i] = 0ull;
+    {
+        const int fill = s_fill;
+        for (int i = fill + t; i < p.work; i += kSelThreads) work[i] = 0ull;
         __syncthreads();
+        block_sort_desc<kSelThreads>(work, p.work);
     }
     for (int i = t; i < a.k; i += kSelThreads) emit_result(a, q, i, work[i]);
 }
