@@ -56,6 +56,10 @@ void pq_index_free(pq_index* idx);
 /* index.add(xb)  — eval_retrieval.py:103, group_paras.py:50, trec_process.py:75.
  * Appends n rows (C-contiguous float32 [n, d]); ids are sequential insertion order. */
 int pq_index_add(pq_index* idx, int64_t n, const float* x_host);
+/* Same, rows given as IEEE half (C-contiguous float16 [n, d]) — what get_embed.py --fp16 saves (retrieval/get_embed.py:147-151)
+ * and eval_retrieval.py:100 widens on the host with .astype('float32'): here the widening happens on the device, exactly,
+ * after half as many bytes crossed PCIe. */
+int pq_index_add_f16(pq_index* idx, int64_t n, const void* x_host_f16);
 /* Same, rows already in device memory (skips the .npy -> host -> device round trip). */
 int pq_index_add_device(pq_index* idx, int64_t n, const float* x_dev);
 
@@ -88,7 +92,8 @@ int pq_index_set_profile(pq_index* idx, int on);
 /* Counters of the last search: [0]=queries served by the tensor-core tier, [1]=queries re-run by the
  * fp32 scan after a failed certificate, [2]=fp32-scan launches, [3]=tensor-core filter launches,
  * [4]=select/merge/rescore launches, [5]=total kernel launches, [6]=device microseconds (CUDA events),
- * [7]=microseconds inside the dominant kernel (only with pq_index_set_profile). */
+ * [7]=microseconds inside the dominant kernel (only with pq_index_set_profile), [8]=second attempts at an epoch (queries
+ * whose candidate slabs overflowed: rows in document order can bring a whole cluster above the threshold at once). */
 int pq_index_last_stats(const pq_index* idx, int64_t* out, int n);
 
 /* Merge G per-shard result lists (each [nq,k], best-first, global ids) into one — the kernel run

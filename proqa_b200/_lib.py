@@ -32,6 +32,7 @@ SIGNATURES = {
     "pq_index_free": (None, [_vp]),
     "pq_index_add": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
     "pq_index_add_device": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
+    "pq_index_add_f16": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
     "pq_index_search": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, _vp]),
     "pq_index_search_device": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, _vp]),
     "pq_index_reset": (ctypes.c_int, [_vp]),

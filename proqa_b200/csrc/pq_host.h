@@ -63,7 +63,7 @@ struct pq_index {
     pq::DevBuf ws_rr_idx, ws_rr_q, ws_rr_qn, ws_rr_D, ws_rr_I;
     pq::DevBuf ws_mma[12];
 
-    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
     // optional per-kernel timing of the dominant kernel (fp32 scan / tensor-core filter): event pairs on the stream
     bool profile = false;

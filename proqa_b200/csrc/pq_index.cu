@@ -7,6 +7,7 @@
 #include "pq_common.cuh"
 #include "pq_host.h"
 
+#include <cuda_fp16.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -258,6 +259,76 @@ static int staged_add_rows(pq_index* ix, float* dst_dev, const float* x_host, in
     return PQ_OK;
 }
 
+// fp16 rows (what get_embed.py --fp16 writes, get_embed.py:147-151) -> fp32 rows: exact, and half the bytes over PCIe.
+__global__ void pq_half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n_elems) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i + 8 <= n_elems) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(in + i);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        float4 a, b;
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+        a = make_float4(f0.x, f0.y, f1.x, f1.y);
+        b = make_float4(f2.x, f2.y, f3.x, f3.y);
+        *reinterpret_cast<float4*>(out + i) = a;
+        *reinterpret_cast<float4*>(out + i + 4) = b;
+    }
+}
+
+// Caller holds g_device_mutex.  x_host: n rows of 128 IEEE half values.
+int index_add_f16_locked(pq_index* ix, int64_t n, const void* x_host) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    if (n < 0 || (n > 0 && !x_host)) return set_error(PQ_ERR_INVALID, "add_f16: bad arguments");
+    if (n == 0) return PQ_OK;
+    if (ix->ntotal + n > (int64_t)0x7fffff00) return set_error(PQ_ERR_UNSUPPORTED, "add: more than 2^31 rows per shard");
+    int rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    rc = index_grow(ix, ix->ntotal + n);
+    if (rc) return rc;
+    if (!g_staging.init()) return set_error(PQ_ERR_OOM, "add_f16: pinned staging buffers unavailable");
+    DevBuf tmp[2];
+    const int64_t rows_per_chunk = (int64_t)(StagingBuffers::kBytes / (kDim * 2));
+    rc = tmp[0].ensure(StagingBuffers::kBytes);
+    if (!rc) rc = tmp[1].ensure(StagingBuffers::kBytes);
+    if (rc) {
+        tmp[0].release();
+        tmp[1].release();
+        return rc;
+    }
+    uint32_t* sc = (uint32_t*)ix->scalars.p;
+    const uint16_t* src = (const uint16_t*)x_host;
+    int which = 0;
+    cudaError_t e = cudaSuccess;
+    for (int64_t a = 0; a < n && e == cudaSuccess; a += rows_per_chunk, which ^= 1) {
+        const int64_t rows = std::min(rows_per_chunk, n - a);
+        e = cudaEventSynchronize(g_staging.done[which]);
+        if (e != cudaSuccess) break;
+        parallel_memcpy(g_staging.buf[which], src + (size_t)a * kDim, (size_t)rows * kDim * 2);
+        e = cudaMemcpyAsync(tmp[which].p, g_staging.buf[which], (size_t)rows * kDim * 2, cudaMemcpyHostToDevice, ix->stream);
+        if (e != cudaSuccess) break;
+        e = cudaEventRecord(g_staging.done[which], ix->stream);
+        if (e != cudaSuccess) break;
+        float* d = (float*)ix->rows_f32.p + (size_t)(ix->ntotal + a) * kDim;
+        const long long elems = (long long)rows * kDim;
+        pq_half_to_float_kernel<<<(unsigned)((elems / 8 + 255) / 256), 256, 0, ix->stream>>>((const __half*)tmp[which].p, d, elems);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
+        e = prep_rows_launch(d, rows, (uint16_t*)ix->rows_bf16.p + (size_t)(ix->ntotal + a) * kDim, (float*)ix->norms.p + ix->ntotal + a, sc + 0, sc + 1,
+                             nullptr, ix->stream);
+    }
+    uint32_t host_sc[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_sc, sc, 8, cudaMemcpyDeviceToHost, ix->stream);
+    const cudaError_t e2 = cudaStreamSynchronize(ix->stream);
+    tmp[0].release();
+    tmp[1].release();
+    if (e != cudaSuccess) return cuda_fail(e, __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return cuda_fail(e2, __FILE__, __LINE__);
+    memcpy(&ix->max_norm2, &host_sc[0], 4);
+    ix->has_nonfinite = host_sc[1] != 0;
+    ix->ntotal += n;
+    return index_refresh_maps(ix);
+}
+
 // Caller holds g_device_mutex.
 int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
@@ -498,6 +569,10 @@ int pq_index_add_device(pq_index* ix, int64_t n, const float* x_dev) {
     std::lock_guard<std::mutex> lock(g_device_mutex);
     return index_add_locked(ix, n, x_dev, true);
 }
+int pq_index_add_f16(pq_index* ix, int64_t n, const void* x_host_f16) {
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    return index_add_f16_locked(ix, n, x_host_f16);
+}
 
 int pq_index_search(pq_index* ix, int64_t nq, const float* xq, int64_t k, float* D, int64_t* I) {
     int rc = check_search_args(ix, nq, xq, k, D, I);
@@ -588,7 +663,7 @@ int pq_index_set_profile(pq_index* ix, int on) {
 }
 int pq_index_last_stats(const pq_index* ix, int64_t* out, int n) {
     if (!ix || !out || n < 0) return set_error(PQ_ERR_INVALID, "last_stats: bad arguments");
-    for (int i = 0; i < n; ++i) out[i] = i < 8 ? ix->stats[i] : 0;
+    for (int i = 0; i < n; ++i) out[i] = i < 10 ? ix->stats[i] : 0;
     return PQ_OK;
 }
 

@@ -80,6 +80,10 @@ struct MmaParams {
     int cap;
     int n_sub;               // candidate slabs per query = max(s1, s0) * 2 (one per epilogue warp set)
     int k1_adapt;
+    // second attempt at an epoch ("redo"): only queries whose slabs overflowed the first time (redo[q] != 0) take part,
+    // with the tighter threshold the first attempt produced; the kernel returns at once when no query asked for it
+    const uint32_t* redo;      // [nq_pad] or null
+    const uint32_t* any_redo;  // device counter, read at kernel start when redo != null
 };
 
 // D[tmem] (+)= A[tmem] * B[smem desc]^T: the stationary operand (queries) is read from tensor memory, so shared
@@ -226,13 +230,14 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
     const int mt0 = group * p.base + min(group, p.rem);
     const int m = min(M_TILES, p.base + (group < p.rem ? 1 : 0));
 
+    if (p.redo != nullptr && *p.any_redo == 0) return;  // redo launch with nothing to redo (block-uniform, before any setup)
+    // Row tiles are dealt to the slices round-robin (slice s takes tiles s, s + n_slices, ...): a run of consecutive rows that
+    // all beat the threshold — a topic cluster in a corpus stored in document order — spreads over every slab of the query
+    // instead of flooding one.
     const long long total_tiles = (p.row_end - p.row_begin + kBN - 1) / kBN;
-    const long long tiles_per_slice = (total_tiles + n_slices - 1) / n_slices;
-    const long long tile_begin = (long long)slice * tiles_per_slice;
-    long long nt = total_tiles - tile_begin;
-    nt = nt < 0 ? 0 : (nt > tiles_per_slice ? tiles_per_slice : nt);
-    const int ntiles = (int)nt;
-    const long long row0 = p.row_begin + tile_begin * kBN;
+    const int ntiles = total_tiles > slice ? (int)((total_tiles - slice + n_slices - 1) / n_slices) : 0;
+    const long long row0 = p.row_begin + (long long)slice * kBN;
+    const long long tile_stride = (long long)n_slices * kBN;  // rows between two consecutive tiles of this CTA
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_c);
     if (warp == 1) {
@@ -292,7 +297,7 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
             mbar_wait(&ctrl->empty[s], ph ^ 1u);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&ctrl->full[s], kTileBytes + (kL2 ? kBN * 4 : 0));
-                const int y = (int)(row0 + (long long)t * kBN);
+                const int y = (int)(row0 + (long long)t * tile_stride);
 #pragma unroll
                 for (int pnl = 0; pnl < 2; ++pnl)
                     tma_load_2d(smem_b + (size_t)s * kStageBytes + pnl * kPanelBytes, &tmap_c, pnl * 64, y, &ctrl->full[s]);
@@ -349,7 +354,7 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         const int sub = slice * 2 + set;
         for (int mi = 0; mi < m; ++mi) {
             const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
-            s_thr[mi * 256 + tid_e] = p.thr[q];
+            s_thr[mi * 256 + tid_e] = (p.redo == nullptr || p.redo[q] != 0u) ? p.thr[q] : INFINITY;
             s_2e[mi * 256 + tid_e] = p.two_e[q];
             s_cnt[mi * 256 + tid_e] = 0;
         }
@@ -357,7 +362,7 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         const uint32_t cap = (uint32_t)p.cap;
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
-            const uint32_t base_row = (uint32_t)(row0 + (long long)t * kBN + set * kSubN);
+            const uint32_t base_row = (uint32_t)(row0 + (long long)t * tile_stride + set * kSubN);
             const int s = t % kStages;
             const float4* norms = reinterpret_cast<const float4*>(smem_b + (size_t)s * kStageBytes + kTileBytes) + set * (kSubN / 4);
             if (kL2) mbar_wait(&ctrl->full[s], (uint32_t)(t / kStages) & 1u);  // already complete (the MMAs needed it): acquire only
@@ -425,6 +430,8 @@ struct QState {
     float* dropmax;      // [nq_pad]
     uint32_t* overflow;  // [nq_pad]
     uint64_t* carry;     // [nq_pad][kp]
+    uint32_t* redo;      // [nq_pad] this epoch's slabs overflowed: run the epoch again for this query with the new threshold
+    uint32_t* any_redo;  // [1] number of queries with redo set
 };
 
 __global__ void pq_mma_init_state_kernel(QState st, const float* __restrict__ q_norm2, const uint8_t* __restrict__ q_bad, int nq,
@@ -446,7 +453,10 @@ struct EpochSelParams {
     QState st;
     const uint64_t* cand_keys;
     const uint32_t* cand_cnt;
-    int n_sub, cap, kp, k, lmax;  // lmax: power of two >= max(kp, cap); shared work array holds 2*lmax keys
+    int n_sub, cap, kp, k, lmax;  // lmax: keys the shared pool holds (old carry + one chunk of candidates)
+    int is_redo;                  // second attempt at this epoch: only queries with st.redo set take part
+    int allow_redo;               // first attempt: a slab overflow asks for a second attempt instead of failing the query
+    long long row_begin;          // first row of the epoch (a redo drops the carry entries the first attempt took from it)
 };
 
 // One CTA per query: carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
@@ -538,6 +548,7 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
     __shared__ unsigned long long s_dropkey;
     const int q = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (p.is_redo && p.st.redo[q] == 0u) return;  // block-uniform: this query's first attempt was fine
     uint64_t* carry = p.st.carry + (size_t)q * p.kp;
     const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
     const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
@@ -596,11 +607,13 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
             const uint64_t pivot = block_radix_select(pool, n, p.kp, hist, s_u64, s_int);
             if (t == 0) s_slot = 0;
             __syncthreads();
+            // truncation bookkeeping: when this epoch is going to be run again, its own rows are regenerated, not lost
+            const bool redo_coming = s_ovf && p.allow_redo;
             uint64_t dropped = 0ull;
             for (int i = t; i < n; i += 256) {
                 const uint64_t k = pool[i];
                 if (k >= pivot) out[atomicAdd(&s_slot, 1)] = k;
-                else dropped = max(dropped, k);
+                else if (!redo_coming || (long long)key_row(k) < p.row_begin) dropped = max(dropped, k);
             }
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) dropped = max(dropped, __shfl_xor_sync(0xffffffffu, dropped, s));
@@ -618,12 +631,51 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
     for (int i = nc + t; i < p.kp; i += 256) pool[i] = 0ull;
     __syncthreads();
     block_sort_desc<256>(pool, p.kp);
-    for (int i = t; i < p.kp; i += 256) carry[i] = pool[i];
+    const bool ask_redo = s_ovf && p.allow_redo;
     if (t == 0) {
-        if (s_dropkey != 0ull) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], key_score((uint64_t)s_dropkey));
-        if (s_ovf) p.st.overflow[q] = 1u;
+        // the k-th best of what fitted is the score of a real row: a valid (and usually much tighter) threshold either way
         const uint64_t kth = pool[p.k - 1];
         if (kth != 0ull) p.st.thr[q] = fmaxf(p.st.thr[q], key_score(kth) - p.st.two_e[q]);
+        if (s_dropkey != 0ull) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], key_score((uint64_t)s_dropkey));
+        if (ask_redo) {
+            p.st.redo[q] = 1u;
+            atomicAdd(p.st.any_redo, 1u);
+            atomicAdd(p.st.any_redo + 1, 1u);  // running total of second attempts, reported in the search statistics
+        } else if (s_ovf) {
+            p.st.overflow[q] = 1u;
+        }
+    }
+    if (ask_redo) {
+        // Some candidates of this epoch were lost.  Keep only what earlier epochs contributed (rows below row_begin) and
+        // let the second attempt regenerate this epoch's candidates — all of them, now against the tighter threshold.
+        // (Entries of earlier epochs that fell out of the top-K' above did so against real rows: they stay dropped and were
+        // accounted in dropmax like any other truncation.)
+        __syncthreads();
+        if (t == 0) s_slot = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < p.kp; i0 += 256) {   // ordered compaction, 256 entries at a time
+            const int i = i0 + t;
+            const uint64_t key = i < p.kp ? pool[i] : 0ull;
+            const bool keep = key != 0ull && (long long)key_row(key) < p.row_begin;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            __shared__ int s_wbase[8];
+            if (lane == 0) s_wbase[warp] = __popc(m);
+            __syncthreads();
+            int before = s_slot;
+            for (int w = 0; w < warp; ++w) before += s_wbase[w];
+            if (keep) out[before + __popc(m & ((1u << lane) - 1u))] = key;
+            __syncthreads();
+            if (t == 0) {
+                int tot = 0;
+                for (int w = 0; w < 8; ++w) tot += s_wbase[w];
+                s_slot += tot;
+            }
+            __syncthreads();
+        }
+        const int kept = s_slot;
+        for (int i = t; i < p.kp; i += 256) carry[i] = i < kept ? out[i] : 0ull;
+    } else {
+        for (int i = t; i < p.kp; i += 256) carry[i] = pool[i];
     }
 }
 
@@ -915,9 +967,12 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
                     ep.cap = kBN / gs.subs_per_slice;
                 } else {
                     pick_slices(gs, n_mtiles, tiles, ix->n_sms, &ep.s1, &ep.s0);
+                    // survivors per query with the threshold frozen at the start of the epoch: about k * (end/begin - 1), times
+                    // ~1.5 for the 2E margin, on exchangeable rows; three times that is provisioned (rows in document order
+                    // bring whole clusters above the threshold at once — beyond the provision the epoch is run a second time)
                     const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
-                    const double expect = (double)kp * log((double)ep.end / (double)ep.begin) / slabs;
-                    ep.cap = std::min(4096, std::max(64, next_pow2i((int)(4.0 * expect) + 32)));
+                    const double expect = 1.5 * (double)k * ((double)(ep.end - ep.begin) / (double)ep.begin) / slabs;
+                    ep.cap = std::min(4096, std::max(64, next_pow2i((int)(3.0 * expect) + 64)));
                 }
                 plan.push_back(ep);
                 begin = ep.end;
@@ -941,6 +996,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         if (!rc) rc = w[5].ensure(max_slab);                      // candidate slabs
         if (!rc) rc = w[6].ensure(max_cnt);                       // slab counts
         if (!rc) rc = w[7].ensure((size_t)nq_pad);                // fail flags
+        if (!rc) rc = w[8].ensure((size_t)nq_pad * 4 + 256);      // redo flags, then the any_redo counter
         if (rc) return rc;
         QState st;
         st.thr = (float*)w[0].p;
@@ -948,8 +1004,11 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         st.dropmax = (float*)w[2].p;
         st.overflow = (uint32_t*)w[3].p;
         st.carry = (uint64_t*)w[4].p;
+        st.redo = (uint32_t*)w[8].p;
+        st.any_redo = st.redo + nq_pad;
 
         if (!k1) PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
+        PQ_CUDA(cudaMemsetAsync(st.any_redo, 0, 8, ix->stream));
         pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, dq_bad, nq, nq_pad, kp, ix->max_norm2, ix->metric);
         PQ_CUDA(cudaGetLastError());
         ix->stats[5] += 1;
@@ -973,6 +1032,8 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.cap = ep.cap;
             mp.n_sub = std::max(ep.s1, ep.s0) * gs.subs_per_slice;
             mp.k1_adapt = k1 ? 1 : 0;
+            mp.redo = nullptr;
+            mp.any_redo = nullptr;
             const int n_ctas = gs.rem * ep.s1 + (gs.n_groups - gs.rem) * ep.s0;
             // slabs a CTA never touches (unequal slice counts, query tiles owned by the other warp set) must read as empty
             PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
@@ -1008,6 +1069,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
                 continue;
             }
 
+            const bool can_overflow = ep.begin > 0;  // the bootstrap epoch's slabs hold every row they can see
             EpochSelParams sp;
             sp.st = st;
             sp.cand_keys = mp.cand_keys;
@@ -1017,12 +1079,30 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.kp = kp;
             sp.k = k;
             sp.lmax = std::max(2 * kp, 4096);  // pool: old carry + one chunk of candidates
+            sp.is_redo = 0;
+            sp.allow_redo = can_overflow ? 1 : 0;
+            sp.row_begin = ep.begin;
             const size_t smem = ((size_t)sp.lmax + kp) * 8 + (size_t)sp.n_sub * 8;
             PQ_CUDA(cudaFuncSetAttribute(pq_epoch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (can_overflow) PQ_CUDA(cudaMemsetAsync(st.redo, 0, (size_t)nq_pad * 4 + 4, ix->stream));
             pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
             PQ_CUDA(cudaGetLastError());
             ix->stats[4] += 1;
             ix->stats[5] += 1;
+            if (can_overflow) {
+                // Second attempt for the queries whose slabs overflowed (rows in document order: a whole cluster above the
+                // threshold), against the threshold their first attempt produced.  Both kernels return at once when no
+                // query asked for it — the common case costs two empty launches, no host synchronisation.
+                mp.redo = st.redo;
+                mp.any_redo = st.any_redo;
+                PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
+                PQ_CUDA(launch_filter_any(gs.m_max, ix->metric == kMetricL2, false, ix->tmap_bf16, mp, n_ctas, ix->stream));
+                sp.is_redo = 1;
+                sp.allow_redo = 0;
+                pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
+                PQ_CUDA(cudaGetLastError());
+                ix->stats[5] += 2;
+            }
         }
 
         // ---- exact rescoring + certificate ------------------------------------------------------
@@ -1051,8 +1131,11 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         }
 
         std::vector<uint8_t> fail((size_t)nq);
+        uint32_t redo_counts[2] = {0, 0};
         PQ_CUDA(cudaMemcpyAsync(fail.data(), w[7].p, (size_t)nq, cudaMemcpyDeviceToHost, ix->stream));
+        PQ_CUDA(cudaMemcpyAsync(redo_counts, st.any_redo, 8, cudaMemcpyDeviceToHost, ix->stream));
         PQ_CUDA(cudaStreamSynchronize(ix->stream));
+        ix->stats[8] += redo_counts[1];
         for (int q = 0; q < nq; ++q)
             if (fail[q]) rerun->push_back(qb + q);
     }

@@ -23,13 +23,13 @@ from . import _lib
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 
-_LAST_STATS = [0] * 8
+_LAST_STATS = [0] * 10
 
 
 def last_search_stats():
     """Counters of the most recent search in this process (see pq_index_last_stats in include/proqa_b200.h)."""
     keys = ["tc_queries", "fp32_rerun_queries", "fp32_scan_launches", "tc_filter_launches", "select_launches", "kernel_launches",
-            "device_us", "dominant_kernel_us"]
+            "device_us", "dominant_kernel_us", "epoch_second_attempts", "reserved"]
     return dict(zip(keys, _LAST_STATS))
 
 
@@ -61,6 +61,15 @@ class IndexFlat:
         return None
 
     def add(self, x):
+        """float32 [n, d] as FAISS requires; a float16 array (embeddings saved by get_embed.py --fp16, before the
+        .astype('float32') of eval_retrieval.py:100) is accepted too and widened on the device."""
+        if getattr(x, "dtype", None) == np.float16:
+            x = np.ascontiguousarray(x)
+            assert x.ndim == 2, "add expects a 2-D array"
+            n, d = x.shape
+            assert d == self.d, f"dimension mismatch: got {d}, index has {self.d}"
+            _lib.check(_lib.lib().pq_index_add_f16(self._h, n, x.ctypes.data), "add")
+            return
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2, "add expects a 2-D array"
         n, d = x.shape
@@ -114,8 +123,8 @@ class IndexFlat:
         _lib.check(_lib.lib().pq_index_set_profile(self._h, 1 if on else 0), "set_profile")
 
     def _pull_stats(self):
-        buf = (ctypes.c_int64 * 8)()
-        if _lib.lib().pq_index_last_stats(self._h, buf, 8) == 0:
+        buf = (ctypes.c_int64 * 10)()
+        if _lib.lib().pq_index_last_stats(self._h, buf, 10) == 0:
             _LAST_STATS[:] = list(buf)
         self.last_stats = list(buf)
 

@@ -258,3 +258,41 @@ def test_online_sampler_shape_nq1_large_k():
     ix = _index(0, xb, "auto")
     D, I = ix.search(xq, 5000)
     _assert_bit_exact(D, I, *oracle.engine_spec(xq, xb, 5000, 0))
+
+
+def test_add_float16_rows_matches_host_widening():
+    """index.add(fp16 array) == index.add(fp16.astype(float32)) (eval_retrieval.py:100), through the staged device path too."""
+    xh = data.corpus(300000, kind="fp16").astype(np.float16)     # 77 MB: more than one staging chunk
+    xq = data.queries(9)
+    a, b = _index(0, np.zeros((0, 128), np.float32), "auto"), _index(0, np.zeros((0, 128), np.float32), "auto")
+    a.add(xh)
+    b.add(xh.astype(np.float32))
+    assert a.ntotal == b.ntotal == 300000
+    Da, Ia = a.search(xq, 20)
+    Db, Ib = b.search(xq, 20)
+    _assert_bit_exact(Da, Ia, Db, Ib)
+
+
+@pytest.mark.parametrize("ncl,nq,spread,expect_second_attempts", [(150, 200, 0.7, False), (8, 600, 2.0, True)])
+def test_corpus_in_document_order_stays_on_the_tensor_tier(ncl, nq, spread, expect_second_attempts):
+    """Real paragraph indexes are stored in document order: the rows that match a query sit together, far from the prefix
+    the first thresholds come from, and enter all at once.  The slabs interleave row tiles and an overflowing epoch is run a
+    second time with the threshold its first attempt produced — no query may need the fp32 re-scan, results stay exact.
+    (8 clusters of ~37k rows: more survivors in one epoch than the slabs of a query hold.  With tightly packed clusters the
+    K'-truncation certificate itself can fail — hundreds of rows within 2E of the k-th — and the fp32 re-scan takes over; the
+    wide spread used here keeps the top of each cluster separable, as retrieval scores are.)"""
+    rng = np.random.default_rng(11)
+    n = 300000
+    cent = rng.standard_normal((ncl, 128)).astype(np.float32)
+    lab = np.sort(rng.integers(0, ncl, n))                                  # topic-sorted corpus
+    xb = (cent[lab] + spread * rng.standard_normal((n, 128))).astype(np.float32)
+    qcl = rng.integers(0, ncl, nq)
+    xq = (cent[qcl] + 0.3 * rng.standard_normal((nq, 128))).astype(np.float32)
+    ix = _index(0, xb, "bf16")
+    D, I = ix.search(xq, 100)
+    Dr, Ir = oracle.engine_spec(xq, xb, 100, 0)
+    _assert_bit_exact(D, I, Dr, Ir)
+    st = ix.last_stats
+    assert st[1] == 0, f"{st[1]} queries fell back to the fp32 scan (second attempts: {st[8]})"
+    if expect_second_attempts:
+        assert st[8] > 0, "the second-attempt path was not exercised"
