@@ -51,6 +51,7 @@ struct pq_index {
     int64_t capacity = 0;
     int64_t id_base = 0;
     float max_norm2 = 0.f;       // max squared row norm (drives the bf16 filter's error bound)
+    float max_resid2 = 0.f;      // max |x - bf16(x)|^2 over the rows (same)
     bool has_nonfinite = false;  // some row is inf/NaN (or overflows bf16): tensor-core tier disabled
 
     // HBM layout of the shard: fp32 rows [cap,128] (512 B/row), bf16 copy [cap,128] (256 B/row), squared norms [cap]
@@ -58,7 +59,7 @@ struct pq_index {
     CUtensorMap tmap_f32, tmap_bf16;
 
     // per-search workspaces (grow-only)
-    pq::DevBuf ws_q, ws_D, ws_I, ws_qnorm, ws_qbf16, ws_qbad;
+    pq::DevBuf ws_q, ws_D, ws_I, ws_qnorm, ws_qbf16, ws_qbad, ws_qresid;
     pq::DevBuf ws_scan_keys, ws_gthr;
     pq::DevBuf ws_rr_idx, ws_rr_q, ws_rr_qn, ws_rr_D, ws_rr_I;
     pq::DevBuf ws_mma[12];
@@ -100,7 +101,7 @@ struct pq_index {
 
     void release_all() {
         pq::DevBuf* all[] = {&rows_f32, &rows_bf16, &norms,    &scalars,  &ws_q,     &ws_D,      &ws_I,      &ws_qnorm, &ws_qbf16,
-                             &ws_qbad,  &ws_scan_keys, &ws_gthr, &ws_rr_idx, &ws_rr_q, &ws_rr_qn, &ws_rr_D,   &ws_rr_I};
+                             &ws_qbad,  &ws_qresid, &ws_scan_keys, &ws_gthr, &ws_rr_idx, &ws_rr_q, &ws_rr_qn, &ws_rr_D,   &ws_rr_I};
         for (pq::DevBuf* b : all) b->release();
         for (pq::DevBuf& b : ws_mma) b.release();
     }

@@ -243,7 +243,7 @@ static int staged_add_rows(pq_index* ix, float* dst_dev, const float* x_host, in
     if (n * kDim * 4 < (int64_t)(8u << 20) || !g_staging.init()) {  // small (k-means centroids, tests): one plain copy
         PQ_CUDA(cudaMemcpyAsync(dst_dev, x_host, (size_t)n * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
         return cuda_ok_or_fail(prep_rows_launch(dst_dev, n, (uint16_t*)ix->rows_bf16.p + (size_t)first_row * kDim, (float*)ix->norms.p + first_row,
-                                                sc + 0, sc + 1, nullptr, ix->stream));
+                                                sc + 0, sc + 1, nullptr, nullptr, sc + 2, ix->stream));
     }
     int which = 0;
     for (int64_t a = 0; a < n; a += rows_per_chunk, which ^= 1) {
@@ -254,7 +254,7 @@ static int staged_add_rows(pq_index* ix, float* dst_dev, const float* x_host, in
         PQ_CUDA(cudaMemcpyAsync(d, g_staging.buf[which], (size_t)rows * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
         PQ_CUDA(cudaEventRecord(g_staging.done[which], ix->stream));
         PQ_CUDA(prep_rows_launch(d, rows, (uint16_t*)ix->rows_bf16.p + (size_t)(first_row + a) * kDim, (float*)ix->norms.p + first_row + a, sc + 0,
-                                 sc + 1, nullptr, ix->stream));
+                                 sc + 1, nullptr, nullptr, sc + 2, ix->stream));
     }
     return PQ_OK;
 }
@@ -314,16 +314,17 @@ int index_add_f16_locked(pq_index* ix, int64_t n, const void* x_host) {
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
         e = prep_rows_launch(d, rows, (uint16_t*)ix->rows_bf16.p + (size_t)(ix->ntotal + a) * kDim, (float*)ix->norms.p + ix->ntotal + a, sc + 0, sc + 1,
-                             nullptr, ix->stream);
+                             nullptr, nullptr, sc + 2, ix->stream);
     }
-    uint32_t host_sc[2] = {0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(host_sc, sc, 8, cudaMemcpyDeviceToHost, ix->stream);
+    uint32_t host_sc[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_sc, sc, 12, cudaMemcpyDeviceToHost, ix->stream);
     const cudaError_t e2 = cudaStreamSynchronize(ix->stream);
     tmp[0].release();
     tmp[1].release();
     if (e != cudaSuccess) return cuda_fail(e, __FILE__, __LINE__);
     if (e2 != cudaSuccess) return cuda_fail(e2, __FILE__, __LINE__);
     memcpy(&ix->max_norm2, &host_sc[0], 4);
+    memcpy(&ix->max_resid2, &host_sc[2], 4);
     ix->has_nonfinite = host_sc[1] != 0;
     ix->ntotal += n;
     return index_refresh_maps(ix);
@@ -345,15 +346,16 @@ int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device) {
     if (on_device) {
         PQ_CUDA(cudaMemcpyAsync(dst, x, (size_t)n * kDim * 4, cudaMemcpyDeviceToDevice, ix->stream));
         PQ_CUDA(prep_rows_launch(dst, n, (uint16_t*)ix->rows_bf16.p + (size_t)ix->ntotal * kDim, (float*)ix->norms.p + ix->ntotal, sc + 0,
-                                 sc + 1, nullptr, ix->stream));
+                                 sc + 1, nullptr, nullptr, sc + 2, ix->stream));
     } else {
         rc = staged_add_rows(ix, dst, x, n, ix->ntotal);
         if (rc) return rc;
     }
-    uint32_t host_sc[2];
-    PQ_CUDA(cudaMemcpyAsync(host_sc, sc, 8, cudaMemcpyDeviceToHost, ix->stream));
+    uint32_t host_sc[3];
+    PQ_CUDA(cudaMemcpyAsync(host_sc, sc, 12, cudaMemcpyDeviceToHost, ix->stream));
     PQ_CUDA(cudaStreamSynchronize(ix->stream));
     memcpy(&ix->max_norm2, &host_sc[0], 4);
+    memcpy(&ix->max_resid2, &host_sc[2], 4);
     ix->has_nonfinite = host_sc[1] != 0;
     ix->ntotal += n;
     return index_refresh_maps(ix);
@@ -462,10 +464,11 @@ int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t k, flo
     int rc = ix->ws_qnorm.ensure((size_t)nq_pad * 4);
     if (!rc) rc = ix->ws_qbf16.ensure((size_t)nq_pad * kDim * 2);
     if (!rc) rc = ix->ws_qbad.ensure((size_t)nq_pad);
+    if (!rc) rc = ix->ws_qresid.ensure((size_t)nq_pad * 4);
     if (rc) return rc;
     PQ_CUDA(cudaMemsetAsync(ix->ws_qbf16.p, 0, (size_t)nq_pad * kDim * 2, ix->stream));
     PQ_CUDA(prep_rows_launch(dq, nq, (uint16_t*)ix->ws_qbf16.p, (float*)ix->ws_qnorm.p, nullptr, nullptr, (uint8_t*)ix->ws_qbad.p,
-                             ix->stream));
+                             (float*)ix->ws_qresid.p, nullptr, ix->stream));
     ix->stats[5] += 1;
 
     if (tier_uses_mma(ix, nq, k)) {
@@ -619,6 +622,7 @@ namespace pq {
 int index_reset_locked(pq_index* ix) {
     ix->ntotal = 0;
     ix->max_norm2 = 0.f;
+    ix->max_resid2 = 0.f;
     ix->has_nonfinite = false;
     if (ix->device_ready) {
         PQ_CUDA(cudaSetDevice(ix->device));

@@ -65,7 +65,8 @@ cudaError_t merge_di_launch(const float* D_in, const long long* I_in, int n_list
 // Row preparation (corpus rows at add(), query rows at search()): squared norms (engine_dot(row,row)),
 // bf16 copy, max squared norm, non-finite detection (global flag and/or per-row byte).  Optional outputs may be null
 // except rows_bf16 and norms.
+// resid2 (optional, per row) / max_resid_bits (optional, running maximum): |x - bf16(x)|^2, rounded up.
 cudaError_t prep_rows_launch(const float* rows, long long n, uint16_t* rows_bf16, float* norms, uint32_t* max_norm_bits,
-                             uint32_t* nonfinite_flag, uint8_t* row_bad, cudaStream_t stream);
+                             uint32_t* nonfinite_flag, uint8_t* row_bad, float* resid2, uint32_t* max_resid_bits, cudaStream_t stream);
 
 }  // namespace pq

@@ -50,9 +50,6 @@ constexpr int kEpiWarps = 8;
 constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
 constexpr int kMaxMTiles = 4;       // 4 x 64 TMEM columns of bf16 queries + 4 x 64 columns of accumulators = 512
 
-// eps: bf16 rounding of both operands (2^-8 + 2^-18), tensor-core fp32 accumulation slack (2^-13) and the
-// fp32 score's own rounding (<= 19 * 2^-24), relative to sum|q_i c_i| <= |q||c|; plus 2% head-room.
-constexpr float kEps = 0.0042f;
 
 struct MmaCtrl {
     uint64_t full[kStages];
@@ -190,7 +187,9 @@ __device__ __forceinline__ void mma_filter32_k1(float (&v)[32], float& thr, floa
     const float th = thr;
     if (__any_sync(0xffffffffu, mx >= th)) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) mma_append_if(g4[g] >= th, slab, cnt, cap, g4[g], base_row + 4 * g);
+        for (int g = 0; g < 8; ++g) {
+            if (__any_sync(0xffffffffu, g4[g] >= th)) mma_append_if(g4[g] >= th, slab, cnt, cap, g4[g], base_row + 4 * g);
+        }
     }
 }
 
@@ -434,15 +433,26 @@ struct QState {
     uint32_t* any_redo;  // [1] number of queries with redo set
 };
 
-__global__ void pq_mma_init_state_kernel(QState st, const float* __restrict__ q_norm2, const uint8_t* __restrict__ q_bad, int nq,
-                                         int nq_pad, int kp, float max_norm2, int metric) {
+// Error bound of the bf16 filter, per query:
+//   |sum q^ c^ - sum q c| <= |q^ - q| |c^| + |q| |c^ - c|                      (Cauchy-Schwarz on the two rounding residuals)
+//   + tensor-core accumulation (products of bf16 are exact in fp32; <= 128 truncating adds)   <= 2^-14 |q^| |c^|
+//   + rounding of the engine's own fp32 score (19 roundings)                                    <= 2.4e-6 |q| |c|
+// with |q^ - q| measured per query, max |c^ - c| and max |c| measured over the corpus at add().
+__global__ void pq_mma_init_state_kernel(QState st, const float* __restrict__ q_norm2, const float* __restrict__ q_resid2,
+                                         const uint8_t* __restrict__ q_bad, int nq, int nq_pad, int kp, float max_norm2, float max_resid2,
+                                         int metric) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq_pad) return;
     const bool live = q < nq && !q_bad[q];
-    // 2E with E = eps * |q| * max|c|; sqrt rounded up by the head-room in kEps
-    float e2 = live ? 2.f * kEps * sqrtf(q_norm2[q]) * sqrtf(max_norm2) : 0.f;
-    // L2 ranks by 2<q,x> - |x|^2: twice the inner-product error, plus the fp32 rounding of that fmaf on both sides
-    if (metric == kMetricL2) e2 = 2.f * e2 + 4.8e-7f * (2.f * sqrtf(q_norm2[q]) * sqrtf(max_norm2) + max_norm2);
+    float e2 = 0.f;
+    if (live) {
+        const float Q = sqrtf(q_norm2[q]) * 1.000001f, rq = sqrtf(q_resid2[q]) * 1.000001f;
+        const float C = sqrtf(max_norm2) * 1.000001f, rc = sqrtf(max_resid2) * 1.000001f;
+        const float E = 1.0002f * (rq * (C + rc) + Q * rc) + 6.2e-5f * (Q + rq) * (C + rc) + 2.4e-6f * Q * C;
+        e2 = 2.f * E;
+        // L2 ranks by 2<q,x> - |x|^2: twice the inner-product error, plus the fp32 rounding of that fmaf on both sides
+        if (metric == kMetricL2) e2 = 2.f * e2 + 4.8e-7f * (2.f * Q * C + max_norm2);
+    }
     st.two_e[q] = e2;
     st.thr[q] = live ? PQ_THR_FLOOR : INFINITY;
     st.dropmax[q] = -INFINITY;
@@ -691,6 +701,7 @@ struct RescoreParams {
     float* D;
     long long* I;
     uint8_t* fail;
+    uint32_t* fail_count;
 };
 
 // One CTA per query: exact fp32 scores for the carry list, final order, certificate.
@@ -762,6 +773,7 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) 
             if (dropmax >= bar) fail = true;
         }
         p.fail[q] = fail ? 1 : 0;
+        if (fail) atomicAdd(p.fail_count, 1u);
     }
 }
 
@@ -786,6 +798,7 @@ struct K1Params {
     float* D;
     long long* I;
     uint8_t* fail;
+    uint32_t* fail_count;  // number of queries flagged in `fail` (the host fetches the flags only when it is not zero)
 };
 
 __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
@@ -847,6 +860,7 @@ __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
         p.D[q] = d;
         p.I[q] = id;
         p.fail[q] = fail ? 1 : 0;
+        if (fail) atomicAdd(p.fail_count, 1u);
     }
 }
 
@@ -1008,8 +1022,9 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         st.any_redo = st.redo + nq_pad;
 
         if (!k1) PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
-        PQ_CUDA(cudaMemsetAsync(st.any_redo, 0, 8, ix->stream));
-        pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, dq_bad, nq, nq_pad, kp, ix->max_norm2, ix->metric);
+        PQ_CUDA(cudaMemsetAsync(st.any_redo, 0, 12, ix->stream));  // any_redo, total second attempts, failed queries
+        pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, (const float*)ix->ws_qresid.p + qb, dq_bad, nq, nq_pad, kp,
+                                                                             ix->max_norm2, ix->max_resid2, ix->metric);
         PQ_CUDA(cudaGetLastError());
         ix->stats[5] += 1;
 
@@ -1062,6 +1077,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
                 kp1.D = dD_all + (size_t)qb;
                 kp1.I = dI_all + (size_t)qb;
                 kp1.fail = (uint8_t*)w[7].p;
+                kp1.fail_count = st.any_redo + 2;
                 pq_k1_finalize_kernel<<<(nq + 7) / 8, 256, 0, ix->stream>>>(kp1);
                 PQ_CUDA(cudaGetLastError());
                 ix->stats[4] += 1;
@@ -1122,6 +1138,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         rp.D = dD_all + (size_t)qb * k;
         rp.I = dI_all + (size_t)qb * k;
         rp.fail = (uint8_t*)w[7].p;
+        rp.fail_count = st.any_redo + 2;
         const size_t rsmem = (size_t)rp.work * 8;
         PQ_CUDA(cudaFuncSetAttribute(pq_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         pq_rescore_kernel<<<nq, 256, rsmem, ix->stream>>>(rp);
@@ -1130,14 +1147,16 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         ix->stats[5] += 1;
         }
 
-        std::vector<uint8_t> fail((size_t)nq);
-        uint32_t redo_counts[2] = {0, 0};
-        PQ_CUDA(cudaMemcpyAsync(fail.data(), w[7].p, (size_t)nq, cudaMemcpyDeviceToHost, ix->stream));
-        PQ_CUDA(cudaMemcpyAsync(redo_counts, st.any_redo, 8, cudaMemcpyDeviceToHost, ix->stream));
+        uint32_t counts[3] = {0, 0, 0};  // any_redo (last epoch), total second attempts, failed queries
+        PQ_CUDA(cudaMemcpyAsync(counts, st.any_redo, 12, cudaMemcpyDeviceToHost, ix->stream));
         PQ_CUDA(cudaStreamSynchronize(ix->stream));
-        ix->stats[8] += redo_counts[1];
-        for (int q = 0; q < nq; ++q)
-            if (fail[q]) rerun->push_back(qb + q);
+        ix->stats[8] += counts[1];
+        if (counts[2] != 0) {  // rare: fetch the per-query flags
+            std::vector<uint8_t> fail((size_t)nq);
+            PQ_CUDA(cudaMemcpy(fail.data(), w[7].p, (size_t)nq, cudaMemcpyDeviceToHost));
+            for (int q = 0; q < nq; ++q)
+                if (fail[q]) rerun->push_back(qb + q);
+        }
     }
     return PQ_OK;
 }

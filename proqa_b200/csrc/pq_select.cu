@@ -187,11 +187,12 @@ cudaError_t merge_di_launch(const float* D_in, const long long* I_in, int n_list
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pq_prep_rows_kernel(const float* __restrict__ rows, long long n, uint16_t* __restrict__ rows_bf16,
                                                            float* __restrict__ norms, uint32_t* max_norm_bits,
-                                                           uint32_t* nonfinite_flag, uint8_t* __restrict__ row_bad) {
+                                                           uint32_t* nonfinite_flag, uint8_t* __restrict__ row_bad,
+                                                           float* __restrict__ resid2, uint32_t* max_resid_bits) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    float local_max = 0.f;
+    float local_max = 0.f, local_max_resid = 0.f;
     bool bad = false;
     for (long long row = warp; row < n; row += n_warps) {
         const float4 v = *reinterpret_cast<const float4*>(rows + row * kDim + lane * 4);
@@ -211,17 +212,27 @@ __global__ void __launch_bounds__(256) pq_prep_rows_kernel(const float* __restri
         if (row_bad && lane == 0) row_bad[row] = row_is_bad ? 1 : 0;
         bad |= row_is_bad;
         local_max = fmaxf(local_max, acc);
+        // squared norm of what the bf16 rounding took away, |x - bf16(x)|^2 (drives the filter's error bound);
+        // any summation order will do, the result is inflated to be an upper bound
+        const float dx = v.x - bx, dy = v.y - by, dz = v.z - bz, dw = v.w - bw;
+        float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        r2 *= 1.0001f;
+        if (resid2 && lane == 0) resid2[row] = r2;
+        if (!row_is_bad) local_max_resid = fmaxf(local_max_resid, r2);
     }
+    if (max_resid_bits && lane == 0 && local_max_resid > 0.f) atomicMax(max_resid_bits, __float_as_uint(local_max_resid));
     if (nonfinite_flag && bad && lane == 0) atomicOr(nonfinite_flag, 1u);
     if (max_norm_bits && lane == 0 && local_max > 0.f) atomicMax(max_norm_bits, __float_as_uint(local_max));  // non-negative floats order as uints
 }
 
 cudaError_t prep_rows_launch(const float* rows, long long n, uint16_t* rows_bf16, float* norms, uint32_t* max_norm_bits,
-                             uint32_t* nonfinite_flag, uint8_t* row_bad, cudaStream_t stream) {
+                             uint32_t* nonfinite_flag, uint8_t* row_bad, float* resid2, uint32_t* max_resid_bits, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     long long blocks = (n + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    pq_prep_rows_kernel<<<(int)blocks, 256, 0, stream>>>(rows, n, rows_bf16, norms, max_norm_bits, nonfinite_flag, row_bad);
+    pq_prep_rows_kernel<<<(int)blocks, 256, 0, stream>>>(rows, n, rows_bf16, norms, max_norm_bits, nonfinite_flag, row_bad, resid2, max_resid_bits);
     return cudaGetLastError();
 }
 
