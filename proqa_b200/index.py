@@ -92,6 +92,18 @@ class IndexFlat:
     def reset(self):
         _lib.check(_lib.lib().pq_index_reset(self._h), "reset")
 
+    def add_npy(self, path, chunk_rows=1 << 20):
+        """Append the rows of a .npy file (float32 or float16 [n, d], as written by retrieval/get_embed.py:139) without
+        materialising it in host memory: the file is memory-mapped and streamed chunk by chunk through the pinned staging
+        buffers; float16 files are widened on the device.  Equivalent to ``index.add(np.load(path).astype('float32'))``
+        (eval_retrieval.py:100,103) minus the two full-size host copies."""
+        x = np.load(path, mmap_mode="r")
+        assert x.ndim == 2 and x.shape[1] == self.d, f"expected [n, {self.d}], file has shape {x.shape}"
+        assert x.dtype in (np.float32, np.float16), f"unsupported dtype {x.dtype}"
+        for a in range(0, x.shape[0], int(chunk_rows)):
+            self.add(np.ascontiguousarray(x[a:a + int(chunk_rows)]))
+        return x.shape[0]
+
     # -- engine extensions (not part of FAISS) ----------------------------------------------------
     def add_device(self, ptr, n):
         """Append n rows that already live in device memory (raw float32 device pointer, C-contiguous [n, d])."""

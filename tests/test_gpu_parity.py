@@ -296,3 +296,15 @@ def test_corpus_in_document_order_stays_on_the_tensor_tier(ncl, nq, spread, expe
     assert st[1] == 0, f"{st[1]} queries fell back to the fp32 scan (second attempts: {st[8]})"
     if expect_second_attempts:
         assert st[8] > 0, "the second-attempt path was not exercised"
+
+
+def test_add_npy_streams_float32_and_float16_files(tmp_path):
+    xh = data.corpus(5000, kind="fp16")
+    np.save(tmp_path / "f32.npy", xh)
+    np.save(tmp_path / "f16.npy", xh.astype(np.float16))
+    xq = data.queries(6)
+    ref = _index(0, xh, "auto").search(xq, 10)
+    for name in ("f32.npy", "f16.npy"):
+        ix = _index(0, np.zeros((0, 128), np.float32), "auto")
+        assert ix.add_npy(str(tmp_path / name), chunk_rows=1500) == 5000 and ix.ntotal == 5000
+        _assert_bit_exact(*ix.search(xq, 10), *ref)
