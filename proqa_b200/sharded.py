@@ -151,7 +151,7 @@ class ShardedIndexFlat:
             D_out.copy_(D_local)
             I_out.copy_(I_local)
             return
-        if self.R > 1:
+        if self.R > 1 and n_loc:  # (every rank of a row group has the same slice, so an empty slice skips consistently)
             # rank-major concatenation along dim 0: [R*n_loc, k] is the layout every backend accepts for the output
             Da, Ia = D_all.view(-1)[: self.R * n_loc * k].view(self.R * n_loc, k), I_all.view(-1)[: self.R * n_loc * k].view(self.R * n_loc, k)
             self._dist.all_gather_into_tensor(Da, Dl, group=self.row_group)
