@@ -155,3 +155,46 @@ def test_comparator_flags_wrong_results():
     worse = D.copy()
     worse[1, 0] *= 1.001
     assert oracle.check_against_truth(worse, I, xq, xb, 10, 0)
+
+
+def test_l2_reports_squared_distances_and_paths_agree():
+    """IndexFlatL2.search returns squared L2 distances, ascending; the nq < 20 (direct) and nq >= 20 (|x|^2+|y|^2-2xy)
+    paths of FAISS agree up to fp32 rounding, and the engine's defined L2 score is the same quantity."""
+    xb, xq = data.corpus(1500), data.queries(5)
+    truth = ((xq[:, None, :].astype(np.float64) - xb[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    ix = oracle.IndexFlatL2(128)
+    ix.add(xb)
+    D1, I1 = ix.search(xq, 7, use_blas=False)
+    D2, I2 = ix.search(xq, 7, use_blas=True)
+    De, Ie = oracle.engine_spec(xq, xb, 7, oracle.METRIC_L2)
+    for D, I in ((D1, I1), (D2, I2), (De, Ie)):
+        np.testing.assert_array_equal(I, np.argsort(truth, axis=1)[:, :7])
+        np.testing.assert_allclose(D, np.take_along_axis(truth, I, 1), rtol=2e-5)
+        assert (np.diff(D, axis=1) >= 0).all()
+
+
+def test_l2_distance_of_a_row_to_itself_is_clamped_at_zero():
+    xb = data.corpus(300, kind="skewed")
+    for use_blas in (False, True):
+        ix = oracle.IndexFlatL2(128)
+        ix.add(xb)
+        D, I = ix.search(np.repeat(xb[17:18], 20 if use_blas else 1, axis=0), 1, use_blas=use_blas)
+        assert I[0, 0] == 17 and D[0, 0] >= 0.0 and D[0, 0] < 1e-2
+    De, Ie = oracle.engine_spec(xb[17:18], xb, 1, oracle.METRIC_L2)
+    assert Ie[0, 0] == 17 and De[0, 0] >= 0.0
+
+
+def test_engine_score_definition_is_eight_chains_of_sixteen():
+    """oracle.engine_chain_dot restates pq_common.cuh: engine_dot — checked here against a plain numpy re-derivation."""
+    import ctypes
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal(128).astype(np.float32), rng.standard_normal(128).astype(np.float32)
+    p = []
+    for j in range(8):
+        acc = np.float32(0)
+        for i in range(16 * j, 16 * j + 16):
+            acc = np.float32(np.float64(a[i]) * np.float64(b[i]) + np.float64(acc))   # fmaf: one rounding of the exact a*b+acc
+        p.append(acc)
+    want = np.float32(np.float32(np.float32(p[0] + p[1]) + np.float32(p[2] + p[3])) + np.float32(np.float32(p[4] + p[5]) + np.float32(p[6] + p[7])))
+    got = oracle._lib().engine_chain_dot(a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), b.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 128)
+    assert np.float32(got) == want
