@@ -906,31 +906,36 @@ static int carry_size_for_k(int k) {
 // owns (so all CTAs carry equal work and one wave fills the machine); otherwise a uniform count whose CTA total
 // wastes the least of the last wave.
 static void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n_sms, int* s1, int* s0) {
-    long long a, b;
+    // Base split: with no more groups than SMs, slices in proportion to the query tiles a group owns (equal work per CTA);
+    // otherwise one slice each.  Then the multiplier c (1..8) that minimises
+    //     waves(c) x max over group kinds of  tiles_owned x (row tiles per CTA + 6)
+    // — the 6 stands for the fixed per-CTA cost (TMEM allocation, query staging, pipeline fill and drain).  c > 1 pays when
+    // the CTA count sits just above a multiple of the SM count or well below it (512 query tiles = 128 groups on 148 SMs:
+    // one slice each leaves 20 SMs idle, eight slices each fill 7 waves to 98.8 %).
+    long long a0 = 1, b0 = 1;
     if (g.n_groups <= n_sms) {
-        a = (long long)n_sms * (g.base + 1) / n_mtiles;
-        b = (long long)n_sms * g.base / n_mtiles;
-        if (g.rem == 0) a = b;
-    } else {
-        // more groups than SMs: several waves.  Cost of c slices per group = waves x (row tiles per CTA + a fixed per-CTA
-        // cost — TMEM allocation, query staging, pipeline fill and drain — worth about 6 row tiles)
-        double best = 1e300;
-        a = 1;
-        for (int c = 1; c <= 8 && c <= tiles; ++c) {
-            const long long ctas = (long long)g.n_groups * c;
-            const double waves = (double)((ctas + n_sms - 1) / n_sms);
-            const double cost = waves * ((double)((tiles + c - 1) / c) + 6.0);
-            if (cost < best - 1e-9) {
-                best = cost;
-                a = c;
-            }
-        }
-        b = a;
+        a0 = std::max(1LL, (long long)n_sms * (g.base + 1) / n_mtiles);
+        b0 = std::max(1LL, (long long)n_sms * g.base / n_mtiles);
+        if (g.rem == 0) a0 = b0;
     }
-    a = std::max(1LL, std::min(a, tiles));
-    b = std::max(1LL, std::min(b, tiles));
-    *s1 = (int)a;
-    *s0 = (int)b;
+    double best = 1e300;
+    long long a = a0, b = b0;
+    for (int c = 1; c <= 8; ++c) {
+        const long long sa = std::min(a0 * c, tiles), sb = std::min(b0 * c, tiles);
+        const long long ctas = (long long)g.rem * sa + (long long)(g.n_groups - g.rem) * sb;
+        const double waves = (double)((ctas + n_sms - 1) / n_sms);
+        const double ta = g.rem ? (g.base + 1) * ((double)((tiles + sa - 1) / sa) + 6.0) : 0.0;
+        const double tb = g.base * ((double)((tiles + sb - 1) / sb) + 6.0);
+        const double cost = waves * std::max(ta, tb);
+        if (cost < best * (1.0 - 1e-3)) {  // prefer the smaller c unless the gain is real
+            best = cost;
+            a = sa;
+            b = sb;
+        }
+        if (sa >= tiles && sb >= tiles) break;
+    }
+    *s1 = (int)std::max(1LL, a);
+    *s0 = (int)std::max(1LL, b);
 }
 
 int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, float* dD_all, long long* dI_all,
