@@ -124,6 +124,12 @@ void pq_kmeans_default_params(pq_kmeans_params* p);
 int pq_kmeans_train(pq_index* index, int64_t k, const pq_kmeans_params* params, int64_t n, const float* x_host, float* centroids_out,
                     float* obj_out, int64_t obj_cap, int64_t* n_obj);
 
+/* Introspection (no device needed; used by the CPU tests of the host logic): the launch plan of one tensor-tier search of nq
+ * queries, top-k, over ntotal local rows on a device with n_sms SMs.  out[0..7] = {epochs, CTA groups, query tiles per group
+ * (base), groups owning base+1, max tiles per group, carry length K', padded queries, 0}; then per epoch 8 values
+ * {first row, end row, slices of the base+1 groups, slices of the base groups, slab capacity, CTAs, slabs per query, 0}. */
+int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len);
+
 const char* pq_last_error(void);
 /* "proqa_b200 <version> sm_100a" */
 const char* pq_version(void);

@@ -28,6 +28,7 @@
 // dropmax < A_k(final) - 2E.  Queries that fail it (or overflow a slab) are re-run by the fp32 scan.
 #include "pq_common.cuh"
 #include "pq_host.h"
+#include "pq_plan.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -48,7 +49,8 @@ constexpr int kTileBytes = 2 * kPanelBytes;    // K = 128 -> two panels, 32 KB
 constexpr int kStageBytes = kTileBytes + 1024; // + the tile's 128 squared row norms (L2 only), padded to keep 1024-B alignment
 constexpr int kEpiWarps = 8;
 constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
-constexpr int kMaxMTiles = 4;       // 4 x 64 TMEM columns of bf16 queries + 4 x 64 columns of accumulators = 512
+constexpr int kMaxMTiles = 4;       // 4 x 64 TMEM columns of bf16 queries + 2 x 128 columns of accumulators = 512
+static_assert(kBM == kPlanQueryTile && kBN == kPlanTileRows && kMaxMTiles == kPlanMaxMTiles, "pq_plan.h must describe this kernel");
 
 
 struct MmaCtrl {
@@ -888,56 +890,6 @@ static cudaError_t launch_filter_any(int m_max, bool l2, bool k1, const CUtensor
     return k1 ? launch_filter_m<false, true>(m_max, tc, p, n_ctas, stream) : launch_filter_m<false, false>(m_max, tc, p, n_ctas, stream);
 }
 
-struct EpochPlan {
-    long long begin, end;
-    int s1, s0, cap;   // row slices per CTA group (groups owning base+1 / base query tiles), slab capacity
-};
-
-struct GridShape {
-    int n_groups, base, rem, m_max, subs_per_slice;
-};
-
-static int carry_size_for_k(int k) {
-    int kp = next_pow2i((k * 5 + 1) / 2);
-    return std::max(kp, 64);
-}
-
-// Row slices per CTA group.  With no more groups than SMs every group gets slices in proportion to the query tiles it
-// owns (so all CTAs carry equal work and one wave fills the machine); otherwise a uniform count whose CTA total
-// wastes the least of the last wave.
-static void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n_sms, int* s1, int* s0) {
-    // Base split: with no more groups than SMs, slices in proportion to the query tiles a group owns (equal work per CTA);
-    // otherwise one slice each.  Then the multiplier c (1..8) that minimises
-    //     waves(c) x max over group kinds of  tiles_owned x (row tiles per CTA + 6)
-    // — the 6 stands for the fixed per-CTA cost (TMEM allocation, query staging, pipeline fill and drain).  c > 1 pays when
-    // the CTA count sits just above a multiple of the SM count or well below it (512 query tiles = 128 groups on 148 SMs:
-    // one slice each leaves 20 SMs idle, eight slices each fill 7 waves to 98.8 %).
-    long long a0 = 1, b0 = 1;
-    if (g.n_groups <= n_sms) {
-        a0 = std::max(1LL, (long long)n_sms * (g.base + 1) / n_mtiles);
-        b0 = std::max(1LL, (long long)n_sms * g.base / n_mtiles);
-        if (g.rem == 0) a0 = b0;
-    }
-    double best = 1e300;
-    long long a = a0, b = b0;
-    for (int c = 1; c <= 8; ++c) {
-        const long long sa = std::min(a0 * c, tiles), sb = std::min(b0 * c, tiles);
-        const long long ctas = (long long)g.rem * sa + (long long)(g.n_groups - g.rem) * sb;
-        const double waves = (double)((ctas + n_sms - 1) / n_sms);
-        const double ta = g.rem ? (g.base + 1) * ((double)((tiles + sa - 1) / sa) + 6.0) : 0.0;
-        const double tb = g.base * ((double)((tiles + sb - 1) / sb) + 6.0);
-        const double cost = waves * std::max(ta, tb);
-        if (cost < best * (1.0 - 1e-3)) {  // prefer the smaller c unless the gain is real
-            best = cost;
-            a = sa;
-            b = sb;
-        }
-        if (sa >= tiles && sb >= tiles) break;
-    }
-    *s1 = (int)std::max(1LL, a);
-    *s0 = (int)std::max(1LL, b);
-}
-
 int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, float* dD_all, long long* dI_all,
                       std::vector<int>* rerun) {
     const long long N = ix->ntotal;
@@ -949,57 +901,17 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         const int nq = std::min(kMaxBatch, nq_total - qb);
         const int nq_pad = (nq + kBM - 1) / kBM * kBM;
         const int n_mtiles = nq_pad / kBM;
-        GridShape gs;
-        gs.n_groups = (n_mtiles + kMaxMTiles - 1) / kMaxMTiles;
-        gs.base = n_mtiles / gs.n_groups;
-        gs.rem = n_mtiles % gs.n_groups;
-        gs.m_max = gs.base + (gs.rem ? 1 : 0);
-        gs.subs_per_slice = 2;  // the two epilogue warp sets (row halves of every tile) keep separate slabs
+        const GridShape gs = make_grid_shape(n_mtiles);
         const float* dq = dq_all + (size_t)qb * kDim;
         const uint16_t* dq_bf16 = (const uint16_t*)ix->ws_qbf16.p + (size_t)qb * kDim;
         const float* dq_norm = (const float*)ix->ws_qnorm.p + qb;
         const uint8_t* dq_bad = (const uint8_t*)ix->ws_qbad.p + qb;
 
-        // ---- epoch plan -----------------------------------------------------------------------
-        std::vector<EpochPlan> plan;
-        if (k1) {
-            EpochPlan ep;
-            ep.begin = 0;
-            ep.end = N;
-            pick_slices(gs, n_mtiles, (N + kBN - 1) / kBN, ix->n_sms, &ep.s1, &ep.s0);
-            ep.cap = 64;  // a thread keeps only rows within 2E of its running maximum: a few dozen at most
-            plan.push_back(ep);
-        } else {
-            // Epoch growth: every epoch costs a fixed ~0.1-0.2 ms (launches, select) and about 1.5 k (growth - 1) survivors per
-            // query; small batches are dominated by the fixed part, large ones by the survivors.
-            const long long growth = nq_pad <= 128 ? 64 : (nq_pad <= 512 ? 16 : 8);  // measured: nq=16 1.19 ms at 64; nq=256 1.66 ms at 8 vs 1.81 at 64
-            const long long n0 = std::min<long long>(N, std::max(1024, next_pow2i(2 * kp)));
-            long long begin = 0, end = n0;
-            while (begin < N) {
-                EpochPlan ep;
-                ep.begin = begin;
-                ep.end = std::min(end, N);
-                const long long tiles = (ep.end - ep.begin + kBN - 1) / kBN;
-                if (begin == 0) {  // bootstrap: every score is a candidate, one row tile per slice
-                    ep.s1 = ep.s0 = (int)tiles;
-                    ep.cap = kBN / gs.subs_per_slice;
-                } else {
-                    pick_slices(gs, n_mtiles, tiles, ix->n_sms, &ep.s1, &ep.s0);
-                    // survivors per query with the threshold frozen at the start of the epoch: about k * (end/begin - 1), times
-                    // ~1.5 for the 2E margin, on exchangeable rows; three times that is provisioned (rows in document order
-                    // bring whole clusters above the threshold at once — beyond the provision the epoch is run a second time)
-                    const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
-                    const double expect = 1.5 * (double)k * ((double)(ep.end - ep.begin) / (double)ep.begin) / slabs;
-                    ep.cap = std::min(4096, std::max(64, next_pow2i((int)(3.0 * expect) + 64)));
-                }
-                plan.push_back(ep);
-                begin = ep.end;
-                end = (ep.end >= N / 2 || ep.end * growth >= N) ? N : ep.end * growth;
-            }
-        }
+        // ---- epoch plan (pq_plan.h) -----------------------------------------------------------
+        const std::vector<EpochPlan> plan = plan_epochs(N, k, nq_pad, gs, ix->n_sms);
         size_t max_slab = 0, max_cnt = 0;
         for (const EpochPlan& ep : plan) {
-            const size_t n_sub = (size_t)std::max(ep.s1, ep.s0) * gs.subs_per_slice;
+            const size_t n_sub = (size_t)plan_n_sub(gs, ep);
             max_slab = std::max(max_slab, (size_t)nq_pad * n_sub * ep.cap * 8);
             max_cnt = std::max(max_cnt, (size_t)nq_pad * n_sub * 4);
         }
@@ -1049,11 +961,11 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.s1 = ep.s1;
             mp.s0 = ep.s0;
             mp.cap = ep.cap;
-            mp.n_sub = std::max(ep.s1, ep.s0) * gs.subs_per_slice;
+            mp.n_sub = plan_n_sub(gs, ep);
             mp.k1_adapt = k1 ? 1 : 0;
             mp.redo = nullptr;
             mp.any_redo = nullptr;
-            const int n_ctas = gs.rem * ep.s1 + (gs.n_groups - gs.rem) * ep.s0;
+            const int n_ctas = plan_n_ctas(gs, ep);
             // slabs a CTA never touches (unequal slice counts, query tiles owned by the other warp set) must read as empty
             PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
             ix->prof_begin();
@@ -1166,3 +1078,36 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
 }
 
 }  // namespace pq
+
+// Introspection for the CPU test-suite (no device needed): the launch plan of one tensor-tier search.
+extern "C" int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len) {
+    using namespace pq;
+    if (ntotal < 1 || nq < 1 || k < 1 || k > kMmaMaxK || n_sms < 1 || !out || out_len < 8)
+        return set_error(PQ_ERR_INVALID, "plan_describe: bad arguments");
+    const int nq_pad = (int)((nq + kBM - 1) / kBM * kBM);
+    const int n_mtiles = nq_pad / kBM;
+    const GridShape gs = make_grid_shape(n_mtiles);
+    const std::vector<EpochPlan> plan = plan_epochs(ntotal, (int)k, nq_pad, gs, n_sms);
+    if ((int)(8 + 8 * plan.size()) > out_len) return set_error(PQ_ERR_INVALID, "plan_describe: output too small");
+    out[0] = (int64_t)plan.size();
+    out[1] = gs.n_groups;
+    out[2] = gs.base;
+    out[3] = gs.rem;
+    out[4] = gs.m_max;
+    out[5] = carry_size_for_k((int)k);
+    out[6] = nq_pad;
+    out[7] = 0;
+    for (size_t e = 0; e < plan.size(); ++e) {
+        int64_t* o = out + 8 + 8 * e;
+        o[0] = plan[e].begin;
+        o[1] = plan[e].end;
+        o[2] = plan[e].s1;
+        o[3] = plan[e].s0;
+        o[4] = plan[e].cap;
+        o[5] = plan_n_ctas(gs, plan[e]);
+        o[6] = plan_n_sub(gs, plan[e]);
+        o[7] = 0;
+    }
+    return PQ_OK;
+}
+

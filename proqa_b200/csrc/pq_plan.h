@@ -1,0 +1,127 @@
+// proqa_b200 — launch planning of the tensor-core tier (host only, no CUDA): how a query batch and a row shard are cut
+// into CTA groups, row slices, epochs and candidate-slab capacities.  Pure functions of (ntotal, nq, k, #SMs) so that the
+// CPU test-suite can check their invariants through pq_plan_describe (include/proqa_b200.h).
+#pragma once
+
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace pq {
+
+constexpr int kPlanTileRows = 128;   // corpus rows per B tile (= kBN in pq_mma.cu)
+constexpr int kPlanQueryTile = 128;  // queries per M tile (= kBM)
+constexpr int kPlanMaxMTiles = 4;    // query tiles one CTA keeps in tensor memory (= kMaxMTiles)
+
+struct EpochPlan {
+    long long begin, end;
+    int s1, s0, cap;   // row slices per CTA group (groups owning base+1 / base query tiles), slab capacity
+};
+
+struct GridShape {
+    int n_groups, base, rem, m_max, subs_per_slice;
+};
+
+inline int plan_next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Carry list length K' >= 2.5 k (power of two, at least 64).
+inline int carry_size_for_k(int k) { return std::max(plan_next_pow2((k * 5 + 1) / 2), 64); }
+
+// Query tiles are dealt to ceil(n_mtiles / 4) CTA groups as evenly as possible: `rem` groups own base+1 tiles, the others base.
+inline GridShape make_grid_shape(int n_mtiles) {
+    GridShape gs;
+    gs.n_groups = (n_mtiles + kPlanMaxMTiles - 1) / kPlanMaxMTiles;
+    gs.base = n_mtiles / gs.n_groups;
+    gs.rem = n_mtiles % gs.n_groups;
+    gs.m_max = gs.base + (gs.rem ? 1 : 0);
+    gs.subs_per_slice = 2;  // the two epilogue warp sets (row halves of every tile) keep separate slabs
+    return gs;
+}
+
+// Row slices per CTA group.
+// Base split: with no more groups than SMs, slices in proportion to the query tiles a group owns (equal work per CTA);
+// otherwise one slice each.  Then the multiplier c (1..8) that minimises
+//     waves(c) x max over group kinds of  tiles_owned x (row tiles per CTA + 6)
+// — the 6 stands for the fixed per-CTA cost (TMEM allocation, query staging, pipeline fill and drain).  c > 1 pays when
+// the CTA count sits just above a multiple of the SM count or well below it (512 query tiles = 128 groups on 148 SMs:
+// one slice each leaves 20 SMs idle, eight slices each fill 7 waves to 98.8 %).
+inline void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n_sms, int* s1, int* s0) {
+    long long a0 = 1, b0 = 1;
+    if (g.n_groups <= n_sms) {
+        a0 = std::max(1LL, (long long)n_sms * (g.base + 1) / n_mtiles);
+        b0 = std::max(1LL, (long long)n_sms * g.base / n_mtiles);
+        if (g.rem == 0) a0 = b0;
+    }
+    double best = 1e300;
+    long long a = a0, b = b0;
+    for (int c = 1; c <= 8; ++c) {
+        const long long sa = std::max(1LL, std::min(a0 * c, tiles)), sb = std::max(1LL, std::min(b0 * c, tiles));
+        const long long ctas = (long long)g.rem * sa + (long long)(g.n_groups - g.rem) * sb;
+        const double waves = (double)((ctas + n_sms - 1) / n_sms);
+        const double ta = g.rem ? (g.base + 1) * ((double)((tiles + sa - 1) / sa) + 6.0) : 0.0;
+        const double tb = g.base * ((double)((tiles + sb - 1) / sb) + 6.0);
+        const double cost = waves * std::max(ta, tb);
+        if (cost < best * (1.0 - 1e-3)) {  // prefer the smaller c unless the gain is real
+            best = cost;
+            a = sa;
+            b = sb;
+        }
+        if (sa >= tiles && sb >= tiles) break;
+    }
+    *s1 = (int)std::max(1LL, a);
+    *s0 = (int)std::max(1LL, b);
+}
+
+// Epochs of one search over rows [0, N): contiguous, in order, covering every row once.
+inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const GridShape& gs, int n_sms) {
+    std::vector<EpochPlan> plan;
+    const int n_mtiles = nq_pad / kPlanQueryTile;
+    const int kp = carry_size_for_k(k);
+    if (k == 1) {  // running-maximum filter: one pass
+        EpochPlan ep;
+        ep.begin = 0;
+        ep.end = N;
+        pick_slices(gs, n_mtiles, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
+        ep.cap = 64;  // a thread keeps only rows within 2E of its running maximum: a few dozen at most
+        plan.push_back(ep);
+        return plan;
+    }
+    // Epoch growth: every epoch costs a fixed ~0.1-0.2 ms (launches, select) and about 1.5 k (growth - 1) survivors per
+    // query; small batches are dominated by the fixed part, large ones by the survivors
+    // (measured: nq=16 1.19 ms at 64x; nq=256 1.66 ms at 8x vs 1.81 at 64x).
+    const long long growth = nq_pad <= 128 ? 64 : (nq_pad <= 512 ? 16 : 8);
+    const long long n0 = std::min<long long>(N, std::max(1024, plan_next_pow2(2 * kp)));
+    long long begin = 0, end = n0;
+    while (begin < N) {
+        EpochPlan ep;
+        ep.begin = begin;
+        ep.end = std::min(end, N);
+        const long long tiles = (ep.end - ep.begin + kPlanTileRows - 1) / kPlanTileRows;
+        if (begin == 0) {  // bootstrap: every score is a candidate, one row tile per slice
+            ep.s1 = ep.s0 = (int)tiles;
+            ep.cap = kPlanTileRows / gs.subs_per_slice;
+        } else {
+            pick_slices(gs, n_mtiles, tiles, n_sms, &ep.s1, &ep.s0);
+            // survivors per query with the threshold frozen at the start of the epoch: about k * (end/begin - 1), times
+            // ~1.5 for the 2E margin, on exchangeable rows; three times that is provisioned (rows in document order
+            // bring whole clusters above the threshold at once — beyond the provision the epoch is run a second time)
+            const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
+            const double expect = 1.5 * (double)k * ((double)(ep.end - ep.begin) / (double)ep.begin) / slabs;
+            ep.cap = std::min(4096, std::max(64, plan_next_pow2((int)(3.0 * expect) + 64)));
+        }
+        plan.push_back(ep);
+        begin = ep.end;
+        end = (ep.end >= N / 2 || ep.end * growth >= N) ? N : ep.end * growth;
+    }
+    return plan;
+}
+
+inline int plan_n_ctas(const GridShape& gs, const EpochPlan& ep) { return gs.rem * ep.s1 + (gs.n_groups - gs.rem) * ep.s0; }
+inline int plan_n_sub(const GridShape& gs, const EpochPlan& ep) { return std::max(ep.s1, ep.s0) * gs.subs_per_slice; }
+
+}  // namespace pq

@@ -1,0 +1,75 @@
+"""CPU: the launch planner of the tensor-core tier (proqa_b200/csrc/pq_plan.h, through pq_plan_describe — no device needed).
+Invariants the kernels rely on, and the plans of the BASELINE.json configurations."""
+import ctypes
+
+import numpy as np
+import pytest
+
+N_SMS = 148
+
+
+def plan(ntotal, nq, k, n_sms=N_SMS):
+    from proqa_b200 import _lib
+    out = (ctypes.c_int64 * (8 + 8 * 64))()
+    rc = _lib.lib().pq_plan_describe(ntotal, nq, k, n_sms, out, len(out))
+    assert rc == 0, _lib.last_error()
+    head = dict(zip(["epochs", "groups", "base", "rem", "m_max", "kp", "nq_pad"], list(out[:7])))
+    eps = [dict(zip(["begin", "end", "s1", "s0", "cap", "ctas", "n_sub"], list(out[8 + 8 * e: 8 + 8 * e + 7]))) for e in range(head["epochs"])]
+    return head, eps
+
+
+CASES = [(21_000_000, 3610, 100), (1_000_000, 2032, 80), (21_000_000, 65536, 80), (12_500_000, 8192, 1000), (10_000, 1 << 20, 1),
+         (21_000_000, 16, 80), (21_000_000, 5, 1), (50, 4, 80), (1024, 130, 7), (1025, 600, 1024), (300_000, 262_144, 33), (7, 9, 1)]
+
+
+@pytest.mark.parametrize("ntotal,nq,k", CASES)
+def test_plan_invariants(ntotal, nq, k):
+    head, eps = plan(ntotal, nq, k)
+    n_mtiles = head["nq_pad"] // 128
+    assert head["nq_pad"] >= nq and head["nq_pad"] % 128 == 0 and head["nq_pad"] - nq < 128
+    # query tiles are dealt as evenly as possible, never more than 4 per CTA (TMEM: 4 x 64 columns of queries)
+    assert head["groups"] * head["base"] + head["rem"] == n_mtiles
+    assert 1 <= head["base"] <= head["m_max"] <= 4 and 0 <= head["rem"] < head["groups"]
+    assert head["kp"] >= 64 and head["kp"] >= 2.5 * k - 1 and head["kp"] & (head["kp"] - 1) == 0
+    # epochs: contiguous, in order, every row exactly once
+    assert eps[0]["begin"] == 0 and eps[-1]["end"] == ntotal
+    for a, b in zip(eps, eps[1:]):
+        assert a["end"] == b["begin"] and a["begin"] < a["end"]
+    for i, ep in enumerate(eps):
+        tiles = -(-(ep["end"] - ep["begin"]) // 128)
+        assert 1 <= ep["s1"] <= tiles and 1 <= ep["s0"] <= tiles, "never more slices than row tiles"
+        assert ep["ctas"] == head["rem"] * ep["s1"] + (head["groups"] - head["rem"]) * ep["s0"] >= 1
+        assert ep["n_sub"] == 2 * max(ep["s1"], ep["s0"])
+        assert 64 <= ep["cap"] <= 4096 and ep["cap"] & (ep["cap"] - 1) == 0
+        if ep["begin"] > 0:  # epoch boundaries are multiples of a tile, so a tile never straddles two epochs
+            assert ep["begin"] % 128 == 0
+        if k > 1 and i == 0:  # bootstrap: every score is a survivor, the slabs must hold a whole row half each
+            assert ep["s1"] == ep["s0"] == tiles and ep["cap"] == 64
+        if k > 1 and i > 0:   # provision: at least twice the survivors expected on exchangeable rows (1.5 k (end/begin - 1))
+            expect = 1.5 * k * (ep["end"] - ep["begin"]) / ep["begin"]
+            assert ep["cap"] * 2 * min(ep["s1"], ep["s0"]) >= min(2 * expect, 4096 * 2 * min(ep["s1"], ep["s0"]))
+        # the candidate slabs of one pass stay far below a B200's 180 GB
+        assert head["nq_pad"] * ep["n_sub"] * ep["cap"] * 8 <= 48e9
+    if k == 1:
+        assert len(eps) == 1
+
+
+def test_plans_of_the_baseline_configs():
+    head, eps = plan(21_000_000, 3610, 100)                  # C2
+    assert (head["groups"], head["base"], head["rem"]) == (8, 3, 5) and len(eps) == 6
+    assert [e["end"] for e in eps] == [1024, 8192, 65536, 524288, 4194304, 21_000_000]
+    assert eps[-1]["ctas"] == 145 and (eps[-1]["s1"], eps[-1]["s0"]) == (20, 15)     # slices in proportion to the tiles owned
+    head, eps = plan(21_000_000, 65536, 80)                  # C3: 128 groups on 148 SMs -> 8 slices each, 7 full waves
+    assert head["groups"] == 128 and eps[-1]["ctas"] == 1024
+    head, eps = plan(10_000, 1 << 20, 1)                     # C4 batch: one pass, one slice per group (79 row tiles only)
+    assert len(eps) == 1 and eps[0]["s0"] == 1 and eps[0]["ctas"] == head["groups"] == 2048
+    head, eps = plan(21_000_000, 16, 80)                     # small batch: fewer, larger epochs; all SMs on one query tile
+    assert len(eps) == 4 and eps[-1]["ctas"] == N_SMS
+
+
+def test_plan_rejects_bad_arguments():
+    from proqa_b200 import _lib
+    out = (ctypes.c_int64 * 64)()
+    assert _lib.lib().pq_plan_describe(0, 1, 1, N_SMS, out, 64) != 0
+    assert _lib.lib().pq_plan_describe(10, 1, 4096, N_SMS, out, 64) != 0      # k above the tensor tier's limit
+    assert _lib.lib().pq_plan_describe(21_000_000, 3610, 100, N_SMS, out, 8) != 0   # output too small
