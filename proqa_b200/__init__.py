@@ -9,6 +9,7 @@ there is no CPU fallback — without the built library or without a B200 the cal
 from .index import (METRIC_INNER_PRODUCT, METRIC_L2, IndexFlat, IndexFlatIP, IndexFlatL2, last_search_stats)  # noqa: F401
 from .clustering import Clustering, ClusteringParameters, vector_float_to_array  # noqa: F401
 from ._lib import library_path, version  # noqa: F401
+from .idmap import IdMap  # noqa: F401
 
 __all__ = ["IndexFlat", "IndexFlatIP", "IndexFlatL2", "METRIC_INNER_PRODUCT", "METRIC_L2", "library_path", "version",
-           "last_search_stats", "Clustering", "ClusteringParameters", "vector_float_to_array"]
+           "last_search_stats", "Clustering", "ClusteringParameters", "vector_float_to_array", "IdMap"]
