@@ -129,6 +129,13 @@ int pq_kmeans_train(pq_index* index, int64_t k, const pq_kmeans_params* params, 
  * (base), groups owning base+1, max tiles per group, carry length K', padded queries, 0}; then per epoch 8 values
  * {first row, end row, slices of the base+1 groups, slices of the base groups, slab capacity, CTAs, slabs per query, 0}. */
 int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len);
+/* The same for 1024 < k <= PQ_MAX_K (retrieval/trec_process.py:76 asks for k = 10000).  That tensor-tier path — thresholds from a
+ * row sample, one filter pass, a finalize kernel — is opt-in through the environment (PROQA_B200_LARGEK=1 at pq_index_create)
+ * until validated on hardware; by default such k are answered by the exact fp32 scan.  out[0..15] = {applies, sample step,
+ * k of the sample search, sample rows, finalize pool keys, sort length, sample epochs, pass slices (base+1 groups), pass slices
+ * (base groups), slab capacity, pass CTAs, slabs per query, queries per batch, slab bytes of a batch, finalize shared-memory
+ * bytes, carry length of the sample search}. */
+int pq_plan_describe_large_k(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len);
 
 const char* pq_last_error(void);
 /* "proqa_b200 <version> sm_100a" */

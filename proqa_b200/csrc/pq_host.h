@@ -58,6 +58,14 @@ struct pq_index {
     pq::DevBuf rows_f32, rows_bf16, norms, scalars;
     CUtensorMap tmap_f32, tmap_bf16;
 
+    // large-k tier (off unless PROQA_B200_LARGEK=1): compact bf16 copy of every sample_step-th row (+ norms) the thresholds
+    // are estimated on; rebuilt lazily after add()/reset() (sample_rows < 0 = stale)
+    bool largek = false;
+    pq::DevBuf sample_bf16, sample_norms;
+    CUtensorMap tmap_sample;
+    int64_t sample_rows = -1;
+    int sample_step = 0;
+
     // per-search workspaces (grow-only)
     pq::DevBuf ws_q, ws_D, ws_I, ws_qnorm, ws_qbf16, ws_qbad, ws_qresid;
     pq::DevBuf ws_scan_keys, ws_gthr;
@@ -104,6 +112,9 @@ struct pq_index {
                              &ws_qbad,  &ws_qresid, &ws_scan_keys, &ws_gthr, &ws_rr_idx, &ws_rr_q, &ws_rr_qn, &ws_rr_D,   &ws_rr_I};
         for (pq::DevBuf* b : all) b->release();
         for (pq::DevBuf& b : ws_mma) b.release();
+        sample_bf16.release();
+        sample_norms.release();
+        sample_rows = -1;
     }
 };
 
@@ -122,4 +133,6 @@ int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norm
 // prepared.  On return dD/dI hold final results for every query whose exactness certificate passed; the indices of
 // the others are appended to *rerun (the stream has been synchronised for the flag read-back).
 int search_mma_filter(pq_index* ix, int nq, const float* dq, int k, float* dD, long long* dI, std::vector<int>* rerun);
+// same contract for 1024 < k <= PQ_MAX_K (pq_mma.cu, "large k"): sample thresholds, one filter pass, finalize kernel
+int search_mma_largek(pq_index* ix, int nq, const float* dq, int k, float* dD, long long* dI, std::vector<int>* rerun);
 }  // namespace pq

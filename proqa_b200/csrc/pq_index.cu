@@ -6,6 +6,7 @@
 // sm_100 device every call that needs one fails with PQ_ERR_NO_DEVICE.
 #include "pq_common.cuh"
 #include "pq_host.h"
+#include "pq_plan.h"
 
 #include <cuda_fp16.h>
 #include <stdarg.h>
@@ -161,6 +162,7 @@ int index_init_device(pq_index* ix) {
 }
 
 static int index_refresh_maps(pq_index* ix) {
+    ix->sample_rows = -1;  // the rows changed: the large-k threshold sample is stale
     if (ix->ntotal == 0) return PQ_OK;
     int rc = make_row_tensor_map(&ix->tmap_f32, ix->rows_f32.p, ix->ntotal, 4, 32, kFfmaTileRows);
     if (rc) return rc;
@@ -438,9 +440,16 @@ __global__ void pq_scatter_results_kernel(const float* __restrict__ Ds, const lo
     }
 }
 
+// 1024 < k: the tensor tier needs the sample-threshold path, which is opt-in (PROQA_B200_LARGEK=1) until it has been
+// validated on hardware; otherwise such requests are answered by the fp32 scan.
+static bool tier_uses_largek(const pq_index* ix, int64_t nq, int64_t k) {
+    if (!ix->largek || ix->has_nonfinite || ix->tier == PQ_TIER_FP32) return false;
+    return k > kMmaMaxK && k <= PQ_MAX_K && nq >= kMmaMinQueries && plan_large_k_applies(ix->ntotal, (int)k);
+}
+
 static bool tier_uses_mma(const pq_index* ix, int64_t nq, int64_t k) {
     if (ix->has_nonfinite) return false;
-    if (k > kMmaMaxK) return false;
+    if (k > kMmaMaxK) return tier_uses_largek(ix, nq, k);
     if (ix->tier == PQ_TIER_FP32) return false;
     if (ix->tier == PQ_TIER_BF16) return ix->ntotal >= 1;
     // enough (query,row) pairs to pay for the epoch machinery: a big corpus, or the k-means shape (few centroids, millions of points)
@@ -473,7 +482,7 @@ int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t k, flo
 
     if (tier_uses_mma(ix, nq, k)) {
         std::vector<int> rerun;
-        rc = search_mma_filter(ix, (int)nq, dq, (int)k, dD, dI, &rerun);
+        rc = k > kMmaMaxK ? search_mma_largek(ix, (int)nq, dq, (int)k, dD, dI, &rerun) : search_mma_filter(ix, (int)nq, dq, (int)k, dD, dI, &rerun);
         if (rc) return rc;
         ix->stats[0] = nq - (int64_t)rerun.size();
         ix->stats[1] = (int64_t)rerun.size();
@@ -545,6 +554,8 @@ int pq_index_create(int d, int metric, int device, pq_index** out) {
         if (!strcmp(t, "fp32")) ix->tier = PQ_TIER_FP32;
         else if (!strcmp(t, "bf16")) ix->tier = PQ_TIER_BF16;
     }
+    const char* lk = getenv("PROQA_B200_LARGEK");
+    ix->largek = lk && !strcmp(lk, "1");
     *out = ix;  // CUDA is touched lazily (first add/search): the reference forks after importing faiss
     return PQ_OK;
 }
@@ -621,6 +632,7 @@ int pq_index_reset(pq_index* ix) {
 namespace pq {
 int index_reset_locked(pq_index* ix) {
     ix->ntotal = 0;
+    ix->sample_rows = -1;
     ix->max_norm2 = 0.f;
     ix->max_resid2 = 0.f;
     ix->has_nonfinite = false;

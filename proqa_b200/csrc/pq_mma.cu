@@ -1077,6 +1077,8 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
     return PQ_OK;
 }
 
+#include "pq_mma_largek.inl"
+
 }  // namespace pq
 
 // Introspection for the CPU test-suite (no device needed): the launch plan of one tensor-tier search.
@@ -1111,3 +1113,34 @@ extern "C" int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms
     return PQ_OK;
 }
 
+
+// Same for the large-k path (1024 < k <= PQ_MAX_K): out[0..15] =
+//   applies, step, k_sample, sample_rows, pool, sort_n, sample epochs, pass s1, pass s0, pass cap, pass CTAs, pass slabs per
+//   query, queries per batch, slab bytes of a full batch, finalize shared-memory bytes, carry length of the sample search
+extern "C" int pq_plan_describe_large_k(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len) {
+    using namespace pq;
+    if (ntotal < 1 || nq < 1 || k <= kMmaMaxK || k > PQ_MAX_K || n_sms < 1 || !out || out_len < 16)
+        return set_error(PQ_ERR_INVALID, "plan_describe_large_k: bad arguments");
+    const LargeKPlan lp = plan_large_k(ntotal, (int)k);
+    const int nqb = (int)std::min<int64_t>(nq, kLargeKBatch);
+    const int nq_pad = (nqb + kBM - 1) / kBM * kBM;
+    const GridShape gs = make_grid_shape(nq_pad / kBM);
+    const EpochPlan pass = plan_large_k_pass(ntotal, (int)k, nq_pad, gs, n_sms);
+    out[0] = plan_large_k_applies(ntotal, (int)k) ? 1 : 0;
+    out[1] = lp.step;
+    out[2] = lp.k_sample;
+    out[3] = lp.sample_rows;
+    out[4] = lp.pool;
+    out[5] = lp.sort_n;
+    out[6] = lp.sample_rows >= 1 ? (int64_t)plan_epochs(lp.sample_rows, lp.k_sample, nq_pad, gs, n_sms).size() : 0;
+    out[7] = pass.s1;
+    out[8] = pass.s0;
+    out[9] = pass.cap;
+    out[10] = plan_n_ctas(gs, pass);
+    out[11] = plan_n_sub(gs, pass);
+    out[12] = kLargeKBatch;
+    out[13] = (int64_t)nq_pad * plan_n_sub(gs, pass) * pass.cap * 8;
+    out[14] = (int64_t)std::max(lp.pool, lp.sort_n) * 8 + (int64_t)plan_n_sub(gs, pass) * 4;
+    out[15] = carry_size_for_k(lp.k_sample);
+    return PQ_OK;
+}

@@ -121,6 +121,45 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
     return plan;
 }
 
+// ---- large k (1024 < k <= PQ_MAX_K; trec_process.py:76 asks for k = 10000) --------------------------------------------------
+// A carry list of 2.5 k keys no longer fits shared memory, so the epochs are replaced by
+//   A. thresholds from a sample: the ordinary epoch search, k_sample <= 1024, over a compact copy of every step-th row;
+//      its final threshold  A_k_sample(sample) - 2E  sits near full-corpus rank  k_sample * step = 1.35 k
+//   B. ONE filter pass over all rows at those thresholds (about 2 k survivors per query, measured in tools/sim_largek.py)
+//   C. a finalize kernel per query: k-th best bf16 score of the survivors (radix select over the slabs in global memory),
+//      certificate, exact rescoring of the survivors within 2E of it (about 1.5 k rows, kept in shared memory: `pool`),
+//      top-k by exact key, sort.
+struct LargeKPlan {
+    int step, k_sample, pool, sort_n;
+    long long sample_rows;
+};
+constexpr int kLargeKPoolMax = 24576;   // keys (192 KB) the finalize kernel can hold next to its slab counters
+constexpr int kLargeKBatch = 8192;      // queries per pass: bounds the candidate slabs (about 0.7 MB per query at k = 10000)
+
+inline LargeKPlan plan_large_k(long long N, int k) {
+    LargeKPlan lp;
+    const double rank_target = 1.35 * (double)k;
+    lp.step = std::max(2, (int)ceil(rank_target / 1024.0));
+    lp.k_sample = (int)ceil(rank_target / (double)lp.step);
+    lp.sample_rows = N / lp.step;
+    lp.sort_n = plan_next_pow2(k);
+    lp.pool = std::max(lp.sort_n, std::min(kLargeKPoolMax, 2 * k));
+    return lp;
+}
+// The single pass of phase B over rows [0, N): slices as for any epoch, slabs provisioned for 3 x 2.2 k survivors per query.
+inline EpochPlan plan_large_k_pass(long long N, int k, int nq_pad, const GridShape& gs, int n_sms) {
+    EpochPlan ep;
+    ep.begin = 0;
+    ep.end = N;
+    pick_slices(gs, nq_pad / kPlanQueryTile, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
+    const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
+    const double expect = 2.2 * (double)k / slabs;
+    ep.cap = std::min(65536, std::max(64, plan_next_pow2((int)(3.0 * expect) + 64)));
+    return ep;
+}
+// Large enough a corpus for the sample to mean something; otherwise the fp32 scan answers.
+inline bool plan_large_k_applies(long long N, int k) { return N >= 64LL * k; }
+
 inline int plan_n_ctas(const GridShape& gs, const EpochPlan& ep) { return gs.rem * ep.s1 + (gs.n_groups - gs.rem) * ep.s0; }
 inline int plan_n_sub(const GridShape& gs, const EpochPlan& ep) { return std::max(ep.s1, ep.s0) * gs.subs_per_slice; }
 

@@ -73,3 +73,52 @@ def test_plan_rejects_bad_arguments():
     assert _lib.lib().pq_plan_describe(0, 1, 1, N_SMS, out, 64) != 0
     assert _lib.lib().pq_plan_describe(10, 1, 4096, N_SMS, out, 64) != 0      # k above the tensor tier's limit
     assert _lib.lib().pq_plan_describe(21_000_000, 3610, 100, N_SMS, out, 8) != 0   # output too small
+
+
+# ---- large k (1024 < k <= PQ_MAX_K): sample thresholds + one pass + finalize (pq_plan.h: plan_large_k) ----------------------
+LK = ["applies", "step", "k_sample", "sample_rows", "pool", "sort_n", "sample_epochs", "s1", "s0", "cap", "ctas", "n_sub", "batch",
+      "slab_bytes", "finalize_smem", "kp_sample"]
+
+
+def plan_large_k(ntotal, nq, k, n_sms=N_SMS):
+    from proqa_b200 import _lib
+    out = (ctypes.c_int64 * 16)()
+    rc = _lib.lib().pq_plan_describe_large_k(ntotal, nq, k, n_sms, out, len(out))
+    assert rc == 0, _lib.last_error()
+    return dict(zip(LK, list(out)))
+
+
+@pytest.mark.parametrize("ntotal,nq,k", [(8_800_000, 6980, 10000), (8_800_000, 500_000, 10000), (21_000_000, 5, 5000), (21_000_000, 128, 15360),
+                                          (2_000_000, 64, 1025), (300_000, 300, 2000), (100_000, 16, 10000)])
+def test_large_k_plan_invariants(ntotal, nq, k):
+    p = plan_large_k(ntotal, nq, k)
+    assert p["applies"] == (1 if ntotal >= 64 * k else 0)
+    # the sample search is an ordinary k <= 1024 search whose k-th best sits near full-corpus rank 1.35 k
+    assert 2 <= p["step"] and 1 <= p["k_sample"] <= 1024
+    assert 1.35 * k <= p["k_sample"] * p["step"] <= 1.35 * k + p["step"]
+    assert p["sample_rows"] == ntotal // p["step"] and (p["sample_rows"] - 1) * p["step"] + p["step"] // 2 < ntotal
+    assert p["kp_sample"] <= 4096
+    # finalize kernel: the sort area holds k, the pool holds the rescored set (about 1.5 k), all within one SM's shared memory
+    assert p["sort_n"] >= k and p["sort_n"] & (p["sort_n"] - 1) == 0 and p["sort_n"] < 2 * k
+    assert p["pool"] >= p["sort_n"] and p["pool"] >= min(2 * k, 24576)
+    assert p["finalize_smem"] + 2048 <= 227 * 1024
+    # single pass: slabs provisioned for at least 3 x 2.2 k survivors per query, and a batch's slabs stay modest
+    assert p["n_sub"] == 2 * max(p["s1"], p["s0"]) and p["cap"] & (p["cap"] - 1) == 0
+    assert p["cap"] * 2 * min(p["s1"], p["s0"]) >= 6.6 * k
+    assert p["slab_bytes"] <= 16e9
+    if p["applies"]:
+        assert p["sample_rows"] >= 16 * p["k_sample"] and p["sample_epochs"] >= 2
+
+
+def test_large_k_plan_of_the_trec_call():
+    """retrieval/trec_process.py:76 — index.search(xq, 10000) over the 8.8M MS MARCO passages."""
+    p = plan_large_k(8_841_823, 6980, 10000)
+    assert (p["step"], p["k_sample"], p["sort_n"], p["pool"]) == (14, 965, 16384, 20000)
+    assert p["sample_rows"] == 8_841_823 // 14
+
+
+def test_large_k_plan_rejects_small_k():
+    from proqa_b200 import _lib
+    out = (ctypes.c_int64 * 16)()
+    assert _lib.lib().pq_plan_describe_large_k(1_000_000, 10, 1024, N_SMS, out, 16) != 0
+    assert _lib.lib().pq_plan_describe_large_k(1_000_000, 10, 15361, N_SMS, out, 16) != 0

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round 2, first GPU call for the large-k tensor tier: parity, then sanitizer on a small case.
+# Fail fast: every step under its own hard timeout so that a hang cannot hold the box.
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+export PROQA_B200_LARGEK=1
+timeout -s KILL 600 python -m pytest tests/test_gpu_largek.py -m gpu -x -q > gpurun_out/largek_tests.log 2>&1
+echo "tests exit $?" | tee -a gpurun_out/largek_tests.log
+tail -30 gpurun_out/largek_tests.log
+timeout -s KILL 600 compute-sanitizer --tool memcheck python - > gpurun_out/largek_memcheck.log 2>&1 <<'PY'
+import numpy as np, proqa_b200 as pq
+from tests import data
+xb, xq = data.corpus(120_000), data.queries(8)
+ix = pq.IndexFlatIP(128); ix.add(xb)
+D, I = ix.search(xq, 1500)
+print("stats", ix.last_stats)
+PY
+echo "memcheck exit $?" | tee -a gpurun_out/largek_memcheck.log
+tail -15 gpurun_out/largek_memcheck.log
