@@ -29,6 +29,8 @@ WORKLOADS = {
     "s0": dict(nq=16, rows=21_000_000, k=80, desc="small-batch sweep point: 16 queries x 21M x 128 fp32, k=80 (HBM-bound)"),
     "c4": dict(nq=21_000_000, rows=10_000, k=1, kind="kmeans",
                desc="group_paras.py k-means assignment: 21M x 128 points x 10,000 centroids, k=1 (points are the query side)"),
+    "trec": dict(nq=256, rows=8_841_823, k=10000,
+                 desc="trec_process.py:76 shape: a 256-query sample of index.search(xq, 10000) over 8.8M x 128 fp32 (MS MARCO passages)"),
     "c5": dict(nq=8192, rows=100_000_000, k=1000, desc="scale-out: 8192 queries x 100M x 128 fp32, k=1000 (needs 8 GPUs for the full corpus)"),
 }
 CHUNK = 1_000_000  # rows per generated chunk; chunk c is seeded with 1234 + c so the corpus does not depend on N
