@@ -1,0 +1,272 @@
+// Test infrastructure — a minimal SIMT emulator for running ONE hand-written CUDA kernel's *logic* on the CPU.
+//
+// Why: kernels written while no GPU was at hand (tests/test_simt_largek.py) can still be executed against the oracle:
+// block-wide barriers, warp votes/shuffles/matches, shared-memory atomics and divergence are modelled; timing, the memory
+// model and data races are NOT (threads of a block are cooperative fibers on one OS thread, switched only at barriers and
+// warp collectives).  A collective that can never complete (divergent __syncthreads, a vote some lane of the mask never
+// reaches) is reported as a deadlock instead of hanging; barriers are matched by count, not by call site.  This is a checker for tests/, never a product path.
+#pragma once
+
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <vector>
+
+namespace simt {
+
+struct Dim3 {
+    unsigned x = 1, y = 1, z = 1;
+};
+
+struct Rendezvous {
+    uint64_t vals[32];
+    uint64_t snap[32];
+    unsigned arrived = 0;
+    unsigned gen = 0;
+};
+
+struct Fiber {
+    ucontext_t ctx;
+    bool done = false;
+    unsigned tid = 0;
+};
+constexpr size_t kStackBytes = 128 * 1024;
+inline std::vector<std::vector<char>> g_stacks;   // reused from block to block
+
+struct BlockState {
+    std::vector<Fiber> fibers;
+    ucontext_t sched;
+    int current = -1;
+    unsigned bar_arrived = 0, bar_gen = 0, live = 0;
+    unsigned long long progress = 0;   // bumped whenever any collective completes or a thread exits
+    std::map<std::pair<int, unsigned>, Rendezvous> rv;   // (warp, mask) -> rendezvous
+    std::function<void()> body;
+    const char* deadlock = nullptr;
+};
+
+inline BlockState* g_block = nullptr;
+inline Dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+inline void yield_to_scheduler() {
+    BlockState* b = g_block;
+    Fiber& f = b->fibers[b->current];
+    swapcontext(&f.ctx, &b->sched);
+}
+
+inline void fiber_entry() {
+    BlockState* b = g_block;
+    b->body();
+    Fiber& f = b->fibers[b->current];
+    f.done = true;
+    b->live--;
+    b->progress++;
+    // a barrier the remaining threads are waiting at may now be complete (exited threads do not take part)
+    if (b->live > 0 && b->bar_arrived == b->live) {
+        b->bar_arrived = 0;
+        b->bar_gen++;
+    }
+    swapcontext(&f.ctx, &b->sched);
+}
+
+// Runs `body` once per thread of every block, blocks one after the other.  Returns null, or a message on deadlock.
+inline const char* launch(unsigned grid, unsigned block, const std::function<void()>& body) {
+    gridDim.x = grid;
+    blockDim.x = block;
+    for (unsigned bx = 0; bx < grid; ++bx) {
+        BlockState b;
+        g_block = &b;
+        b.body = body;
+        b.fibers.resize(block);
+        b.live = block;
+        blockIdx.x = bx;
+        if (g_stacks.size() < block) g_stacks.resize(block);
+        for (unsigned t = 0; t < block; ++t) {
+            Fiber& f = b.fibers[t];
+            f.tid = t;
+            if (g_stacks[t].empty()) g_stacks[t].resize(kStackBytes);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = g_stacks[t].data();
+            f.ctx.uc_stack.ss_size = g_stacks[t].size();
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+        }
+        unsigned long long last_progress = ~0ull;
+        while (b.live > 0) {
+            if (b.progress == last_progress) {
+                g_block = nullptr;
+                return "deadlock: no thread of the block can make progress (divergent barrier or incomplete warp collective)";
+            }
+            last_progress = b.progress;
+            for (unsigned t = 0; t < block; ++t) {
+                if (b.fibers[t].done) continue;
+                b.current = (int)t;
+                threadIdx.x = t;
+                swapcontext(&b.sched, &b.fibers[t].ctx);
+            }
+        }
+        g_block = nullptr;
+    }
+    return nullptr;
+}
+
+inline void syncthreads() {
+    BlockState* b = g_block;
+    const unsigned my_gen = b->bar_gen;
+    b->bar_arrived++;
+    if (b->bar_arrived == b->live) {
+        b->bar_arrived = 0;
+        b->bar_gen++;
+        b->progress++;
+        return;
+    }
+    while (b->bar_gen == my_gen) {
+        yield_to_scheduler();
+        threadIdx.x = g_block->fibers[g_block->current].tid;
+    }
+}
+
+// every lane named in `mask` contributes v; returns the 32 contributed values (valid until this lane's next collective)
+inline const uint64_t* warp_exchange(unsigned mask, uint64_t v) {
+    BlockState* b = g_block;
+    const unsigned tid = b->fibers[b->current].tid;
+    const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
+    // lanes of a partial last warp that do not exist cannot arrive
+    unsigned exist = 0xffffffffu;
+    const unsigned n = (unsigned)b->fibers.size();
+    if ((unsigned)(warp + 1) * 32 > n) exist = (1u << (n - warp * 32)) - 1u;
+    mask &= exist;
+    if (!(mask & (1u << lane))) {
+        fprintf(stderr, "simt: lane %d called a collective whose mask %08x does not name it\n", lane, mask);
+        abort();
+    }
+    Rendezvous& r = b->rv[std::make_pair(warp, mask)];
+    r.vals[lane] = v;
+    r.arrived |= 1u << lane;
+    const unsigned my_gen = r.gen;
+    if (r.arrived == mask) {
+        memcpy(r.snap, r.vals, sizeof(r.snap));
+        r.arrived = 0;
+        r.gen++;
+        b->progress++;
+    } else {
+        while (r.gen == my_gen) {
+            yield_to_scheduler();
+            threadIdx.x = g_block->fibers[g_block->current].tid;
+        }
+    }
+    return r.snap;
+}
+
+template <typename T>
+inline uint64_t to_bits(T v) {
+    uint64_t u = 0;
+    static_assert(sizeof(T) <= 8, "collective payloads are at most 64 bits");
+    memcpy(&u, &v, sizeof(T));
+    return u;
+}
+template <typename T>
+inline T from_bits(uint64_t u) {
+    T v;
+    memcpy(&v, &u, sizeof(T));
+    return v;
+}
+inline int lane_id() { return (int)(g_block->fibers[g_block->current].tid & 31); }
+
+}  // namespace simt
+
+// ---- the CUDA surface the kernels under test use ---------------------------------------------------------------------------
+using simt::blockDim;
+using simt::blockIdx;
+using simt::gridDim;
+using simt::threadIdx;
+using std::max;
+using std::min;
+
+// (when the CUDA host headers were included first they have their own idea of these)
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __align__
+#undef __shared__
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+#define __align__(n) alignas(n)
+
+inline void __syncthreads() { simt::syncthreads(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::warp_exchange(mask, 0); }
+template <typename T>
+inline T __shfl_sync(unsigned mask, T v, int src) {
+    return simt::from_bits<T>(simt::warp_exchange(mask, simt::to_bits(v))[src & 31]);
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
+    return simt::from_bits<T>(simt::warp_exchange(mask, simt::to_bits(v))[(simt::lane_id() ^ lane_mask) & 31]);
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
+    const int src = simt::lane_id() + (int)delta;
+    const uint64_t* s = simt::warp_exchange(mask, simt::to_bits(v));
+    return src > 31 ? v : simt::from_bits<T>(s[src]);
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+    const int src = simt::lane_id() - (int)delta;
+    const uint64_t* s = simt::warp_exchange(mask, simt::to_bits(v));
+    return src < 0 ? v : simt::from_bits<T>(s[src]);
+}
+inline unsigned __ballot_sync(unsigned mask, bool pred) {
+    const uint64_t* s = simt::warp_exchange(mask, pred ? 1u : 0u);
+    unsigned out = 0;
+    for (int l = 0; l < 32; ++l)
+        if ((mask >> l & 1u) && s[l]) out |= 1u << l;
+    return out;
+}
+inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
+template <typename T>
+inline unsigned __match_any_sync(unsigned mask, T v) {
+    const uint64_t mine = simt::to_bits(v);
+    const uint64_t* s = simt::warp_exchange(mask, mine);
+    unsigned out = 0;
+    for (int l = 0; l < 32; ++l)
+        if ((mask >> l & 1u) && s[l] == mine) out |= 1u << l;
+    return out;
+}
+template <typename T>
+inline T atomicAdd(T* p, T v) {
+    const T old = *p;
+    *p = old + v;
+    return old;
+}
+template <typename T>
+inline T atomicMax(T* p, T v) {
+    const T old = *p;
+    if (v > old) *p = v;
+    return old;
+}
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+#if !defined(__VECTOR_TYPES_H__)
+struct float4 {
+    float x, y, z, w;
+};
+struct uint2 {
+    unsigned x, y;
+};
+#endif
