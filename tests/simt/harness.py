@@ -1,0 +1,141 @@
+"""Test infrastructure: build and call the CPU emulations of the tensor-core tier (see simt_emu.h, mma_host_emu.cpp.in).
+
+The engine's own source text is extracted from proqa_b200/csrc (never copied into the repo a second time), `__shared__`
+becomes static, `kernel<<<...>>>(...)` becomes EMU_LAUNCH, and the result is compiled with g++ into a throw-away .so.
+Nothing here is importable by the product; it exists so that `-m "not gpu"` can execute kernel and driver LOGIC against
+the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CSRC = os.path.join(ROOT, "proqa_b200", "csrc")
+SIMT = os.path.join(ROOT, "tests", "simt")
+
+
+def extract(text, signature, upto=None):
+    """The top-level definition whose first line contains `signature` (plus a preceding template<> line), through the first
+    line that is exactly '}' or '};' — or, when `upto` is given, through the first line containing it."""
+    lines = text.split("\n")
+    start = next(i for i, ln in enumerate(lines) if signature in ln)
+    if start > 0 and lines[start - 1].startswith("template"):
+        start -= 1
+    end = start
+    while not ((upto in lines[end]) if upto else lines[end] in ("}", "};")):
+        end += 1
+    return "\n".join(lines[start:end + 1]) + "\n"
+
+
+def to_host(src):
+    src = re.sub(r"extern __shared__ __align__\(16\)", "extern", src)
+    src = src.replace("__shared__", "static")
+    return re.sub(r"(\w+)<<<(.*?)>>>\((.*?)\);", r"EMU_LAUNCH(\1, \2, \3);", src, flags=re.S)
+
+
+def sources():
+    return (open(os.path.join(CSRC, "pq_common.cuh")).read(), open(os.path.join(CSRC, "pq_mma.cu")).read(),
+            open(os.path.join(CSRC, "pq_mma_largek.inl")).read())
+
+
+def key_and_sort_helpers(common):
+    return [extract(common, "uint32_t f32_to_ordered(float f)", upto="uint32_t key_row(uint64_t key)"),
+            extract(common, "float warp_engine_dot(const float4 a, const float4 b, int lane)"),
+            extract(common, "void block_sort(uint64_t* a, int n, bool ascending)"),
+            extract(common, "void block_sort_desc(uint64_t* a, int n)")]
+
+
+def compile_so(cpp_text, workdir, name, opt="-O1", extra=()):
+    cpp = os.path.join(str(workdir), name + ".cpp")
+    open(cpp, "w").write(cpp_text)
+    so = os.path.join(str(workdir), name + ".so")
+    r = subprocess.run(["g++", opt, "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", "-I", SIMT, *extra, cpp, "-o", so],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return ctypes.CDLL(so)
+
+
+def build_host_emu(workdir):
+    """The tensor-tier host drivers (search_mma_filter, search_mma_largek) + their kernels, emulated; the tcgen05 filter
+    kernel replaced by the functional stand-in in mma_host_emu.cpp.in."""
+    common, mma, inl = sources()
+    device = "\n".join(key_and_sort_helpers(common) + [
+        extract(mma, "struct MmaParams {"),
+        extract(mma, "struct QState {"),
+        extract(mma, "__global__ void pq_mma_init_state_kernel(QState st"),
+        extract(mma, "struct EpochSelParams {"),
+        extract(mma, "uint64_t block_radix_select(const uint64_t* pool"),
+        extract(mma, "pq_epoch_select_kernel(const EpochSelParams p)"),
+        extract(mma, "struct RescoreParams {"),
+        extract(mma, "pq_rescore_kernel(const RescoreParams p)"),
+        extract(mma, "struct K1Params {"),
+        extract(mma, "pq_k1_finalize_kernel(const K1Params p)"),
+    ])
+    host = extract(mma, "static int next_pow2i(int v)") + extract(mma, "int search_mma_filter(pq_index* ix")
+    tmpl = open(os.path.join(SIMT, "mma_host_emu.cpp.in")).read()
+    text = tmpl.replace("@EXTRACTED_DEVICE@", to_host(device)).replace("@EXTRACTED_HOST@", to_host(host)).replace("@EXTRACTED_LARGEK@", to_host(inl))
+    # -Bsymbolic: our fake CUDA runtime, not a libcudart some other module of the test process has loaded
+    lib = compile_so(text, workdir, "mma_host_emu", opt="-O2", extra=("-I", CSRC, "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic"))
+    vp = ctypes.c_void_p
+    lib.emu_search_mma.restype = ctypes.c_char_p
+    lib.emu_search_mma.argtypes = [vp, vp, vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
+    return lib
+
+
+# ---- what add() and the query preparation leave on the device, computed on the host ----------------------------------------
+def bf16_round(x):
+    u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def bf16_bits(x):
+    return (bf16_round(x).view(np.uint32) >> 16).astype(np.uint16)
+
+
+def f32_ordered(f):
+    u = np.asarray(f, np.float32).view(np.uint32)
+    return np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
+
+
+def engine_norms(x):
+    f32p = ctypes.POINTER(ctypes.c_float)
+    L = oracle._lib()
+    return np.array([L.engine_chain_dot(r.ctypes.data_as(f32p), r.ctypes.data_as(f32p), 128) for r in x], np.float32)
+
+
+def resid2(x):
+    return (((x - bf16_round(x)).astype(np.float64) ** 2).sum(1) * 1.0001).astype(np.float32)
+
+
+def run_host_emu(lib, xb, xq, k, metric, n_sms=8):
+    """-> D, I, sorted list of queries the driver wants re-run by the fp32 scan, the driver's statistics."""
+    nq = len(xq)
+    nq_pad = (nq + 127) // 128 * 128
+    xb = np.ascontiguousarray(xb, np.float32)
+    xq = np.ascontiguousarray(xq, np.float32)
+    xb_b = bf16_bits(xb)
+    xq_b = np.zeros((nq_pad, 128), np.uint16)
+    xq_b[:nq] = bf16_bits(xq)
+    norms = np.zeros(len(xb) + 256, np.float32)         # (add() keeps the norm buffer padded to whole tiles)
+    norms[:len(xb)] = engine_norms(xb)
+    q_norm = np.zeros(nq_pad, np.float32)
+    q_norm[:nq] = engine_norms(xq)
+    q_resid = np.zeros(nq_pad, np.float32)
+    q_resid[:nq] = resid2(xq)
+    q_bad = np.zeros(nq_pad, np.uint8)
+    D = np.full((nq, k), np.nan, np.float32)
+    I = np.full((nq, k), -7, np.int64)
+    rerun = np.zeros(nq, np.int32)
+    n_rerun = ctypes.c_int(0)
+    stats = np.zeros(10, np.int64)
+    msg = lib.emu_search_mma(xb.ctypes.data, xb_b.ctypes.data, norms.ctypes.data, len(xb), float(norms.max()), float(resid2(xb).max()),
+                             xq.ctypes.data, xq_b.ctypes.data, q_norm.ctypes.data, q_resid.ctypes.data, q_bad.ctypes.data, nq, k, metric,
+                             n_sms, D.ctypes.data, I.ctypes.data, rerun.ctypes.data, ctypes.byref(n_rerun), stats.ctypes.data)
+    assert msg is None, msg.decode()
+    return D, I, sorted(rerun[:n_rerun.value].tolist()), stats

@@ -10,50 +10,24 @@ model the memory system or races.  Test infrastructure only — the product has 
 """
 import ctypes
 import math
-import os
-import re
-import subprocess
 
 import numpy as np
 import pytest
 
 from oracle import oracle
 from tests import data
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "proqa_b200", "csrc")
-
-
-def _extract(text, signature, upto=None):
-    """The top-level definition whose first line contains `signature` (plus a preceding template<> line), through the first
-    line that is exactly '}' — or through the line containing `upto`."""
-    lines = text.split("\n")
-    start = next(i for i, ln in enumerate(lines) if signature in ln)
-    if start > 0 and lines[start - 1].startswith("template"):
-        start -= 1
-    end = start
-    while not ((upto in lines[end]) if upto else lines[end] in ("}", "};")):
-        end += 1
-    return "\n".join(lines[start:end + 1]) + "\n"
+from tests.simt import harness
+from tests.simt.harness import bf16_round, engine_norms, f32_ordered
 
 
 def _device_source():
-    common = open(os.path.join(CSRC, "pq_common.cuh")).read()
-    mma = open(os.path.join(CSRC, "pq_mma.cu")).read()
-    inl = open(os.path.join(CSRC, "pq_mma_largek.inl")).read()
-    parts = [
-        _extract(common, "uint32_t f32_to_ordered(float f)", upto="uint32_t key_row(uint64_t key)"),
-        _extract(common, "void block_sort(uint64_t* a, int n, bool ascending)"),
-        _extract(common, "void block_sort_desc(uint64_t* a, int n)"),
-        _extract(mma, "uint64_t block_radix_select(const uint64_t* pool"),
-        _extract(inl, "struct LargeKParams {"),
-        _extract(inl, "uint32_t slab_radix_select_score(const uint64_t* keys"),
-        _extract(inl, "pq_largek_finalize_kernel(const LargeKParams p)"),
-    ]
-    src = "\n".join(parts)
-    src = re.sub(r"extern __shared__ __align__\(16\)", "extern", src)
-    src = src.replace("__shared__", "static")
-    return src
+    common, mma, inl = harness.sources()
+    return harness.to_host("\n".join(harness.key_and_sort_helpers(common) + [
+        harness.extract(mma, "uint64_t block_radix_select(const uint64_t* pool"),
+        harness.extract(inl, "struct LargeKParams {"),
+        harness.extract(inl, "uint32_t slab_radix_select_score(const uint64_t* keys"),
+        harness.extract(inl, "pq_largek_finalize_kernel(const LargeKParams p)"),
+    ]))
 
 
 HARNESS = r'''
@@ -82,35 +56,11 @@ extern "C" const char* emu_largek_finalize(const uint64_t* cand_keys, const uint
 
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    d = tmp_path_factory.mktemp("simt")
-    cpp = d / "largek_finalize_emu.cpp"
-    cpp.write_text(HARNESS % _device_source())
-    so = d / "largek_finalize_emu.so"
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "simt"), str(cpp), "-o", str(so)],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    lib = ctypes.CDLL(str(so))
+    lib = harness.compile_so(HARNESS % _device_source(), tmp_path_factory.mktemp("simt"), "largek_finalize_emu")
     vp = ctypes.c_void_p
     lib.emu_largek_finalize.restype = ctypes.c_char_p
     lib.emu_largek_finalize.argtypes = [vp] * 9 + [ctypes.c_int] * 6 + [ctypes.c_longlong, vp, vp, vp, vp, ctypes.c_int]
     return lib
-
-
-def bf16_round(x):
-    u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
-    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
-    return u.astype(np.uint32).view(np.float32)
-
-
-def f32_ordered(f):
-    u = np.asarray(f, np.float32).view(np.uint32)
-    return np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
-
-
-def engine_norms(x):
-    f32p = ctypes.POINTER(ctypes.c_float)
-    L = oracle._lib()
-    return np.array([L.engine_chain_dot(r.ctypes.data_as(f32p), r.ctypes.data_as(f32p), 128) for r in x], np.float32)
 
 
 class Scenario:
@@ -240,13 +190,7 @@ extern "C" const char* emu_selftest(int* out, int mode) {
 
 
 def test_emulator_collectives_and_deadlock_detection(tmp_path):
-    cpp = tmp_path / "selftest.cpp"
-    cpp.write_text(SELFTEST)
-    so = tmp_path / "selftest.so"
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "simt"), str(cpp), "-o", str(so)],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    lib = ctypes.CDLL(str(so))
+    lib = harness.compile_so(SELFTEST, tmp_path, "selftest")
     lib.emu_selftest.restype = ctypes.c_char_p
     out = (ctypes.c_int * 4)()
     for mode in (0, 1):
@@ -261,80 +205,13 @@ def test_emulator_collectives_and_deadlock_detection(tmp_path):
 # ---- the host driver pq::search_mma_largek (phases A, B, C) on the CPU ------------------------------------------------------
 # Real: the driver's own source, the planner, and the gather-sample / init-state / epoch-select / finalize kernels (emulated).
 # Stand-in: pq_mma_filter_kernel (tcgen05), replaced by a functional model with the same CTA mapping and slab layout
-# (tests/simt/largek_host_emu.cpp.in).
-def _host_source():
-    common = open(os.path.join(CSRC, "pq_common.cuh")).read()
-    mma = open(os.path.join(CSRC, "pq_mma.cu")).read()
-    inl = open(os.path.join(CSRC, "pq_mma_largek.inl")).read()
-    device = "\n".join([
-        _extract(common, "uint32_t f32_to_ordered(float f)", upto="uint32_t key_row(uint64_t key)"),
-        _extract(common, "void block_sort(uint64_t* a, int n, bool ascending)"),
-        _extract(common, "void block_sort_desc(uint64_t* a, int n)"),
-        _extract(mma, "struct MmaParams {"),
-        _extract(mma, "struct QState {"),
-        _extract(mma, "__global__ void pq_mma_init_state_kernel(QState st"),
-        _extract(mma, "struct EpochSelParams {"),
-        _extract(mma, "uint64_t block_radix_select(const uint64_t* pool"),
-        _extract(mma, "pq_epoch_select_kernel(const EpochSelParams p)"),
-    ])
-
-    def fix(src):
-        src = re.sub(r"extern __shared__ __align__\(16\)", "extern", src)
-        src = src.replace("__shared__", "static")
-        return re.sub(r"(\w+)<<<(.*?)>>>\((.*?)\);", r"EMU_LAUNCH(\1, \2, \3);", src, flags=re.S)
-
-    tmpl = open(os.path.join(ROOT, "tests", "simt", "largek_host_emu.cpp.in")).read()
-    return tmpl.replace("@EXTRACTED_DEVICE@", fix(device)).replace("@EXTRACTED_LARGEK@", fix(inl))
-
-
+# (tests/simt/mma_host_emu.cpp.in).
 @pytest.fixture(scope="module")
 def host_emu(tmp_path_factory):
-    d = tmp_path_factory.mktemp("simt_host")
-    cpp = d / "largek_host_emu.cpp"
-    cpp.write_text(_host_source())
-    so = d / "largek_host_emu.so"
-    r = subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", "-I", os.path.join(ROOT, "tests", "simt"), "-I", CSRC,
-                        "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic",   # our fake runtime, not a libcudart some other module loaded
-                        str(cpp), "-o", str(so)], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-4000:]
-    lib = ctypes.CDLL(str(so))
-    vp = ctypes.c_void_p
-    lib.emu_search_largek.restype = ctypes.c_char_p
-    lib.emu_search_largek.argtypes = [vp, vp, vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp,
-                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
-    return lib
+    return harness.build_host_emu(tmp_path_factory.mktemp("simt_host"))
 
 
-def bf16_bits(x):
-    return (bf16_round(x).view(np.uint32) >> 16).astype(np.uint16)
-
-
-def run_host_emu(lib, xb, xq, k, metric, n_sms=8):
-    nq = len(xq)
-    nq_pad = (nq + 127) // 128 * 128
-    xb = np.ascontiguousarray(xb, np.float32)
-    xq = np.ascontiguousarray(xq, np.float32)
-    xb_b = bf16_bits(xb)
-    xq_b = np.zeros((nq_pad, 128), np.uint16)
-    xq_b[:nq] = bf16_bits(xq)
-    norms = np.zeros(len(xb) + 256, np.float32)         # (add() keeps the norm buffer padded to whole tiles)
-    norms[:len(xb)] = engine_norms(xb)
-    q_norm = np.zeros(nq_pad, np.float32)
-    q_norm[:nq] = engine_norms(xq)
-    resid = lambda x: (((x - bf16_round(x)).astype(np.float64) ** 2).sum(1) * 1.0001).astype(np.float32)   # noqa: E731
-    q_resid = np.zeros(nq_pad, np.float32)
-    q_resid[:nq] = resid(xq)
-    q_bad = np.zeros(nq_pad, np.uint8)
-    D = np.full((nq, k), np.nan, np.float32)
-    I = np.full((nq, k), -7, np.int64)
-    rerun = np.zeros(nq, np.int32)
-    n_rerun = ctypes.c_int(0)
-    stats = np.zeros(10, np.int64)
-    msg = lib.emu_search_largek(xb.ctypes.data, xb_b.ctypes.data, norms.ctypes.data, len(xb), float(norms.max()), float(resid(xb).max()),
-                                xq.ctypes.data, xq_b.ctypes.data, q_norm.ctypes.data, q_resid.ctypes.data, q_bad.ctypes.data, nq, k, metric,
-                                n_sms, D.ctypes.data, I.ctypes.data, rerun.ctypes.data, ctypes.byref(n_rerun), stats.ctypes.data)
-    assert msg is None, msg.decode()
-    return D, I, sorted(rerun[:n_rerun.value].tolist()), stats
+run_host_emu = harness.run_host_emu
 
 
 @pytest.mark.parametrize("metric,nb,nq,k,kind,n_sms", [(0, 80_000, 6, 1100, "normal", 8), (1, 72_000, 4, 1100, "normal", 8),

@@ -1,0 +1,71 @@
+"""CPU: the host driver of the default tensor-core tier, pq::search_mma_filter (k <= 1024: epochs, candidate slabs, carry
+lists, second attempts, rescoring + certificate, the k = 1 path), executed on the CPU and checked bit for bit against the
+oracle — the same checks tests/test_gpu_parity.py makes on the B200, minus the tcgen05 kernel itself.
+
+Real: the driver's source, the planner (pq_plan.h), and pq_mma_init_state_kernel / pq_epoch_select_kernel / pq_rescore_kernel
+/ pq_k1_finalize_kernel under the SIMT emulator (tests/simt/simt_emu.h).  Stand-in: pq_mma_filter_kernel, replaced by a
+functional model with the same CTA mapping, slab layout and admission rules (tests/simt/mma_host_emu.cpp.in).  This guards
+the host logic and the selection kernels against regressions on machines without a GPU; it is test infrastructure only.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import data
+from tests.simt import harness
+
+
+@pytest.fixture(scope="module")
+def host_emu(tmp_path_factory):
+    return harness.build_host_emu(tmp_path_factory.mktemp("simt_host"))
+
+
+def _exact(D, I, xq, xb, k, metric, rows=None):
+    rows = list(range(len(xq))) if rows is None else rows
+    Dr, Ir = oracle.engine_spec(xq[rows], xb, k, metric)
+    np.testing.assert_array_equal(I[rows], Ir)
+    np.testing.assert_array_equal(D[rows].view(np.uint32), Dr.view(np.uint32))
+
+
+@pytest.mark.parametrize("metric,nb,nq,k,kind,n_sms", [(0, 40_000, 20, 80, "normal", 8), (1, 30_000, 8, 10, "normal", 8), (0, 20_000, 130, 256, "fp16", 6),
+                                                        (0, 9_000, 5, 1024, "normal", 4), (0, 25_000, 12, 100, "skewed", 148)])
+def test_epoch_search_matches_the_oracle(host_emu, metric, nb, nq, k, kind, n_sms):
+    xb, xq = data.corpus(nb, kind=kind), data.queries(nq, kind=kind)
+    D, I, rerun, st = harness.run_host_emu(host_emu, xb, xq, k, metric, n_sms)
+    assert rerun == []
+    _exact(D, I, xq, xb, k, metric, rows=list(range(min(nq, 12))))
+    assert st[3] >= 2 and st[4] == st[3] + 1     # one select per epoch, then the rescoring kernel
+
+
+@pytest.mark.parametrize("metric,nb,nq", [(1, 2_000, 300), (0, 1_500, 200), (1, 130, 140)])
+def test_k1_assignment_path_matches_the_oracle(host_emu, metric, nb, nq):
+    """group_paras.py:45,51 — few centroids (the rows), many points (the queries), k = 1."""
+    xb, xq = data.corpus(nb), data.queries(nq)
+    D, I, rerun, st = harness.run_host_emu(host_emu, xb, xq, 1, metric)
+    assert rerun == []
+    _exact(D, I, xq, xb, 1, metric)
+    assert st[3] == 1 and st[4] == 1             # one filter pass, one finalize
+
+
+def test_k_larger_than_ntotal_pads(host_emu):
+    xb, xq = data.corpus(50), data.queries(4)
+    D, I, rerun, _ = harness.run_host_emu(host_emu, xb, xq, 80, 0)
+    assert rerun == []
+    assert (I[:, 50:] == -1).all() and (D[:, 50:] == -oracle.FLT_MAX).all()
+    _exact(D, I, xq, xb, 80, 0)
+
+
+def test_rows_in_document_order_take_the_second_attempt(host_emu):
+    """Topic-sorted rows: a whole cluster beats the threshold inside one epoch, the slabs overflow, the epoch is run again
+    with the threshold the first attempt produced (pq_epoch_select_kernel: allow_redo / is_redo)."""
+    rng = np.random.default_rng(11)
+    n, ncl, nq, k = 120_000, 2, 6, 100
+    cent = rng.standard_normal((ncl, 128)).astype(np.float32)
+    lab = np.sort(rng.integers(0, ncl, n))
+    xb = (cent[lab] + 2.0 * rng.standard_normal((n, 128))).astype(np.float32)
+    xq = (cent[rng.integers(0, ncl, nq)] + 0.3 * rng.standard_normal((nq, 128))).astype(np.float32)
+    D, I, rerun, st = harness.run_host_emu(host_emu, xb, xq, k, 0, n_sms=4)
+    assert st[8] > 0, "the second-attempt path was not exercised"
+    ok = [q for q in range(nq) if q not in rerun]
+    assert len(ok) >= nq - 1
+    _exact(D, I, xq, xb, k, 0, rows=ok)
