@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kSelThreads) pq_merge_lists_kernel(const Merge
         }
         __syncthreads();
         const int fill = s_fill;
+        __syncthreads();  // every thread has read the fill before the next batch's appends move it (the branch below must stay uniform)
         if (fill + kStep > p.work) {  // the next batch might not fit: keep the best k
             for (int i = fill + t; i < p.work; i += kSelThreads) work[i] = 0ull;
             __syncthreads();

@@ -139,3 +139,49 @@ def run_host_emu(lib, xb, xq, k, metric, n_sms=8):
                              n_sms, D.ctypes.data, I.ctypes.data, rerun.ctypes.data, ctypes.byref(n_rerun), stats.ctypes.data)
     assert msg is None, msg.decode()
     return D, I, sorted(rerun[:n_rerun.value].tolist()), stats
+
+
+def build_select_emu(workdir):
+    """pq_select.cu: pq_merge_lists_kernel (fp32 scan: per-CTA lists -> result) and pq_merge_di_kernel (multi-GPU: shard
+    results -> result) with their launchers."""
+    common = open(os.path.join(CSRC, "pq_common.cuh")).read()
+    sel = open(os.path.join(CSRC, "pq_select.cu")).read()
+    parts = key_and_sort_helpers(common) + [
+        extract(common, "void block_bitonic_merge_desc(uint64_t* a, int n)"),
+        extract(sel, "constexpr int kSelThreads = 256;", upto="constexpr int kSelThreads = 256;"),
+        extract(sel, "struct MergeParams {"),
+        extract(sel, "void emit_result(const MergeLaunch& a, int q, int i, uint64_t key)"),
+        extract(sel, "pq_merge_lists_kernel(const MergeParams p)"),
+        extract(sel, "static int next_pow2(int v)"),
+        extract(sel, "cudaError_t merge_lists_launch(const MergeLaunch& a, cudaStream_t stream)"),
+        extract(sel, "struct MergeDIParams {"),
+        extract(sel, "pq_merge_di_kernel(const MergeDIParams p)"),
+        extract(sel, "cudaError_t merge_di_launch(const float* D_in"),
+    ]
+    tmpl = open(os.path.join(SIMT, "select_emu.cpp.in")).read()
+    compile_so(tmpl.replace("@EXTRACTED@", to_host("\n".join(parts))), workdir, "select_emu", opt="-O2",
+               extra=("-I", CSRC, "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic"))
+    return load_select_emu(os.path.join(str(workdir), "select_emu.so"))
+
+
+def load_select_emu(path):
+    lib = ctypes.CDLL(path)
+    lib.path = path
+    vp, ll, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    lib.emu_merge_di.restype = ctypes.c_char_p
+    lib.emu_merge_di.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.emu_merge_lists.restype = ctypes.c_char_p
+    lib.emu_merge_lists.argtypes = [vp, ll, ll, i32, i32, vp, ll, vp, i32, i32, i32, vp, ll, vp, vp, vp]
+    return lib
+
+
+def merge_di(lib, D_all, I_all, k, metric):
+    """pq_merge_shard_results on numpy arrays [G, nq, k] -> (D [nq,k], I [nq,k])."""
+    D_all = np.ascontiguousarray(D_all, np.float32)
+    I_all = np.ascontiguousarray(I_all, np.int64)
+    G, nq, _ = D_all.shape
+    D = np.empty((nq, k), np.float32)
+    I = np.empty((nq, k), np.int64)
+    msg = lib.emu_merge_di(D_all.ctypes.data, I_all.ctypes.data, G, nq, k, metric, D.ctypes.data, I.ctypes.data)
+    assert msg is None, msg.decode()
+    return D, I

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <new>
 #include <map>
 #include <vector>
 

@@ -48,13 +48,26 @@ def _merge_double(D_all, I_all, k, metric):
     return torch.from_numpy(Do), torch.from_numpy(Io)
 
 
-def _worker(rank, world, port, metric, n, nq, k, out, row_shards=None):
+def _merge_kernel_emulated(so_path):
+    """The engine's own merge kernel (pq_merge_di_kernel + its launcher, what pq_merge_shard_results runs) executed under the
+    SIMT emulator of tests/simt — so that the gloo path is checked with the real merge logic, not only with a double."""
+    from tests.simt import harness
+    lib = harness.load_select_emu(so_path)
+
+    def merge(D_all, I_all, k, metric):
+        D, I = harness.merge_di(lib, D_all.numpy(), I_all.numpy(), k, metric)
+        return torch.from_numpy(D), torch.from_numpy(I)
+    return merge
+
+
+def _worker(rank, world, port, metric, n, nq, k, out, row_shards=None, merge_so=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from proqa_b200.sharded import ShardedIndexFlat, shard_bounds
         xb, xq = data.corpus(n), data.queries(nq)
-        sh = ShardedIndexFlat(128, metric, local_factory=lambda: _OracleLocal(metric), merge_fn=_merge_double, row_shards=row_shards)
+        merge_fn = _merge_kernel_emulated(merge_so) if merge_so else _merge_double
+        sh = ShardedIndexFlat(128, metric, local_factory=lambda: _OracleLocal(metric), merge_fn=merge_fn, row_shards=row_shards)
         sh.add(xb)
         R = row_shards or world
         lo, hi = shard_bounds(n, R, rank % R)
@@ -93,6 +106,21 @@ def test_query_groups_times_row_shards_equals_single_index(tmp_path, world, row_
     n, k = 1500, 12
     mp.spawn(_worker, args=(world, _free_port(), 0, n, nq, k, out, row_shards), nprocs=world, join=True)
     Dr, Ir = oracle.engine_spec(data.queries(nq), data.corpus(n), k, 0)
+    for rank in range(world):
+        z = np.load(out + f".{rank}.npz")
+        np.testing.assert_array_equal(z["I"], Ir)
+        np.testing.assert_array_equal(z["D"].view(np.uint32), Dr.view(np.uint32))
+
+
+@pytest.mark.parametrize("world,row_shards,metric,n,nq,k", [(2, None, 0, 3001, 7, 20), (2, None, 1, 900, 4, 50), (4, 2, 0, 1500, 9, 12)])
+def test_sharded_search_through_the_engines_merge_kernel(tmp_path, world, row_shards, metric, n, nq, k):
+    """Same as above with merge_fn = the engine's pq_merge_di_kernel under the SIMT emulator (built once, loaded by every rank)."""
+    from oracle import oracle
+    from tests.simt import harness
+    so = harness.build_select_emu(tmp_path).path
+    out = str(tmp_path / "res")
+    mp.spawn(_worker, args=(world, _free_port(), metric, n, nq, k, out, row_shards, so), nprocs=world, join=True)
+    Dr, Ir = oracle.engine_spec(data.queries(nq), data.corpus(n), k, metric)
     for rank in range(world):
         z = np.load(out + f".{rank}.npz")
         np.testing.assert_array_equal(z["I"], Ir)

@@ -1,0 +1,121 @@
+"""CPU: the selection / merge kernels of pq_select.cu — pq_merge_lists_kernel (fp32 scan: the per-CTA top-k lists of a query ->
+its result) and pq_merge_di_kernel (multi-GPU: the R shard results -> one, pq_merge_shard_results) — with their launchers,
+executed under the SIMT emulator (tests/simt) and compared with a plain numpy statement of what they must produce.
+Test infrastructure only; the kernels' source is taken verbatim from the engine."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests.simt import harness
+from tests.simt.harness import f32_ordered
+
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+
+@pytest.fixture(scope="module")
+def sel(tmp_path_factory):
+    return harness.build_select_emu(tmp_path_factory.mktemp("simt_select"))
+
+
+def make_keys(scores, rows):
+    return (f32_ordered(scores).astype(np.uint64) << np.uint64(32)) | ((~rows.astype(np.uint32)) & np.uint32(0xFFFFFFFF)).astype(np.uint64)
+
+
+def key_score(keys):
+    o = (keys >> np.uint64(32)).astype(np.uint32)
+    u = np.where(o & 0x80000000, o & 0x7FFFFFFF, ~o).astype(np.uint32)
+    return u.view(np.float32)
+
+
+def key_row(keys):
+    return (~(keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)).astype(np.int64)
+
+
+@pytest.mark.parametrize("nq,n_lists,list_len,k,metric,with_counts,with_gthr", [(3, 16, 100, 100, 0, False, False), (2, 148, 80, 80, 1, True, True),
+                                                                             (2, 40, 1000, 1000, 0, True, False), (1, 7, 30, 50, 0, False, True),
+                                                                             (1, 30, 5000, 5000, 0, False, False)])
+def test_merge_lists_kernel(sel, nq, n_lists, list_len, k, metric, with_counts, with_gthr):
+    rng = np.random.default_rng(nq * 1000 + n_lists)
+    rows = rng.permutation(n_lists * list_len * nq * 3)[:nq * n_lists * list_len].reshape(nq, n_lists, list_len)
+    scores = rng.standard_normal((nq, n_lists, list_len)).astype(np.float32)
+    scores[:, :, ::7] = np.float32(0.25)                       # exact ties: order must fall back to the row id
+    keys = make_keys(scores, rows)
+    keys[rng.random(keys.shape) < 0.1] = 0                     # empty slots
+    counts = rng.integers(0, list_len + 1, (nq, n_lists)).astype(np.uint32) if with_counts else None
+    gthr = f32_ordered(np.full(nq, -0.3, np.float32)) if with_gthr else None
+    q_norms = (rng.random(nq) * 50 + 100).astype(np.float32)
+    D = np.full((nq, k), np.nan, np.float32)
+    I = np.full((nq, k), -7, np.int64)
+    out_keys = np.zeros((nq, k), np.uint64)
+    msg = sel.emu_merge_lists(keys.ctypes.data, n_lists * list_len, list_len, n_lists, list_len, counts.ctypes.data if with_counts else None, n_lists,
+                              gthr.ctypes.data if with_gthr else None, nq, k, metric, q_norms.ctypes.data, 1000, D.ctypes.data, I.ctypes.data,
+                              out_keys.ctypes.data)
+    assert msg is None, msg.decode()
+    for q in range(nq):
+        live = keys[q].copy()
+        if with_counts:
+            live[np.arange(list_len)[None, :] >= counts[q][:, None]] = 0
+        live = live[live != 0]
+        if with_gthr:
+            live = live[live >= (np.uint64(gthr[q]) << np.uint64(32))]
+        want = np.sort(live)[::-1][:k]
+        n = len(want)
+        np.testing.assert_array_equal(out_keys[q, :n], want)
+        assert (out_keys[q, n:] == 0).all()
+        np.testing.assert_array_equal(I[q, :n], key_row(want) + 1000)
+        assert (I[q, n:] == -1).all()
+        s = key_score(want)
+        want_d = np.maximum(np.float32(0), q_norms[q] - s) if metric == 1 else s
+        np.testing.assert_array_equal(D[q, :n].view(np.uint32), want_d.astype(np.float32).view(np.uint32))
+        assert (D[q, n:] == (FLT_MAX if metric == 1 else -FLT_MAX)).all()
+
+
+def reference_merge(D_all, I_all, k, metric):
+    """Best-first; ties -> the lower global id; -1 padding last (what pq_merge_shard_results documents)."""
+    G, nq, _ = D_all.shape
+    D = D_all.transpose(1, 0, 2).reshape(nq, -1)
+    I = I_all.transpose(1, 0, 2).reshape(nq, -1)
+    Do = np.empty((nq, k), np.float32)
+    Io = np.empty((nq, k), np.int64)
+    for q in range(nq):
+        valid = I[q] >= 0
+        key = -D[q] if metric == 0 else D[q]
+        order = np.lexsort((I[q], key, ~valid))[:k]
+        Do[q], Io[q] = D[q, order], I[q, order]
+        pad = ~valid[order]
+        Do[q, pad] = FLT_MAX if metric == 1 else -FLT_MAX
+        Io[q, pad] = -1
+    return Do, Io
+
+
+@pytest.mark.parametrize("G,nq,k,metric", [(2, 5, 20, 0), (8, 3, 100, 1), (4, 2, 1000, 0), (3, 4, 7, 1), (1, 2, 16, 0)])
+def test_merge_shard_results_kernel(sel, G, nq, k, metric):
+    rng = np.random.default_rng(G * 100 + k)
+    per = 5000
+    D_all = np.empty((G, nq, k), np.float32)
+    I_all = np.empty((G, nq, k), np.int64)
+    for g in range(G):       # shard g owns ids [g*per, (g+1)*per); its list is best-first with ties in ascending id order
+        for q in range(nq):
+            n_valid = k if (g + q) % 3 else k // 2          # some shards hold fewer than k rows: -1 padding
+            ids = np.sort(rng.choice(per, n_valid, replace=False)) + g * per
+            sc = np.round(rng.standard_normal(n_valid), 1).astype(np.float32)      # coarse scores: many ties within and across shards
+            if metric == 1:
+                sc = np.abs(sc)
+            order = np.lexsort((ids, -sc if metric == 0 else sc))
+            D_all[g, q, :n_valid], I_all[g, q, :n_valid] = sc[order], ids[order]
+            D_all[g, q, n_valid:] = FLT_MAX if metric == 1 else -FLT_MAX
+            I_all[g, q, n_valid:] = -1
+    D, I = harness.merge_di(sel, D_all, I_all, k, metric)
+    Dr, Ir = reference_merge(D_all, I_all, k, metric)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D.view(np.uint32), Dr.view(np.uint32))
+
+
+def test_merge_refuses_what_does_not_fit_shared_memory(sel):
+    D_all = np.zeros((4, 1, 8000), np.float32)
+    I_all = np.zeros((4, 1, 8000), np.int64)
+    D = np.empty((1, 8000), np.float32)
+    I = np.empty((1, 8000), np.int64)
+    msg = sel.emu_merge_di(D_all.ctypes.data, I_all.ctypes.data, 4, 1, 8000, 0, D.ctypes.data, I.ctypes.data)
+    assert msg is not None and b"refused" in msg
