@@ -97,7 +97,9 @@ int pq_index_set_profile(pq_index* idx, int on);
 int pq_index_last_stats(const pq_index* idx, int64_t* out, int n);
 
 /* Merge G per-shard result lists (each [nq,k], best-first, global ids) into one — the kernel run
- * after the NCCL all-gather in the multi-GPU layer.  All pointers are device pointers on `device`. */
+ * after the NCCL all-gather in the multi-GPU layer.  All pointers are device pointers on `device`.  Up to 16384 keys per
+ * query (G * k) are sorted inside one CTA; beyond that every entry finds its place by ranking against the other lists
+ * (G <= 64). */
 int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists_dev,
                            const int64_t* I_lists_dev, float* D_out_dev, int64_t* I_out_dev);
 

@@ -168,6 +168,63 @@ __global__ void __launch_bounds__(kSelThreads) pq_merge_di_kernel(const MergeDIP
     }
 }
 
+// The same merge without shared memory, for n_lists * k beyond what one CTA can sort (two shards at k = 10000): every entry
+// finds its output position directly — its index in its own list plus, by binary search, the number of entries of every
+// other list that come before it in (score, global id) order.  Ids are disjoint across shards, so positions are unique.
+constexpr int kMergeRankMaxLists = 64;
+
+__device__ __forceinline__ bool di_before(float da, long long ia, float db, long long ib, bool l2) {
+    if (da != db) return l2 ? da < db : da > db;
+    return ia < ib;
+}
+
+__global__ void __launch_bounds__(kSelThreads) pq_merge_di_rank_kernel(const MergeDIParams p) {
+    __shared__ int s_len[kMergeRankMaxLists];  // valid entries per list (the -1 padding is a suffix)
+    const int q = blockIdx.x;
+    const int t = threadIdx.x;
+    const bool l2 = p.metric == kMetricL2;
+    for (int g = t; g < p.n_lists; g += kSelThreads) {
+        const long long* ids = p.I_in + ((size_t)g * p.nq + q) * p.k;
+        int lo = 0, hi = p.k;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ids[mid] >= 0) lo = mid + 1;
+            else hi = mid;
+        }
+        s_len[g] = lo;
+    }
+    __syncthreads();
+    int total_valid = 0;
+    for (int g = 0; g < p.n_lists; ++g) total_valid += s_len[g];
+    for (int e = t; e < p.n_lists * p.k; e += kSelThreads) {
+        const int g = e / p.k, i = e - g * p.k;
+        if (i >= s_len[g]) continue;
+        const size_t off = ((size_t)g * p.nq + q) * p.k + i;
+        const float d = p.D_in[off];
+        const long long id = p.I_in[off];
+        int pos = i;
+        for (int h = 0; h < p.n_lists && pos < p.k; ++h) {
+            if (h == g) continue;
+            const size_t base = ((size_t)h * p.nq + q) * p.k;
+            int lo = 0, hi = s_len[h];
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (di_before(p.D_in[base + mid], p.I_in[base + mid], d, id, l2)) lo = mid + 1;
+                else hi = mid;
+            }
+            pos += lo;
+        }
+        if (pos < p.k) {
+            p.D_out[(size_t)q * p.k + pos] = d;
+            p.I_out[(size_t)q * p.k + pos] = id;
+        }
+    }
+    for (int i = total_valid + t; i < p.k; i += kSelThreads) {
+        p.D_out[(size_t)q * p.k + i] = l2 ? FLT_MAX : -FLT_MAX;
+        p.I_out[(size_t)q * p.k + i] = -1;
+    }
+}
+
 cudaError_t merge_di_launch(const float* D_in, const long long* I_in, int n_lists, int nq, int k, int metric, float* D_out,
                             long long* I_out, cudaStream_t stream) {
     if (nq <= 0) return cudaSuccess;
@@ -175,7 +232,11 @@ cudaError_t merge_di_launch(const float* D_in, const long long* I_in, int n_list
     p.work = next_pow2(n_lists * k);
     if (p.work < 2) p.work = 2;
     const size_t smem = (size_t)p.work * 8;
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 200 * 1024) {  // too many keys for the in-CTA sort: position-by-ranking kernel
+        if (n_lists > kMergeRankMaxLists) return cudaErrorInvalidValue;
+        pq_merge_di_rank_kernel<<<nq, kSelThreads, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(pq_merge_di_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pq_merge_di_kernel<<<nq, kSelThreads, smem, stream>>>(p);

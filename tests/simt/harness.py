@@ -156,6 +156,9 @@ def build_select_emu(workdir):
         extract(sel, "cudaError_t merge_lists_launch(const MergeLaunch& a, cudaStream_t stream)"),
         extract(sel, "struct MergeDIParams {"),
         extract(sel, "pq_merge_di_kernel(const MergeDIParams p)"),
+        extract(sel, "constexpr int kMergeRankMaxLists = 64;", upto="constexpr int kMergeRankMaxLists = 64;"),
+        extract(sel, "bool di_before(float da, long long ia, float db, long long ib, bool l2)"),
+        extract(sel, "pq_merge_di_rank_kernel(const MergeDIParams p)"),
         extract(sel, "cudaError_t merge_di_launch(const float* D_in"),
     ]
     tmpl = open(os.path.join(SIMT, "select_emu.cpp.in")).read()

@@ -89,10 +89,11 @@ def reference_merge(D_all, I_all, k, metric):
     return Do, Io
 
 
-@pytest.mark.parametrize("G,nq,k,metric", [(2, 5, 20, 0), (8, 3, 100, 1), (4, 2, 1000, 0), (3, 4, 7, 1), (1, 2, 16, 0)])
+@pytest.mark.parametrize("G,nq,k,metric", [(2, 5, 20, 0), (8, 3, 100, 1), (4, 2, 1000, 0), (3, 4, 7, 1), (1, 2, 16, 0),
+                                           (2, 2, 10000, 0), (8, 1, 4000, 1), (3, 2, 15360, 0)])   # the last three: beyond the in-CTA sort
 def test_merge_shard_results_kernel(sel, G, nq, k, metric):
     rng = np.random.default_rng(G * 100 + k)
-    per = 5000
+    per = max(5000, 2 * k)
     D_all = np.empty((G, nq, k), np.float32)
     I_all = np.empty((G, nq, k), np.int64)
     for g in range(G):       # shard g owns ids [g*per, (g+1)*per); its list is best-first with ties in ascending id order
@@ -112,10 +113,11 @@ def test_merge_shard_results_kernel(sel, G, nq, k, metric):
     np.testing.assert_array_equal(D.view(np.uint32), Dr.view(np.uint32))
 
 
-def test_merge_refuses_what_does_not_fit_shared_memory(sel):
-    D_all = np.zeros((4, 1, 8000), np.float32)
-    I_all = np.zeros((4, 1, 8000), np.int64)
-    D = np.empty((1, 8000), np.float32)
-    I = np.empty((1, 8000), np.int64)
-    msg = sel.emu_merge_di(D_all.ctypes.data, I_all.ctypes.data, 4, 1, 8000, 0, D.ctypes.data, I.ctypes.data)
+def test_merge_refuses_more_lists_than_the_ranking_kernel_takes(sel):
+    G, k = 65, 300                                     # 65 x 300 keys do not fit the in-CTA sort, and 65 lists exceed the ranking kernel
+    D_all = np.zeros((G, 1, k), np.float32)
+    I_all = np.zeros((G, 1, k), np.int64)
+    D = np.empty((1, k), np.float32)
+    I = np.empty((1, k), np.int64)
+    msg = sel.emu_merge_di(D_all.ctypes.data, I_all.ctypes.data, G, 1, k, 0, D.ctypes.data, I.ctypes.data)
     assert msg is not None and b"refused" in msg
