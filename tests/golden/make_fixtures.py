@@ -12,6 +12,9 @@
    pure integer work and no reference code.
 2. known_answers.json — hand-checkable exact cases (small integers: every product and sum is exact in fp32, so any
    correct implementation, any accumulation order, must return these bits).
+3. trec_fixture.npz — retrieval/trec_process.py: retrieve_topk() (the k = 10000 call site, trec_process.py:69-94) imported and
+   called UNMODIFIED on synthetic inputs with the same ``faiss`` binding.  Stored: the seed of the inputs (regenerated and
+   checksummed by the tests), the labels, the I the function obtained (from the file it wrote) and the line it printed.
 """
 import json
 import os
@@ -120,6 +123,7 @@ def main():
     print("eval_fixture.npz written; seed", seed, "bytes", os.path.getsize(os.path.join(HERE, "eval_fixture.npz")))
 
     make_kmeans_fixture()
+    make_trec_fixture()
 
     # ---- hand-checkable known answers ---------------------------------------------------------------------------
     cases = []
@@ -187,8 +191,53 @@ def make_kmeans_fixture():
     print("kmeans_fixture.npz written, bytes", os.path.getsize(os.path.join(HERE, "kmeans_fixture.npz")), "split sizes", [len(sp) for sp in splits])
 
 
+TREC_N, TREC_NQ, TREC_K, TREC_SEED = 12000, 4, 10000, 987
+
+
+def trec_inputs():
+    """Deterministic inputs of the trec fixture (fp16 values, as get_embed.py --fp16 writes them)."""
+    rng = np.random.default_rng(TREC_SEED)
+    xb = rng.standard_normal((TREC_N, D)).astype(np.float16)
+    xq = rng.standard_normal((TREC_NQ, D)).astype(np.float16)
+    return xb, xq
+
+
+def make_trec_fixture():
+    import hashlib
+    xb, xq = trec_inputs()
+    S = xq.astype(np.float64) @ xb.astype(np.float64).T
+    order = np.argsort(-S, axis=1)
+    # labels: queries 0, 1, 3 have a relevant passage well inside the top 10000 (true ranks 3, 700, 9000), query 2 only
+    # far outside it (rank 11500 of 12000) — so the printed recall is 0.75 and no label sits near the k-th place
+    labels = [[int(order[0, 3]), int(order[0, 11000])], [int(order[1, 700])], [int(order[2, 11500])], [int(order[3, 9000])]]
+    tmp = tempfile.mkdtemp(prefix="proqa_golden_trec_")
+    np.save(os.path.join(tmp, "paras.npy"), xb)
+    np.save(os.path.join(tmp, "queries.npy"), xq)
+    with open(os.path.join(tmp, "queries.txt"), "w") as f:
+        for i in range(TREC_NQ):
+            f.write(json.dumps({"question": f"q {i}", "labels": labels[i], "qid": 100 + i}) + "\n")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "_oracle_faiss"), REF, env.get("PYTHONPATH", "")])
+    code = ("import trec_process as t; t.retrieve_topk(index_path='paras.npy', query_embeds='queries.npy', "
+            "query_input='queries.txt', output='out.txt')")
+    out = subprocess.run([sys.executable, "-c", code], cwd=tmp, env=env, capture_output=True, text=True, check=True)
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("Avg recall")]
+    assert len(line) == 1, out.stdout + out.stderr
+    rows = [json.loads(ln) for ln in open(os.path.join(tmp, "out.txt"))]
+    I = np.array([r["para_embed_idx"] for r in rows], dtype=np.int32)
+    assert I.shape == (TREC_NQ, TREC_K)
+    n_hit = np.array([int(np.sum(r["para_labels"])) for r in rows], np.int32)
+    np.savez_compressed(os.path.join(HERE, "trec_fixture.npz"), seed=np.int32(TREC_SEED), n=np.int32(TREC_N), nq=np.int32(TREC_NQ),
+                        k=np.int32(TREC_K), xb_sha1=np.array(hashlib.sha1(xb.tobytes()).hexdigest()),
+                        xq_sha1=np.array(hashlib.sha1(xq.tobytes()).hexdigest()), I=I, label_hits=n_hit,
+                        labels=np.array([json.dumps(lb) for lb in labels]), recall_line=np.array(line[0]))
+    print(line[0], "| label hits", n_hit.tolist(), "| trec_fixture.npz bytes", os.path.getsize(os.path.join(HERE, "trec_fixture.npz")))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "kmeans":
         make_kmeans_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "trec":
+        make_trec_fixture()
     else:
         main()

@@ -207,6 +207,18 @@ def test_large_k_trec_shape():
     _assert_bit_exact(D, I, *oracle.engine_spec(xq, xb, 10000, 0))
 
 
+def test_trec_fixture_ids_and_recall_line():
+    """tests/golden/trec_fixture.npz: the reference's retrieve_topk() (trec_process.py:69-94, k = 10000) run on the FAISS
+    restatement.  The engine must print the same recall line and name the same rows up to fp32 near-ties."""
+    from tests.golden_util import assert_same_up_to_near_ties, load_trec_fixture, trec_recall_line
+    fx = load_trec_fixture()
+    ix = _index(0, fx["xb"], "auto")
+    D, I = ix.search(fx["xq"], fx["k"])
+    _assert_bit_exact(D, I, *oracle.engine_spec(fx["xq"], fx["xb"], fx["k"], 0))
+    assert_same_up_to_near_ties(I, fx["I"], fx["xq"], fx["xb"])
+    assert trec_recall_line(I, fx) == fx["recall_line"]
+
+
 # ---- golden vectors (tests/golden/, generated from the reference's own eval_retrieval.py) ------------------------
 @pytest.mark.parametrize("tier", ["fp32", "bf16", "auto"])
 def test_eval_fixture_ids_and_recall_lines(tier):

@@ -16,7 +16,7 @@ import pytest
 
 from oracle import oracle
 from tests import data
-from tests.golden_util import load_eval_fixture, recall_lines
+from tests.golden_util import assert_same_up_to_near_ties, load_eval_fixture, load_trec_fixture, recall_lines, trec_recall_line
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -69,6 +69,19 @@ def test_eval_fixture_reproduced_by_the_oracle():
     De, Ie = oracle.engine_spec(fx["xq"], fx["xb"], fx["topk"], 0)
     np.testing.assert_array_equal(Ie, fx["I"])
     assert recall_lines(Ie, fx) == fx["recall_lines"]
+
+
+def test_trec_fixture_reproduced_by_the_oracle():
+    """The k = 10000 call site (trec_process.py:76), from the reference's own retrieve_topk() run on the restatement."""
+    fx = load_trec_fixture()
+    ix = oracle.IndexFlatIP(128)
+    ix.add(fx["xb"])
+    D, I = ix.search(fx["xq"], fx["k"])
+    np.testing.assert_array_equal(I, fx["I"])
+    assert trec_recall_line(I, fx) == fx["recall_line"] == "Avg recall: 0.75"
+    De, Ie = oracle.engine_spec(fx["xq"], fx["xb"], fx["k"], 0)
+    assert_same_up_to_near_ties(Ie, fx["I"], fx["xq"], fx["xb"])      # 10000 ranks deep there are fp32 near-ties
+    assert trec_recall_line(Ie, fx) == fx["recall_line"]
 
 
 @pytest.mark.parametrize("metric", [0, 1])
