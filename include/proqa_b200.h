@@ -126,6 +126,24 @@ void pq_kmeans_default_params(pq_kmeans_params* p);
 int pq_kmeans_train(pq_index* index, int64_t k, const pq_kmeans_params* params, int64_t n, const float* x_host, float* centroids_out,
                     float* obj_out, int64_t obj_cap, int64_t* n_obj);
 
+/* The same k-means iteration in steps, for training with the POINTS sharded over several GPUs (assignment
+ * needs no exchange, the centroid update needs one all-reduce of [k,128] sums + [k] counts).  Every rank holds the k current
+ * centroids in `index` and its own points on its device:
+ *   pq_kmeans_set_centroids   load the initial centroids (host array; renormalised when spherical) into the index
+ *   pq_kmeans_partial_device  assign the local points (index.search(x, 1)), leave per-centroid fp32 sums (added in index
+ *                             order) and counts in caller-provided device buffers, return the local objective
+ *   -- the caller all-reduces sums, counts and objective across ranks (NCCL) --
+ *   pq_kmeans_finish_device   centroids = sums / counts, void clusters split as FAISS does, renormalise when spherical,
+ *                             index.reset(); index.add(centroids).  Identical inputs give identical centroids on every rank.
+ * pq_rand_perm is FAISS's rand_perm (mt19937 seeded with `seed`), which Clustering uses to subsample and to pick the
+ * initial centroids.  Host mirror: proqa_b200/sharded_clustering.py. */
+void pq_rand_perm(int64_t n, int64_t seed, int32_t* out);
+int pq_kmeans_set_centroids(pq_index* index, int64_t k, const float* centroids_host, int spherical);
+int pq_kmeans_partial_device(pq_index* index, int64_t k, int64_t n_local, const float* x_dev, float* sums_dev, int32_t* counts_dev,
+                             double* objective_out);
+int pq_kmeans_finish_device(pq_index* index, int64_t k, int64_t n_total, int spherical, const float* sums_dev, const int32_t* counts_dev,
+                            float* centroids_out_host, int* nsplit_out);
+
 /* Introspection (no device needed; used by the CPU tests of the host logic): the launch plan of one tensor-tier search of nq
  * queries, top-k, over ntotal local rows on a device with n_sms SMs.  out[0..7] = {epochs, CTA groups, query tiles per group
  * (base), groups owning base+1, max tiles per group, carry length K', padded queries, 0}; then per epoch 8 values

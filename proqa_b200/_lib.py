@@ -50,6 +50,10 @@ SIGNATURES = {
                                                     _vp, _vp, _vp]),
     "pq_kmeans_default_params": (None, [ctypes.POINTER(KMeansParams)]),
     "pq_kmeans_train": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.POINTER(KMeansParams), ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int64, _i64p]),
+    "pq_rand_perm": (None, [ctypes.c_int64, ctypes.c_int64, _vp]),
+    "pq_kmeans_set_centroids": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int]),
+    "pq_kmeans_partial_device": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_double)]),
+    "pq_kmeans_finish_device": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int)]),
     "pq_plan_describe": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _i64p, ctypes.c_int]),
     "pq_plan_describe_large_k": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _i64p, ctypes.c_int]),
     "pq_last_error": (ctypes.c_char_p, []),

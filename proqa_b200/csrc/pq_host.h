@@ -71,6 +71,7 @@ struct pq_index {
     pq::DevBuf ws_scan_keys, ws_gthr;
     pq::DevBuf ws_rr_idx, ws_rr_q, ws_rr_qn, ws_rr_D, ws_rr_I;
     pq::DevBuf ws_mma[12];
+    pq::DevBuf ws_km[10];  // staged k-means (multi-GPU training): centroids, assignment, sort buffers
 
     int64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -112,6 +113,7 @@ struct pq_index {
                              &ws_qbad,  &ws_qresid, &ws_scan_keys, &ws_gthr, &ws_rr_idx, &ws_rr_q, &ws_rr_qn, &ws_rr_D,   &ws_rr_I};
         for (pq::DevBuf* b : all) b->release();
         for (pq::DevBuf& b : ws_mma) b.release();
+        for (pq::DevBuf& b : ws_km) b.release();
         sample_bf16.release();
         sample_norms.release();
         sample_rows = -1;

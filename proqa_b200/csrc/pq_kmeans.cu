@@ -57,6 +57,8 @@ __global__ void km_keys_kernel(const long long* __restrict__ assign, int n, int*
 }
 
 // One warp per centroid: lane l owns dims 4l..4l+3; points are added in ascending point index (stable sort order).
+// kMean = false leaves the plain sums (multi-GPU training: the shards' sums are all-reduced before the division).
+template <bool kMean>
 __global__ void __launch_bounds__(256) km_centroid_kernel(const float* __restrict__ x, const int* __restrict__ sorted_idx,
                                                           const int* __restrict__ offsets, const int* __restrict__ hist, int k,
                                                           float* __restrict__ centroids) {
@@ -82,11 +84,26 @@ __global__ void __launch_bounds__(256) km_centroid_kernel(const float* __restric
         const float4 r = __ldg(reinterpret_cast<const float4*>(x + (size_t)idx[j] * kDim) + lane);
         acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
     }
-    if (n > 0) {
+    if (kMean && n > 0) {
         const float ni = (float)n;
         acc.x /= ni; acc.y /= ni; acc.z /= ni; acc.w /= ni;
     }
     reinterpret_cast<float4*>(centroids + (size_t)c * kDim)[lane] = acc;
+}
+
+// centroid c = sums[c] / counts[c] (counts[c] == 0 leaves the zero sum; void clusters are handled on the host afterwards)
+__global__ void __launch_bounds__(256) km_divide_kernel(const float* __restrict__ sums, const int* __restrict__ counts, int k,
+                                                        float* __restrict__ centroids) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= k) return;
+    float4 v = reinterpret_cast<const float4*>(sums + (size_t)c * kDim)[lane];
+    const int n = counts[c];
+    if (n > 0) {
+        const float ni = (float)n;
+        v.x /= ni; v.y /= ni; v.z /= ni; v.w /= ni;
+    }
+    reinterpret_cast<float4*>(centroids + (size_t)c * kDim)[lane] = v;
 }
 
 // fvec_renorm_L2: every centroid scaled to unit norm (spherical k-means).
@@ -301,7 +318,7 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
             }
             const double imbalance = uf * (double)k / ((double)run * (double)run);
             KM_CUDA(cudaMemcpyAsync(d_off.p, offsets.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
-            km_centroid_kernel<<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, (const int*)d_vals2.p, (const int*)d_off.p, (const int*)d_hist.p, (int)k,
+            km_centroid_kernel<true><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, (const int*)d_vals2.p, (const int*)d_off.p, (const int*)d_hist.p, (int)k,
                                                                        (float*)d_cent.p);
             KM_CUDA(cudaGetLastError());
             int nsplit = 0;
@@ -353,9 +370,138 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
     return PQ_OK;
 }
 
+// ---- the same iteration in three steps, for training with the points sharded over several GPUs ------------------------
+// (proqa_b200/sharded_clustering.py: every rank calls partial on its points, the sums / counts / objective are all-reduced
+//  over NCCL, every rank calls finish with the identical totals and ends up with identical centroids.)
+static int kmeans_set_centroids_locked(pq_index* ix, int64_t k, const float* cent_host, int spherical) {
+    int rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    rc = ix->ws_km[0].ensure((size_t)k * kDim * 4);
+    if (rc) return rc;
+    PQ_CUDA(cudaMemcpyAsync(ix->ws_km[0].p, cent_host, (size_t)k * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
+    if (spherical) km_renorm_kernel<<<(unsigned)((k + 7) / 8), 256, 0, ix->stream>>>((float*)ix->ws_km[0].p, (int)k);
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    rc = index_reset_locked(ix);
+    if (!rc) rc = index_add_locked(ix, k, (const float*)ix->ws_km[0].p, true);
+    return rc;
+}
+
+static int kmeans_partial_locked(pq_index* ix, int64_t k, int64_t n, const float* dx, float* sums_dev, int* counts_dev, double* obj_out) {
+    if (!ix->device_ready || ix->ntotal != k) return set_error(PQ_ERR_INVALID, "kmeans_partial: the index must hold the k current centroids");
+    if (n < 0 || n > 0x7fffff00LL || k > (1 << 24)) return set_error(PQ_ERR_UNSUPPORTED, "kmeans_partial: k or n too large");
+    PQ_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    PQ_CUDA(cudaMemsetAsync(sums_dev, 0, (size_t)k * kDim * 4, st));
+    PQ_CUDA(cudaMemsetAsync(counts_dev, 0, (size_t)k * 4, st));
+    *obj_out = 0.0;
+    if (n == 0) {
+        PQ_CUDA(cudaStreamSynchronize(st));
+        return PQ_OK;
+    }
+    DevBuf* w = ix->ws_km;  // [1] D, [2] I, [3] keys, [4] keys2, [5] vals, [6] vals2, [7] offsets, [8] sort scratch, [9] partials
+    int rc = w[1].ensure((size_t)n * 4);
+    if (!rc) rc = w[2].ensure((size_t)n * 8);
+    for (int i = 3; i <= 6 && !rc; ++i) rc = w[i].ensure((size_t)n * 4);
+    if (!rc) rc = w[7].ensure((size_t)k * 4);
+    if (!rc) rc = w[9].ensure(1024 * 8);
+    if (rc) return rc;
+    int key_bits = 1;
+    while ((1LL << key_bits) < k) ++key_bits;
+    size_t tmp_bytes = 0;
+    PQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int*)w[3].p, (int*)w[4].p, (const int*)w[5].p, (int*)w[6].p, (int)n, 0, key_bits, st));
+    rc = w[8].ensure(tmp_bytes);
+    if (rc) return rc;
+    rc = search_device_impl(ix, n, dx, 1, (float*)w[1].p, (long long*)w[2].p);  // leaves the stream drained
+    if (rc) return rc;
+    std::vector<double> partial(1024);
+    km_objective_kernel<<<1024, 256, 0, st>>>((const float*)w[1].p, (int)n, (double*)w[9].p);
+    PQ_CUDA(cudaMemcpyAsync(partial.data(), w[9].p, 1024 * 8, cudaMemcpyDeviceToHost, st));
+    km_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const long long*)w[2].p, (int)n, (int*)w[3].p, (int*)w[5].p, counts_dev, (int)k);
+    PQ_CUDA(cub::DeviceRadixSort::SortPairs(w[8].p, tmp_bytes, (const int*)w[3].p, (int*)w[4].p, (const int*)w[5].p, (int*)w[6].p, (int)n, 0, key_bits, st));
+    std::vector<int> hassign((size_t)k), offsets((size_t)k);
+    PQ_CUDA(cudaMemcpyAsync(hassign.data(), counts_dev, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    PQ_CUDA(cudaStreamSynchronize(st));
+    int run = 0;
+    for (int64_t c = 0; c < k; ++c) {
+        offsets[c] = run;
+        run += hassign[c];
+    }
+    PQ_CUDA(cudaMemcpyAsync(w[7].p, offsets.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
+    km_centroid_kernel<false><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, (const int*)w[6].p, (const int*)w[7].p, counts_dev, (int)k, sums_dev);
+    PQ_CUDA(cudaGetLastError());
+    PQ_CUDA(cudaStreamSynchronize(st));  // `offsets` (host vector) must outlive its copy; the caller all-reduces next
+    double e64 = 0.0;
+    for (int b = 0; b < 1024; ++b) e64 += partial[b];
+    *obj_out = e64;
+    return PQ_OK;
+}
+
+static int kmeans_finish_locked(pq_index* ix, int64_t k, int64_t n_total, int spherical, const float* sums_dev, const int* counts_dev,
+                                float* centroids_out, int* nsplit_out) {
+    if (!ix->device_ready) return set_error(PQ_ERR_INVALID, "kmeans_finish: index has no device yet");
+    if (n_total < k) return set_error(PQ_ERR_INVALID, "kmeans_finish: fewer points than clusters");
+    PQ_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    int rc = ix->ws_km[0].ensure((size_t)k * kDim * 4);
+    if (rc) return rc;
+    float* d_cent = (float*)ix->ws_km[0].p;
+    km_divide_kernel<<<(unsigned)((k + 7) / 8), 256, 0, st>>>(sums_dev, counts_dev, (int)k, d_cent);
+    PQ_CUDA(cudaGetLastError());
+    std::vector<int> hassign((size_t)k);
+    PQ_CUDA(cudaMemcpyAsync(hassign.data(), counts_dev, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    PQ_CUDA(cudaStreamSynchronize(st));
+    int n_void = 0;
+    for (int64_t c = 0; c < k; ++c) n_void += hassign[c] == 0;
+    int nsplit = 0;
+    if (n_void) {
+        std::vector<float> cent((size_t)k * kDim);
+        PQ_CUDA(cudaMemcpyAsync(cent.data(), d_cent, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
+        PQ_CUDA(cudaStreamSynchronize(st));
+        nsplit = split_void_clusters(cent, hassign, k, n_total);
+        PQ_CUDA(cudaMemcpyAsync(d_cent, cent.data(), (size_t)k * kDim * 4, cudaMemcpyHostToDevice, st));
+        PQ_CUDA(cudaStreamSynchronize(st));
+    }
+    if (spherical) km_renorm_kernel<<<(unsigned)((k + 7) / 8), 256, 0, st>>>(d_cent, (int)k);
+    if (centroids_out) PQ_CUDA(cudaMemcpyAsync(centroids_out, d_cent, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
+    PQ_CUDA(cudaStreamSynchronize(st));
+    if (nsplit_out) *nsplit_out = nsplit;
+    rc = index_reset_locked(ix);
+    if (!rc) rc = index_add_locked(ix, k, d_cent, true);
+    return rc;
+}
+
 }  // namespace pq
 
 extern "C" {
+
+void pq_rand_perm(int64_t n, int64_t seed, int32_t* out) {
+    if (n <= 0 || !out) return;
+    std::vector<int> perm;
+    pq::rand_perm(perm, (size_t)n, seed);
+    memcpy(out, perm.data(), (size_t)n * 4);
+}
+
+int pq_kmeans_set_centroids(pq_index* index, int64_t k, const float* centroids_host, int spherical) {
+    if (!index || !centroids_host || k < 1) return pq::set_error(PQ_ERR_INVALID, "kmeans_set_centroids: bad argument");
+    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    return pq::kmeans_set_centroids_locked(index, k, centroids_host, spherical);
+}
+
+int pq_kmeans_partial_device(pq_index* index, int64_t k, int64_t n_local, const float* x_dev, float* sums_dev, int32_t* counts_dev,
+                             double* objective_out) {
+    if (!index || !sums_dev || !counts_dev || !objective_out || (n_local > 0 && !x_dev) || k < 1)
+        return pq::set_error(PQ_ERR_INVALID, "kmeans_partial_device: bad argument");
+    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    return pq::kmeans_partial_locked(index, k, n_local, x_dev, sums_dev, (int*)counts_dev, objective_out);
+}
+
+int pq_kmeans_finish_device(pq_index* index, int64_t k, int64_t n_total, int spherical, const float* sums_dev, const int32_t* counts_dev,
+                            float* centroids_out_host, int* nsplit_out) {
+    if (!index || !sums_dev || !counts_dev || k < 1) return pq::set_error(PQ_ERR_INVALID, "kmeans_finish_device: bad argument");
+    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    return pq::kmeans_finish_locked(index, k, n_total, spherical, sums_dev, (const int*)counts_dev, centroids_out_host, nsplit_out);
+}
 
 void pq_kmeans_default_params(pq_kmeans_params* p) {
     if (!p) return;

@@ -13,6 +13,7 @@ cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKin
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void* f, enum cudaFuncAttribute a, int v) {
     if (a == cudaFuncAttributeMaxDynamicSharedMemorySize) g_max_dyn_smem[f] = v;
     return v <= 232448 ? cudaSuccess : cudaErrorInvalidValue;

@@ -34,7 +34,7 @@ def extract(text, signature, upto=None):
 def to_host(src):
     src = re.sub(r"extern __shared__ __align__\(16\)", "extern", src)
     src = src.replace("__shared__", "static")
-    return re.sub(r"(\w+)<<<(.*?)>>>\((.*?)\);", r"EMU_LAUNCH(\1, \2, \3);", src, flags=re.S)
+    return re.sub(r"(\w+(?:<\w+>)?)<<<(.*?)>>>\((.*?)\);", r"EMU_LAUNCH(\1, \2, \3);", src, flags=re.S)
 
 
 def sources():
@@ -188,3 +188,34 @@ def merge_di(lib, D_all, I_all, k, metric):
     msg = lib.emu_merge_di(D_all.ctypes.data, I_all.ctypes.data, G, nq, k, metric, D.ctypes.data, I.ctypes.data)
     assert msg is None, msg.decode()
     return D, I
+
+
+def build_kmeans_emu(workdir):
+    """pq_kmeans.cu: the single-GPU driver and the staged (multi-GPU) steps with their kernels; CUB sort and the index
+    replaced by stand-ins (kmeans_emu.cpp.in)."""
+    common = open(os.path.join(CSRC, "pq_common.cuh")).read()
+    km = open(os.path.join(CSRC, "pq_kmeans.cu")).read()
+    helpers = "\n".join(key_and_sort_helpers(common)[:2] + [extract(common, "float engine_dot(const float* __restrict__ a")])
+    a = km.index("namespace pq {") + len("namespace pq {")
+    b = km.index("}  // namespace pq")
+    tmpl = open(os.path.join(SIMT, "kmeans_emu.cpp.in")).read()
+    text = tmpl.replace("@HELPERS@", to_host(helpers)).replace("@EXTRACTED@", to_host(km[a:b]))
+    compile_so(text, workdir, "kmeans_emu", opt="-O2", extra=("-I", CSRC, "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic"))
+    return load_kmeans_emu(os.path.join(str(workdir), "kmeans_emu.so"))
+
+
+def load_kmeans_emu(path):
+    lib = ctypes.CDLL(path)
+    lib.path = path
+    vp, ll, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    lib.emu_km_new.argtypes = [i32]
+    lib.emu_km_train.restype = ctypes.c_char_p
+    lib.emu_km_train.argtypes = [vp, ll, ll, i32, i32, i32, ll, vp, vp, ll, ctypes.POINTER(ll)]
+    lib.emu_rand_perm.argtypes = [ll, ll, vp]
+    for name, args in (("emu_km_set_centroids", [ll, vp, i32]), ("emu_km_partial", [ll, ll, vp, vp, vp, ctypes.POINTER(ctypes.c_double)]),
+                       ("emu_km_finish", [ll, ll, i32, vp, vp, vp, ctypes.POINTER(i32)])):
+        getattr(lib, name).restype = ctypes.c_char_p
+        getattr(lib, name).argtypes = args
+    lib.emu_km_assign.restype = ll
+    lib.emu_km_assign.argtypes = [vp, ll, vp, vp]
+    return lib

@@ -34,8 +34,48 @@ struct Rendezvous {
     unsigned gen = 0;
 };
 
+// Context switch.  glibc's swapcontext makes a system call (signal mask) per switch, which dominates kernels that
+// synchronise often; on x86-64 a dozen instructions do (callee-saved registers + stack pointer).  Elsewhere: ucontext.
+#if defined(__x86_64__)
+extern "C" void simt_switch(void** save_sp, void* load_sp);
+asm(".text\n"
+    ".globl simt_switch\n"
+    ".type simt_switch,@function\n"
+    "simt_switch:\n"
+    "    pushq %rbp\n    pushq %rbx\n    pushq %r12\n    pushq %r13\n    pushq %r14\n    pushq %r15\n"
+    "    movq %rsp, (%rdi)\n"
+    "    movq %rsi, %rsp\n"
+    "    popq %r15\n    popq %r14\n    popq %r13\n    popq %r12\n    popq %rbx\n    popq %rbp\n"
+    "    ret\n"
+    ".size simt_switch, .-simt_switch\n");
+struct Context {
+    void* sp = nullptr;
+};
+inline void context_switch(Context* from, Context* to) { simt_switch(&from->sp, to->sp); }
+inline void context_make(Context* c, char* stack, size_t bytes, void (*entry)()) {
+    uintptr_t top = ((uintptr_t)stack + bytes) & ~(uintptr_t)15;
+    void** sp = (void**)(top - 64);
+    for (int i = 0; i < 6; ++i) sp[i] = nullptr;   // r15, r14, r13, r12, rbx, rbp
+    sp[6] = (void*)entry;                          // popped by `ret`; the entry then sees rsp = top - 8 (ABI alignment)
+    sp[7] = nullptr;
+    c->sp = sp;
+}
+#else
+struct Context {
+    ucontext_t uc;
+};
+inline void context_switch(Context* from, Context* to) { swapcontext(&from->uc, &to->uc); }
+inline void context_make(Context* c, char* stack, size_t bytes, void (*entry)()) {
+    getcontext(&c->uc);
+    c->uc.uc_stack.ss_sp = stack;
+    c->uc.uc_stack.ss_size = bytes;
+    c->uc.uc_link = nullptr;
+    makecontext(&c->uc, entry, 0);
+}
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
+    Context ctx;
     bool done = false;
     unsigned tid = 0;
 };
@@ -44,7 +84,7 @@ inline std::vector<std::vector<char>> g_stacks;   // reused from block to block
 
 struct BlockState {
     std::vector<Fiber> fibers;
-    ucontext_t sched;
+    Context sched;
     int current = -1;
     unsigned bar_arrived = 0, bar_gen = 0, live = 0;
     unsigned long long progress = 0;   // bumped whenever any collective completes or a thread exits
@@ -59,7 +99,7 @@ inline Dim3 threadIdx, blockIdx, blockDim, gridDim;
 inline void yield_to_scheduler() {
     BlockState* b = g_block;
     Fiber& f = b->fibers[b->current];
-    swapcontext(&f.ctx, &b->sched);
+    context_switch(&f.ctx, &b->sched);
 }
 
 inline void fiber_entry() {
@@ -74,7 +114,8 @@ inline void fiber_entry() {
         b->bar_arrived = 0;
         b->bar_gen++;
     }
-    swapcontext(&f.ctx, &b->sched);
+    context_switch(&f.ctx, &b->sched);   // never resumed
+    abort();
 }
 
 // Runs `body` once per thread of every block, blocks one after the other.  Returns null, or a message on deadlock.
@@ -93,11 +134,7 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
             Fiber& f = b.fibers[t];
             f.tid = t;
             if (g_stacks[t].empty()) g_stacks[t].resize(kStackBytes);
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = g_stacks[t].data();
-            f.ctx.uc_stack.ss_size = g_stacks[t].size();
-            f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+            context_make(&f.ctx, g_stacks[t].data(), g_stacks[t].size(), fiber_entry);
         }
         unsigned long long last_progress = ~0ull;
         while (b.live > 0) {
@@ -110,7 +147,7 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
                 if (b.fibers[t].done) continue;
                 b.current = (int)t;
                 threadIdx.x = t;
-                swapcontext(&b.sched, &b.fibers[t].ctx);
+                context_switch(&b.sched, &b.fibers[t].ctx);
             }
         }
         g_block = nullptr;
