@@ -18,3 +18,11 @@ print("stats", ix.last_stats)
 PY
 echo "memcheck exit $?" | tee -a gpurun_out/largek_memcheck.log
 tail -15 gpurun_out/largek_memcheck.log
+# every path written after round 1's last GPU run, under memcheck and racecheck (includes the merge_lists barrier fix)
+export PROQA_B200_STAGED_KMEANS=1
+timeout -s KILL 600 python -m pytest tests/test_gpu_sharded_kmeans.py -m gpu -x -q > gpurun_out/staged_kmeans_tests.log 2>&1
+echo "staged k-means tests exit $?"; tail -5 gpurun_out/staged_kmeans_tests.log
+for tool in memcheck racecheck synccheck; do
+  PROQA_B200_SANITIZE_NEW=1 timeout -s KILL 900 compute-sanitizer --tool $tool --error-exitcode 3 python tools/sanitize_small.py > gpurun_out/new_paths_$tool.log 2>&1
+  echo "$tool rc=$?"; tail -3 gpurun_out/new_paths_$tool.log
+done
