@@ -310,22 +310,27 @@ static void renorm_l2(int d, int64_t k, float* c) {
     }
 }
 
-/* km_update_centroids: per-centroid sums in point order (fp32), mean, then void clusters split a populated one. */
-static int km_update_centroids(const float* x, float* centroids, const int64_t* assign, int d, int64_t k, int64_t n, int64_t* hassign) {
+/* Clustering.cpp at v1.6.3 (the release that added weighted / encoded k-means): compute_centroids + split_clusters.
+ *   compute_centroids: per-centroid sums in point order (fp32); the counts are FLOATS (hassign[ci] += 1.0); the mean is a
+ *                      multiplication by the reciprocal:  float norm = 1 / hassign[ci];  c[j] *= norm;
+ *   split_clusters:    a void cluster takes a copy of a populated one, picked with probability (hassign[cj] - 1.0) / (n - k)
+ *                      by RandomGenerator(1234), both perturbed by +-1/1024; the counts are split in half AS FLOATS
+ *                      (hassign[ci] = hassign[cj] / 2), which matters for the probabilities of later splits. */
+static int km_update_centroids(const float* x, float* centroids, const int64_t* assign, int d, int64_t k, int64_t n, float* hassign) {
     memset(centroids, 0, sizeof(float) * (size_t)(d * k));
-    memset(hassign, 0, sizeof(int64_t) * (size_t)k);
+    memset(hassign, 0, sizeof(float) * (size_t)k);
     for (int64_t i = 0; i < n; ++i) {
         const int64_t ci = assign[i];
         float* c = centroids + ci * d;
         const float* xi = x + i * d;
-        hassign[ci]++;
+        hassign[ci] += 1.0;
         for (int j = 0; j < d; ++j) c[j] += xi[j];
     }
     for (int64_t ci = 0; ci < k; ++ci) {
+        if (hassign[ci] == 0) continue;
+        const float norm = 1 / hassign[ci];
         float* c = centroids + ci * d;
-        const float ni = (float)hassign[ci];
-        if (ni != 0)
-            for (int j = 0; j < d; ++j) c[j] /= ni;
+        for (int j = 0; j < d; ++j) c[j] *= norm;
     }
     int nsplit = 0;
     const float EPS = 1.f / 1024.f;
@@ -378,7 +383,7 @@ int faiss_kmeans_train(const float* x_in, int64_t n_in, int d, int64_t k, int ni
     }
     int64_t* assign = (int64_t*)malloc(sizeof(int64_t) * (size_t)nx);
     float* dis = (float*)malloc(sizeof(float) * (size_t)nx);
-    int64_t* hassign = (int64_t*)malloc(sizeof(int64_t) * (size_t)k);
+    float* hassign = (float*)malloc(sizeof(float) * (size_t)k);
     int* perm = (int*)malloc(sizeof(int) * (size_t)nx);
     faiss_rand_perm(perm, nx, seed + 1);
     for (int64_t i = 0; i < k; ++i) memcpy(centroids + i * d, x + (int64_t)perm[i] * d, sizeof(float) * (size_t)d);

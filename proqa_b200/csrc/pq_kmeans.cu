@@ -7,7 +7,7 @@
 //     assign = index.search(x, 1)            -> the engine's k = 1 path (tensor-core filter + exact fp32 rescoring)
 //     centroid c = mean of its points        -> here: stable sort of points by centroid, then one warp per centroid
 //                                               adds its points IN INDEX ORDER in fp32 (the same sequential sum
-//                                               FAISS's km_update_centroids performs), divided by the count
+//                                               FAISS's compute_centroids performs), times 1 / count
 //     empty clusters split a big one         -> host, same RandomGenerator(1234) walk and +-1/1024 perturbation
 //     index.reset(); index.add(centroids)
 // The assignment search is the hot part (250 x 10M x 10k); everything else is < 10 % of an iteration.
@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(256) km_centroid_kernel(const float* __restric
         const float4 r = __ldg(reinterpret_cast<const float4*>(x + (size_t)idx[j] * kDim) + lane);
         acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
     }
-    if (kMean && n > 0) {
-        const float ni = (float)n;
-        acc.x /= ni; acc.y /= ni; acc.z /= ni; acc.w /= ni;
+    if (kMean && n > 0) {  // compute_centroids (Clustering.cpp, v1.6.3): float norm = 1 / hassign[ci]; c[j] *= norm;
+        const float norm = 1.f / (float)n;
+        acc.x *= norm; acc.y *= norm; acc.z *= norm; acc.w *= norm;
     }
     reinterpret_cast<float4*>(centroids + (size_t)c * kDim)[lane] = acc;
 }
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(256) km_divide_kernel(const float* __restrict_
     float4 v = reinterpret_cast<const float4*>(sums + (size_t)c * kDim)[lane];
     const int n = counts[c];
     if (n > 0) {
-        const float ni = (float)n;
-        v.x /= ni; v.y /= ni; v.z /= ni; v.w /= ni;
+        const float norm = 1.f / (float)n;
+        v.x *= norm; v.y *= norm; v.z *= norm; v.w *= norm;
     }
     reinterpret_cast<float4*>(centroids + (size_t)c * kDim)[lane] = v;
 }
@@ -145,10 +145,12 @@ static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// km_update_centroids' treatment of void clusters (host; touches only the few affected rows).
-static int split_void_clusters(std::vector<float>& cent, std::vector<int>& hassign, int64_t k, int64_t n) {
+// split_clusters (Clustering.cpp, v1.6.3) — the treatment of void clusters (host; touches only the few affected rows).
+// FAISS keeps the cluster sizes as floats there: a split halves a size as a float, which feeds the probabilities of later splits.
+static int split_void_clusters(std::vector<float>& cent, const std::vector<int>& counts, int64_t k, int64_t n) {
     const float EPS = 1.f / 1024.f;
     int nsplit = 0;
+    std::vector<float> hassign(counts.begin(), counts.end());
     FaissRng rng(1234);
     for (int64_t ci = 0; ci < k; ++ci) {
         if (hassign[ci] != 0) continue;
