@@ -61,7 +61,10 @@ class Clustering(ClusteringParameters):
         n_obj = ctypes.c_int64(0)
         rc = _lib.lib().pq_kmeans_train(index._h, self.k, ctypes.byref(prm), n, x.ctypes.data, cent.ctypes.data, obj.ctypes.data, len(obj),
                                         ctypes.byref(n_obj))
-        _lib.check(rc, "Clustering.train")
+        if rc == -4:
+            raise MemoryError(f"proqa_b200: Clustering.train failed ({rc}): {_lib.last_error()}")
+        if rc != 0:   # FAISS_THROW_IF_NOT_* (too few points, NaN input) reaches Python as RuntimeError through the SWIG layer
+            raise RuntimeError(f"proqa_b200: Clustering.train failed ({rc}): {_lib.last_error()}")
         self.centroids = cent
         self.obj = obj[:n_obj.value].copy()
 

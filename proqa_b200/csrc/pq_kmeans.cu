@@ -179,11 +179,11 @@ static int split_void_clusters(std::vector<float>& cent, const std::vector<int>&
 
 static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& prm, int64_t n_in, const float* x_host, float* centroids_out,
                                float* obj_out, int64_t obj_cap, int64_t* n_obj) {
-    if (k < 1 || n_in < k) return set_error(PQ_ERR_INVALID, "kmeans: number of training points (%lld) should be at least as large as number of clusters (%lld)",
+    if (k < 1 || n_in < k) return set_error(PQ_ERR_INVALID, "Number of training points (%lld) should be at least as large as number of clusters (%lld)",
                                             (long long)n_in, (long long)k);
     if (k > (1 << 24) || n_in > 0x7fffff00LL) return set_error(PQ_ERR_UNSUPPORTED, "kmeans: k or n too large");
     for (int64_t i = 0; i < n_in * kDim; ++i)
-        if (!std::isfinite(x_host[i])) return set_error(PQ_ERR_INVALID, "kmeans: input contains NaN's or Inf's");
+        if (!std::isfinite(x_host[i])) return set_error(PQ_ERR_INVALID, "input contains NaN's or Inf's");
     int rc = index_init_device(ix);
     if (rc) return rc;
     PQ_CUDA(cudaSetDevice(ix->device));

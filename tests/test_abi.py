@@ -52,6 +52,21 @@ def test_bad_arguments_raise_like_faiss():
         ix.search(np.zeros((3, 128), np.float32), 0)
 
 
+def test_clustering_argument_errors_are_faiss_runtime_errors():
+    """Clustering::train's FAISS_THROW_IF_NOT checks surface as RuntimeError through SWIG; the engine's host mirror does the
+    same, with FAISS's wording, before it ever touches a device."""
+    import proqa_b200 as pq
+    clus = pq.Clustering(128, 50)
+    with pytest.raises(RuntimeError, match=r"Number of training points \(10\) should be at least as large as number of clusters \(50\)"):
+        clus.train(np.zeros((10, 128), np.float32), pq.IndexFlatL2(128))
+    bad = np.zeros((100, 128), np.float32)
+    bad[3, 3] = np.nan
+    with pytest.raises(RuntimeError, match="input contains NaN's or Inf's"):
+        clus.train(bad, pq.IndexFlatL2(128))
+    with pytest.raises(AssertionError):
+        clus.train(np.zeros((100, 64), np.float32), pq.IndexFlatL2(128))
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():

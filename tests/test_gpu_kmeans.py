@@ -83,9 +83,9 @@ def test_kmeans_errors():
     import proqa_b200 as pq
     ix = pq.IndexFlatL2(128)
     clus = pq.Clustering(128, 50)
-    with pytest.raises(ValueError):
+    with pytest.raises(RuntimeError, match="should be at least as large as number of clusters"):   # FAISS's exception type and text
         clus.train(np.zeros((10, 128), np.float32), ix)          # fewer points than clusters
     bad = np.zeros((100, 128), np.float32)
     bad[3, 3] = np.nan
-    with pytest.raises(ValueError):
+    with pytest.raises(RuntimeError, match="NaN"):
         clus.train(bad, ix)
