@@ -7,6 +7,8 @@
 static const char* g_emu_error = nullptr;
 static std::map<const void*, int> g_max_dyn_smem;
 
+extern "C" void emu_set_schedule(unsigned seed) { simt::g_schedule_seed = seed; }
+
 extern "C" {
 cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }

@@ -113,8 +113,10 @@ def resid2(x):
     return (((x - bf16_round(x)).astype(np.float64) ** 2).sum(1) * 1.0001).astype(np.float32)
 
 
-def run_host_emu(lib, xb, xq, k, metric, n_sms=8):
-    """-> D, I, sorted list of queries the driver wants re-run by the fp32 scan, the driver's statistics."""
+def run_host_emu(lib, xb, xq, k, metric, n_sms=8, schedule=0):
+    """-> D, I, sorted list of queries the driver wants re-run by the fp32 scan, the driver's statistics.
+    schedule != 0: the emulator resumes the threads of a block in a different pseudo-random order at every pass."""
+    lib.emu_set_schedule(schedule)
     nq = len(xq)
     nq_pad = (nq + 127) // 128 * 128
     xb = np.ascontiguousarray(xb, np.float32)
@@ -141,11 +143,17 @@ def run_host_emu(lib, xb, xq, k, metric, n_sms=8):
     return D, I, sorted(rerun[:n_rerun.value].tolist()), stats
 
 
-def build_select_emu(workdir):
+def build_select_emu(workdir, drop=None):
     """pq_select.cu: pq_merge_lists_kernel (fp32 scan: per-CTA lists -> result) and pq_merge_di_kernel (multi-GPU: shard
-    results -> result) with their launchers."""
+    results -> result) with their launchers.  `drop`: the beginning of one source line to leave out (negative tests)."""
     common = open(os.path.join(CSRC, "pq_common.cuh")).read()
     sel = open(os.path.join(CSRC, "pq_select.cu")).read()
+    if drop:
+        lines = sel.split("\n")
+        hit = [i for i, ln in enumerate(lines) if ln.strip().startswith(drop)]
+        assert len(hit) == 1, f"expected exactly one line starting with {drop!r}"
+        del lines[hit[0]]
+        sel = "\n".join(lines)
     parts = key_and_sort_helpers(common) + [
         extract(common, "void block_bitonic_merge_desc(uint64_t* a, int n)"),
         extract(sel, "constexpr int kSelThreads = 256;", upto="constexpr int kSelThreads = 256;"),

@@ -4,7 +4,8 @@
 // block-wide barriers, warp votes/shuffles/matches, shared-memory atomics and divergence are modelled; timing, the memory
 // model and data races are NOT (threads of a block are cooperative fibers on one OS thread, switched only at barriers and
 // warp collectives).  A collective that can never complete (divergent __syncthreads, a vote some lane of the mask never
-// reaches) is reported as a deadlock instead of hanging; barriers are matched by count, not by call site.  This is a checker for tests/, never a product path.
+// reaches) is reported as a deadlock instead of hanging, and threads of a block meeting at different __syncthreads() calls
+// as a divergent barrier.  This is a checker for tests/, never a product path.
 #pragma once
 
 #include <float.h>
@@ -87,6 +88,8 @@ struct BlockState {
     Context sched;
     int current = -1;
     unsigned bar_arrived = 0, bar_gen = 0, live = 0;
+    int bar_site = 0;                  // source line of the __syncthreads() the current generation's first thread arrived from
+    bool divergent = false;
     unsigned long long progress = 0;   // bumped whenever any collective completes or a thread exits
     std::map<std::pair<int, unsigned>, Rendezvous> rv;   // (warp, mask) -> rendezvous
     std::function<void()> body;
@@ -94,6 +97,12 @@ struct BlockState {
 };
 
 inline BlockState* g_block = nullptr;
+// 0: threads are resumed in ascending order every pass.  Otherwise: a different pseudo-random order every pass, so that which
+// thread arrives last at a barrier (and therefore runs ahead of everyone else to the next one) changes from barrier to
+// barrier — code that reads shared state after a barrier which a thread running ahead may already have changed then shows
+// up as wrong results or as a divergent barrier.
+inline unsigned g_schedule_seed = 0;
+inline char g_message[200];
 inline Dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 inline void yield_to_scheduler() {
@@ -137,13 +146,22 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
             context_make(&f.ctx, g_stacks[t].data(), g_stacks[t].size(), fiber_entry);
         }
         unsigned long long last_progress = ~0ull;
+        std::vector<unsigned> order(block);
+        for (unsigned t = 0; t < block; ++t) order[t] = t;
         while (b.live > 0) {
             if (b.progress == last_progress) {
                 g_block = nullptr;
                 return "deadlock: no thread of the block can make progress (divergent barrier or incomplete warp collective)";
             }
             last_progress = b.progress;
-            for (unsigned t = 0; t < block; ++t) {
+            if (g_schedule_seed) {   // Fisher-Yates with a small LCG
+                for (unsigned i = block - 1; i > 0; --i) {
+                    g_schedule_seed = g_schedule_seed * 1664525u + 1013904223u;
+                    std::swap(order[i], order[(g_schedule_seed >> 8) % (i + 1)]);
+                }
+            }
+            for (unsigned i = 0; i < block; ++i) {
+                const unsigned t = order[i];
                 if (b.fibers[t].done) continue;
                 b.current = (int)t;
                 threadIdx.x = t;
@@ -151,13 +169,22 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
             }
         }
         g_block = nullptr;
+        if (b.divergent) return g_message;
     }
     return nullptr;
 }
 
-inline void syncthreads() {
+// `site` = source line of the call.  The hardware matches barrier arrivals by count only; two groups of threads that meet at
+// different __syncthreads() calls are a bug (undefined behaviour) even when the counts happen to add up, so it is reported.
+inline void syncthreads(int site) {
     BlockState* b = g_block;
     const unsigned my_gen = b->bar_gen;
+    if (b->bar_arrived == 0) b->bar_site = site;
+    else if (b->bar_site != site && !b->divergent) {
+        b->divergent = true;
+        snprintf(g_message, sizeof(g_message), "divergent barrier: threads of one block met at different __syncthreads() calls (generated lines %d and %d)",
+                 b->bar_site, site);
+    }
     b->bar_arrived++;
     if (b->bar_arrived == b->live) {
         b->bar_arrived = 0;
@@ -244,7 +271,7 @@ using std::min;
 #define __restrict__
 #define __align__(n) alignas(n)
 
-inline void __syncthreads() { simt::syncthreads(); }
+#define __syncthreads() simt::syncthreads(__LINE__)
 inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::warp_exchange(mask, 0); }
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src) {

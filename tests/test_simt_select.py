@@ -121,3 +121,50 @@ def test_merge_refuses_more_lists_than_the_ranking_kernel_takes(sel):
     I = np.empty((1, k), np.int64)
     msg = sel.emu_merge_di(D_all.ctypes.data, I_all.ctypes.data, G, 1, k, 0, D.ctypes.data, I.ctypes.data)
     assert msg is not None and b"refused" in msg
+
+
+# ---- the barrier after the fill count is read (pq_merge_lists_kernel) -------------------------------------------------------
+def _fill_boundary_case():
+    """One query, lists of 1024 entries: the first batch leaves 1022 entries in the work array (two empty slots), so the
+    'sort now?' test  fill + 1024 > 2048  is false — unless a thread that ran ahead has already appended its candidates of
+    the second batch."""
+    rng = np.random.default_rng(1)
+    n_lists, list_len, k = 3, 1024, 64
+    scores = rng.standard_normal((1, n_lists, list_len)).astype(np.float32)
+    rows = np.arange(n_lists * list_len).reshape(1, n_lists, list_len)
+    keys = make_keys(scores, rows)
+    keys[0, 0, 5] = 0
+    keys[0, 0, 700] = 0
+    return keys, n_lists, list_len, k
+
+
+def _run_merge(lib, keys, n_lists, list_len, k):
+    D = np.empty((1, k), np.float32)
+    I = np.empty((1, k), np.int64)
+    out = np.zeros((1, k), np.uint64)
+    q_norms = np.zeros(1, np.float32)
+    msg = lib.emu_merge_lists(keys.ctypes.data, n_lists * list_len, list_len, n_lists, list_len, None, n_lists, None, 1, k, 0, q_norms.ctypes.data, 0,
+                              D.ctypes.data, I.ctypes.data, out.ctypes.data)
+    return msg, out
+
+
+def test_fill_count_barrier_holds_under_adversarial_schedules(sel, tmp_path):
+    keys, n_lists, list_len, k = _fill_boundary_case()
+    want = np.sort(keys[keys != 0])[::-1][:k]
+    try:
+        for seed in (0, 1, 2, 3, 4, 5):
+            sel.emu_set_schedule(seed)
+            msg, out = _run_merge(sel, keys, n_lists, list_len, k)
+            assert msg is None, (seed, msg)
+            np.testing.assert_array_equal(out[0], want)
+    finally:
+        sel.emu_set_schedule(0)
+    # the same kernel without that barrier: some schedule lets a thread run ahead into the next batch before the others have
+    # read the fill count, and the block-uniform branch stops being uniform
+    broken = harness.build_select_emu(tmp_path, drop="__syncthreads();  // every thread has read the fill before")
+    bad = 0
+    for seed in (0, 1, 2, 3, 4, 5):
+        broken.emu_set_schedule(seed)
+        msg, out = _run_merge(broken, keys, n_lists, list_len, k)
+        bad += (msg is not None) or not np.array_equal(out[0], want)
+    assert bad > 0, "the emulator's schedules no longer expose the hazard this barrier closes"

@@ -69,3 +69,18 @@ def test_rows_in_document_order_take_the_second_attempt(host_emu):
     ok = [q for q in range(nq) if q not in rerun]
     assert len(ok) >= nq - 1
     _exact(D, I, xq, xb, k, 0, rows=ok)
+
+
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_results_do_not_depend_on_the_thread_schedule(host_emu, schedule):
+    """The emulator resumes a block's threads in a different pseudo-random order after every barrier / warp collective, so
+    that another thread runs ahead each time; shared state read after a barrier that a thread running ahead may already have
+    changed shows up as wrong results or as a divergent barrier (tests/test_simt_select.py has the worked example)."""
+    try:
+        for metric, nb, nq, k in ((0, 30_000, 10, 80), (1, 1_500, 150, 1), (0, 80_000, 5, 1100)):
+            xb, xq = data.corpus(nb), data.queries(nq)
+            D, I, rerun, _ = harness.run_host_emu(host_emu, xb, xq, k, metric, schedule=schedule)
+            assert rerun == []
+            _exact(D, I, xq, xb, k, metric, rows=list(range(min(nq, 6))))
+    finally:
+        host_emu.emu_set_schedule(0)
