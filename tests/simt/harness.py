@@ -167,6 +167,8 @@ def build_select_emu(workdir, drop=None):
         extract(sel, "constexpr int kMergeRankMaxLists = 64;", upto="constexpr int kMergeRankMaxLists = 64;"),
         extract(sel, "bool di_before(float da, long long ia, float db, long long ib, bool l2)"),
         extract(sel, "pq_merge_di_rank_kernel(const MergeDIParams p)"),
+        extract(sel, "pq_prep_rows_kernel(const float* __restrict__ rows"),
+        extract(sel, "cudaError_t prep_rows_launch(const float* rows"),
         extract(sel, "cudaError_t merge_di_launch(const float* D_in"),
     ]
     tmpl = open(os.path.join(SIMT, "select_emu.cpp.in")).read()
@@ -181,6 +183,8 @@ def load_select_emu(path):
     vp, ll, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
     lib.emu_merge_di.restype = ctypes.c_char_p
     lib.emu_merge_di.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.emu_prep_rows.restype = ctypes.c_char_p
+    lib.emu_prep_rows.argtypes = [vp, ll, vp, vp, vp, vp, vp, vp, vp]
     lib.emu_merge_lists.restype = ctypes.c_char_p
     lib.emu_merge_lists.argtypes = [vp, ll, ll, i32, i32, vp, ll, vp, i32, i32, i32, vp, ll, vp, vp, vp]
     return lib
@@ -227,3 +231,48 @@ def load_kmeans_emu(path):
     lib.emu_km_assign.restype = ll
     lib.emu_km_assign.argtypes = [vp, ll, vp, vp]
     return lib
+
+
+def build_fp32_scan_emu(workdir):
+    """The exact fp32 tier: pq_ffma_scan_kernel + launcher, search_fp32_scan, pq_merge_lists_kernel; TMA and mbarriers replaced
+    by stand-ins (ffma_emu.cpp.in)."""
+    common = open(os.path.join(CSRC, "pq_common.cuh")).read()
+    sel = open(os.path.join(CSRC, "pq_select.cu")).read()
+    ffma = open(os.path.join(CSRC, "pq_ffma.cu")).read()
+    index = open(os.path.join(CSRC, "pq_index.cu")).read()
+    helpers = "\n".join(key_and_sort_helpers(common))
+    select = "\n".join([
+        extract(sel, "constexpr int kSelThreads = 256;", upto="constexpr int kSelThreads = 256;"),
+        extract(sel, "struct MergeParams {"),
+        extract(sel, "void emit_result(const MergeLaunch& a, int q, int i, uint64_t key)"),
+        extract(sel, "pq_merge_lists_kernel(const MergeParams p)"),
+        extract(sel, "static int next_pow2(int v)").replace("next_pow2", "sel_next_pow2"),
+        extract(sel, "cudaError_t merge_lists_launch(const MergeLaunch& a, cudaStream_t stream)").replace("next_pow2", "sel_next_pow2"),
+    ])
+    a = ffma.index("namespace pq {") + len("namespace pq {")
+    b = ffma.index("}  // namespace pq")
+    body = ffma[a:b].replace("extern __shared__ __align__(1024) uint8_t smem[];", "uint8_t* smem = smem_raw;")
+    tmpl = open(os.path.join(SIMT, "ffma_emu.cpp.in")).read()
+    text = (tmpl.replace("@HELPERS@", to_host(helpers)).replace("@SELECT@", to_host(select)).replace("@FFMA@", to_host(body))
+            .replace("@SCAN_DRIVER@", to_host(extract(index, "int search_fp32_scan(pq_index* ix"))))
+    lib = compile_so(text, workdir, "ffma_emu", opt="-O2", extra=("-I", CSRC, "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic"))
+    vp, ll, i32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    lib.emu_fp32_scan.restype = ctypes.c_char_p
+    lib.emu_fp32_scan.argtypes = [vp, vp, ll, vp, vp, i32, i32, i32, i32, ll, vp, vp, vp]
+    return lib
+
+
+def run_fp32_scan_emu(lib, xb, xq, k, metric, n_sms=6, id_base=0, schedule=0):
+    lib.emu_set_schedule(schedule)
+    xb = np.ascontiguousarray(xb, np.float32)
+    xq = np.ascontiguousarray(xq, np.float32)
+    norms = np.zeros(len(xb) + 256, np.float32)
+    norms[:len(xb)] = engine_norms(xb) if len(xb) else 0
+    q_norm = engine_norms(xq)
+    D = np.full((len(xq), k), np.nan, np.float32)
+    I = np.full((len(xq), k), -7, np.int64)
+    stats = np.zeros(10, np.int64)
+    msg = lib.emu_fp32_scan(xb.ctypes.data, norms.ctypes.data, len(xb), xq.ctypes.data, q_norm.ctypes.data, len(xq), k, metric, n_sms, id_base,
+                            D.ctypes.data, I.ctypes.data, stats.ctypes.data)
+    assert msg is None, msg.decode()
+    return D, I, stats

@@ -323,6 +323,13 @@ inline T atomicMax(T* p, T v) {
     return old;
 }
 template <typename T>
+inline T atomicOr(T* p, T v) {
+    const T old = *p;
+    *p = old | v;
+    return old;
+}
+inline unsigned __float_as_uint(float f) { return simt::from_bits<unsigned>(simt::to_bits(f)); }
+template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

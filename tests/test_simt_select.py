@@ -168,3 +168,30 @@ def test_fill_count_barrier_holds_under_adversarial_schedules(sel, tmp_path):
         msg, out = _run_merge(broken, keys, n_lists, list_len, k)
         bad += (msg is not None) or not np.array_equal(out[0], want)
     assert bad > 0, "the emulator's schedules no longer expose the hazard this barrier closes"
+
+
+# ---- add()-time row preparation (pq_prep_rows_kernel): bf16 copy, engine norms, residuals, non-finite flags ------------------
+def test_prep_rows_kernel_matches_the_numpy_model(sel):
+    from tests import data
+    x = data.corpus(700, kind="skewed")
+    x[13, 5] = np.inf
+    x[14, 9] = np.nan
+    x[15, 1] = 3.39e38                        # finite in fp32, overflows bf16
+    n = len(x)
+    bf = np.zeros((n, 128), np.uint16)
+    norms = np.zeros(n, np.float32)
+    row_bad = np.full(n, 7, np.uint8)
+    resid = np.zeros(n, np.float32)
+    scal = np.zeros(3, np.uint32)             # max norm bits, non-finite flag, max residual bits
+    msg = sel.emu_prep_rows(x.ctypes.data, n, bf.ctypes.data, norms.ctypes.data, scal[0:].ctypes.data, scal[1:].ctypes.data, row_bad.ctypes.data,
+                            resid.ctypes.data, scal[2:].ctypes.data)
+    assert msg is None, msg
+    good = np.ones(n, bool)
+    good[[13, 14, 15]] = False
+    np.testing.assert_array_equal(bf[good], harness.bf16_bits(x[good]))                          # round to nearest even
+    np.testing.assert_array_equal(norms[good].view(np.uint32), harness.engine_norms(x[good]).view(np.uint32))
+    assert row_bad[good].sum() == 0 and row_bad[[13, 14, 15]].tolist() == [1, 1, 1] and scal[1] == 1
+    model = (((x[good] - harness.bf16_round(x[good])).astype(np.float64) ** 2).sum(1))
+    assert (resid[good] >= model * 0.99999).all() and (resid[good] <= model * 1.001 + 1e-30).all()   # an upper bound, tight
+    assert scal[2:].view(np.float32)[0] == resid[good].max()
+    assert scal[0:1].view(np.float32)[0] >= norms[good].max()
