@@ -48,4 +48,4 @@ static void emu_launch(const void* fn, long long grid, int block, size_t smem, F
 }
 }  // namespace pq
 #define EMU_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    emu_launch((const void*)kernel, (grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
+    emu_launch((const void*)(kernel), (grid), (block), (smem), [&] { (kernel)(__VA_ARGS__); })

@@ -23,7 +23,7 @@ def extract(text, signature, upto=None):
     line that is exactly '}' or '};' — or, when `upto` is given, through the first line containing it."""
     lines = text.split("\n")
     start = next(i for i, ln in enumerate(lines) if signature in ln)
-    if start > 0 and lines[start - 1].startswith("template"):
+    while start > 0 and (lines[start - 1].startswith("template") or lines[start - 1].startswith("__global__")):
         start -= 1
     end = start
     while not ((upto in lines[end]) if upto else lines[end] in ("}", "};")):
@@ -34,7 +34,8 @@ def extract(text, signature, upto=None):
 def to_host(src):
     src = re.sub(r"extern __shared__ __align__\(16\)", "extern", src)
     src = src.replace("__shared__", "static")
-    return re.sub(r"(\w+(?:<\w+>)?)<<<(.*?)>>>\((.*?)\);", r"EMU_LAUNCH(\1, \2, \3);", src, flags=re.S)
+    # (the kernel name goes in parentheses: template arguments contain commas the preprocessor would split on)
+    return re.sub(r"(\w+(?:<[\w, ]+>)?)<<<(.*?)>>>\((.*?)\);", r"EMU_LAUNCH((\1), \2, \3);", src, flags=re.S)
 
 
 def sources():
@@ -59,10 +60,33 @@ def compile_so(cpp_text, workdir, name, opt="-O1", extra=()):
     return ctypes.CDLL(so)
 
 
-def build_host_emu(workdir):
-    """The tensor-tier host drivers (search_mma_filter, search_mma_largek) + their kernels, emulated; the tcgen05 filter
-    kernel replaced by the functional stand-in in mma_host_emu.cpp.in."""
+def build_host_emu(workdir, real_filter=False, mutate=None):
+    """The tensor-tier host drivers (search_mma_filter, search_mma_largek) + their kernels, emulated.  The tcgen05 filter
+    kernel is either replaced by a functional stand-in (filter_functional.inc: fast) or executed itself on models of
+    mbarriers / TMA / TMEM / tcgen05.mma (filter_tcgen05.inc, real_filter=True)."""
     common, mma, inl = sources()
+    if real_filter:
+        kernel = "\n".join([
+            extract(mma, "constexpr int kBM = 128;", upto="static_assert(kBM == kPlanQueryTile"),
+            extract(mma, "struct MmaCtrl {"),
+            extract(common, "uint64_t umma_desc_k128(uint32_t smem_addr)"),
+            extract(common, "constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N)"),
+            extract(mma, "void mma_apply_l2_bias(float (&v)[32], const float4* norms)"),
+            extract(mma, "void mma_mask_tail(float (&v)[32], uint32_t base_row, uint32_t row_end32)"),
+            extract(mma, "void mma_filter32(float (&v)[32], float th, uint32_t base_row"),
+            extract(mma, "void mma_filter32_k1(float (&v)[32], float& thr, float two_e"),
+            extract(mma, "pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams p)")
+            .replace("extern __shared__ __align__(1024) uint8_t smem[];", "uint8_t* smem = smem_raw;"),
+            extract(mma, "static cudaError_t launch_filter(const CUtensorMap& tc"),
+            extract(mma, "static cudaError_t launch_filter_m(int m_max"),
+            extract(mma, "static cudaError_t launch_filter_any(int m_max"),
+        ])
+        if mutate:   # negative tests: (old, new) applied to the kernel text, must hit exactly once
+            assert kernel.count(mutate[0]) == 1, f"{mutate[0]!r} occurs {kernel.count(mutate[0])} times"
+            kernel = kernel.replace(mutate[0], mutate[1])
+        filter_impl = open(os.path.join(SIMT, "filter_tcgen05.inc")).read().replace("@FILTER_KERNEL@", to_host(kernel))
+    else:
+        filter_impl = open(os.path.join(SIMT, "filter_functional.inc")).read()
     device = "\n".join(key_and_sort_helpers(common) + [
         extract(mma, "struct MmaParams {"),
         extract(mma, "struct QState {"),
@@ -77,9 +101,10 @@ def build_host_emu(workdir):
     ])
     host = extract(mma, "static int next_pow2i(int v)") + extract(mma, "int search_mma_filter(pq_index* ix")
     tmpl = open(os.path.join(SIMT, "mma_host_emu.cpp.in")).read()
-    text = tmpl.replace("@EXTRACTED_DEVICE@", to_host(device)).replace("@EXTRACTED_HOST@", to_host(host)).replace("@EXTRACTED_LARGEK@", to_host(inl))
+    text = (tmpl.replace("@EXTRACTED_DEVICE@", to_host(device)).replace("@FILTER_IMPL@", filter_impl)
+            .replace("@EXTRACTED_HOST@", to_host(host)).replace("@EXTRACTED_LARGEK@", to_host(inl)))
     # -Bsymbolic: our fake CUDA runtime, not a libcudart some other module of the test process has loaded
-    lib = compile_so(text, workdir, "mma_host_emu", opt="-O2", extra=("-I", CSRC, "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic"))
+    lib = compile_so(text, workdir, "mma_host_emu_real" if real_filter else "mma_host_emu", opt="-O2", extra=("-I", CSRC, "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic"))
     vp = ctypes.c_void_p
     lib.emu_search_mma.restype = ctypes.c_char_p
     lib.emu_search_mma.argtypes = [vp, vp, vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp,

@@ -20,6 +20,7 @@
 #include <functional>
 #include <new>
 #include <map>
+#include <string>
 #include <vector>
 
 namespace simt {
@@ -79,6 +80,8 @@ struct Fiber {
     Context ctx;
     bool done = false;
     unsigned tid = 0;
+    char waiting_on[48] = "";   // what the thread is blocked at (diagnostics of a reported deadlock)
+    unsigned wait_seq = 0;      // converged waits this thread has begun (see warp_converged_wait)
 };
 constexpr size_t kStackBytes = 128 * 1024;
 inline std::vector<std::vector<char>> g_stacks;   // reused from block to block
@@ -88,6 +91,7 @@ struct BlockState {
     Context sched;
     int current = -1;
     unsigned bar_arrived = 0, bar_gen = 0, live = 0;
+    unsigned warp_passed[32] = {};     // per warp: sequence number of the last converged wait known to have passed
     int bar_site = 0;                  // source line of the __syncthreads() the current generation's first thread arrived from
     bool divergent = false;
     unsigned long long progress = 0;   // bumped whenever any collective completes or a thread exits
@@ -148,8 +152,23 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
         unsigned long long last_progress = ~0ull;
         std::vector<unsigned> order(block);
         for (unsigned t = 0; t < block; ++t) order[t] = t;
+        unsigned long long passes = 0;
         while (b.live > 0) {
+            if (++passes > 4000000ull) {   // watchdog: something keeps moving without ever finishing
+                g_block = nullptr;
+                return "livelock: the block is still running after 4M scheduler passes";
+            }
             if (b.progress == last_progress) {
+                if (getenv("SIMT_EMU_VERBOSE")) {
+                    std::map<std::string, std::vector<unsigned>> who;
+                    for (const Fiber& f : b.fibers)
+                        if (!f.done) who[f.waiting_on].push_back(f.tid);
+                    for (const auto& kv : who) {
+                        fprintf(stderr, "simt deadlock, block %u: %zu thread(s) at [%s]:", bx, kv.second.size(), kv.first.c_str());
+                        for (size_t i = 0; i < kv.second.size() && i < 12; ++i) fprintf(stderr, " %u", kv.second[i]);
+                        fprintf(stderr, "\n");
+                    }
+                }
                 g_block = nullptr;
                 return "deadlock: no thread of the block can make progress (divergent barrier or incomplete warp collective)";
             }
@@ -192,10 +211,38 @@ inline void syncthreads(int site) {
         b->progress++;
         return;
     }
+    snprintf(b->fibers[b->current].waiting_on, 48, "__syncthreads line %d", site);
     while (b->bar_gen == my_gen) {
         yield_to_scheduler();
         threadIdx.x = g_block->fibers[g_block->current].tid;
     }
+    b->fibers[b->current].waiting_on[0] = 0;
+    b->progress++;
+}
+// A spin-wait on some memory-resident condition (an mbarrier phase) that the hardware evaluates ONCE for a converged warp: all
+// lanes of the warp execute the same sequence of such waits, so the n-th wait of a warp has passed for every lane as soon as
+// any lane saw its condition hold — even if the condition has changed again by the time a late fiber looks.  Spinning is not
+// progress: a wait whose condition never comes true ends as a reported deadlock.
+template <class Pred>
+inline void warp_converged_wait(Pred pred, const char* what, const void* p, unsigned v) {
+    BlockState* b = g_block;
+    Fiber& f = b->fibers[b->current];
+    const unsigned warp = f.tid >> 5;
+    const unsigned seq = ++f.wait_seq;
+    while (!(b->warp_passed[warp] >= seq || pred())) {
+        snprintf(f.waiting_on, 48, "%s %p %u", what, p, v);
+        yield_to_scheduler();
+        threadIdx.x = f.tid;
+    }
+    f.waiting_on[0] = 0;
+    if (b->warp_passed[warp] < seq) {
+        b->warp_passed[warp] = seq;
+        b->progress++;
+    }
+}
+inline void note_wait(const char* what, const void* p, unsigned v) {
+    BlockState* b = g_block;
+    snprintf(b->fibers[b->current].waiting_on, 48, "%s %p %u", what, p, v);
 }
 
 // every lane named in `mask` contributes v; returns the 32 contributed values (valid until this lane's next collective)
@@ -222,10 +269,13 @@ inline const uint64_t* warp_exchange(unsigned mask, uint64_t v) {
         r.gen++;
         b->progress++;
     } else {
+        snprintf(b->fibers[b->current].waiting_on, 48, "warp collective mask %08x", mask);
         while (r.gen == my_gen) {
             yield_to_scheduler();
             threadIdx.x = g_block->fibers[g_block->current].tid;
         }
+        b->fibers[b->current].waiting_on[0] = 0;
+        b->progress++;   // (a thread leaving a wait is a state change too: a pass is only dead when nobody moved at all)
     }
     return r.snap;
 }

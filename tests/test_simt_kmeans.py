@@ -19,6 +19,8 @@ from oracle import oracle
 from tests.simt import harness
 from tests.test_kmeans_oracle import blobs
 
+pytestmark = pytest.mark.timeout(600)   # an emulated kernel that never finishes must not hang the suite
+
 
 @pytest.fixture(scope="module")
 def km(tmp_path_factory):

@@ -19,6 +19,8 @@ from tests import data
 from tests.simt import harness
 from tests.simt.harness import bf16_round, engine_norms, f32_ordered
 
+pytestmark = pytest.mark.timeout(600)   # an emulated kernel that never finishes must not hang the suite
+
 
 def _device_source():
     common, mma, inl = harness.sources()

@@ -12,6 +12,8 @@ from tests.simt.harness import f32_ordered
 
 FLT_MAX = np.float32(3.4028234663852886e38)
 
+pytestmark = pytest.mark.timeout(600)   # an emulated kernel that never finishes must not hang the suite
+
 
 @pytest.fixture(scope="module")
 def sel(tmp_path_factory):

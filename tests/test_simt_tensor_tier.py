@@ -14,6 +14,8 @@ from oracle import oracle
 from tests import data
 from tests.simt import harness
 
+pytestmark = pytest.mark.timeout(600)   # an emulated kernel that never finishes must not hang the suite
+
 
 @pytest.fixture(scope="module")
 def host_emu(tmp_path_factory):
