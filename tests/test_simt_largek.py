@@ -242,3 +242,18 @@ def test_host_driver_on_rows_in_document_order(host_emu):
     Dr, Ir = oracle.engine_spec(xq, xb, k, 0)
     np.testing.assert_array_equal(I[ok], Ir[ok])
     np.testing.assert_array_equal(D[ok].view(np.uint32), Dr[ok].view(np.uint32))
+
+
+def test_large_k_path_with_the_filter_kernel_itself(tmp_path):
+    """Phases A and B through pq_mma_filter_kernel's own source on the hardware model of tests/simt/filter_tcgen05.inc (the sample
+    tensor map, a corpus that does not end on a tile boundary), L2, under a fuzzed schedule."""
+    lib = harness.build_host_emu(tmp_path, real_filter=True)
+    xb, xq = data.corpus(72_050), data.queries(4)
+    try:
+        D, I, rerun, stats = run_host_emu(lib, xb, xq, 1100, 1, schedule=1)
+    finally:
+        lib.emu_set_schedule(0)
+    assert rerun == []
+    Dr, Ir = oracle.engine_spec(xq, xb, 1100, 1)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D.view(np.uint32), Dr.view(np.uint32))
