@@ -217,7 +217,7 @@ run_host_emu = harness.run_host_emu
 
 
 @pytest.mark.parametrize("metric,nb,nq,k,kind,n_sms", [(0, 80_000, 6, 1100, "normal", 8), (1, 72_000, 4, 1100, "normal", 8),
-                                                        (0, 140_000, 3, 2048, "fp16", 5), (0, 100_000, 130, 1500, "normal", 16)])
+                                                        (0, 140_000, 3, 2048, "fp16", 5), (0, 72_000, 130, 1100, "normal", 16)])
 def test_host_driver_phases_a_b_c_match_the_oracle(host_emu, metric, nb, nq, k, kind, n_sms):
     xb, xq = data.corpus(nb, kind=kind), data.queries(nq, kind=kind)
     nchk = min(nq, 4)                       # (the emulated kernels run every query; the oracle comparison needs only a few)
