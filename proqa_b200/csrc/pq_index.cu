@@ -687,7 +687,12 @@ static int merge_shard_results_impl(int device, int metric, int n_lists, int64_t
                                     float* D_out, int64_t* I_out, cudaStream_t stream, bool sync) {
     if (n_lists < 1 || nq < 0 || k < 1 || !D_lists || !I_lists || !D_out || !I_out)
         return set_error(PQ_ERR_INVALID, "merge_shard_results: bad arguments");
-    if ((int64_t)n_lists * k > 16384) return set_error(PQ_ERR_UNSUPPORTED, "merge_shard_results: n_lists*k=%lld > 16384", (long long)(n_lists * k));
+    if (k > PQ_MAX_K) return set_error(PQ_ERR_UNSUPPORTED, "merge_shard_results: k=%lld exceeds PQ_MAX_K=%d", (long long)k, PQ_MAX_K);
+    // up to 16384 keys per query are sorted inside one CTA; beyond that every entry is placed by ranking it against the
+    // other lists (pq_merge_di_rank_kernel), which takes at most 64 lists
+    if ((int64_t)n_lists * k > 16384 && n_lists > 64)
+        return set_error(PQ_ERR_UNSUPPORTED, "merge_shard_results: %d lists of k=%lld (more than 64 lists beyond 16384 keys per query)", n_lists,
+                         (long long)k);
     int dev = -1;
     int rc = pick_device(device, &dev);
     if (rc) return rc;

@@ -170,13 +170,11 @@ __global__ void __launch_bounds__(kSelThreads) pq_merge_di_kernel(const MergeDIP
 
 // The same merge without shared memory, for n_lists * k beyond what one CTA can sort (two shards at k = 10000): every entry
 // finds its output position directly — its index in its own list plus, by binary search, the number of entries of every
-// other list that come before it in (score, global id) order.  Ids are disjoint across shards, so positions are unique.
+// other list that come before it.  "Before" is the order pq_merge_di_kernel sorts by: score, then (list, position) — a
+// total order even when an L2 list holds equal distances whose ids are not ascending (the engine orders L2 lists by
+// 2<q,x> - |x|^2 before clamping and rounding |q|^2 - that to D), so output positions never collide.  Within one list the
+// scores are non-increasing (best first), which is all the binary search needs.
 constexpr int kMergeRankMaxLists = 64;
-
-__device__ __forceinline__ bool di_before(float da, long long ia, float db, long long ib, bool l2) {
-    if (da != db) return l2 ? da < db : da > db;
-    return ia < ib;
-}
 
 __global__ void __launch_bounds__(kSelThreads) pq_merge_di_rank_kernel(const MergeDIParams p) {
     __shared__ int s_len[kMergeRankMaxLists];  // valid entries per list (the -1 padding is a suffix)
@@ -201,22 +199,24 @@ __global__ void __launch_bounds__(kSelThreads) pq_merge_di_rank_kernel(const Mer
         if (i >= s_len[g]) continue;
         const size_t off = ((size_t)g * p.nq + q) * p.k + i;
         const float d = p.D_in[off];
-        const long long id = p.I_in[off];
         int pos = i;
         for (int h = 0; h < p.n_lists && pos < p.k; ++h) {
             if (h == g) continue;
-            const size_t base = ((size_t)h * p.nq + q) * p.k;
+            // entries of list h that precede (d, g, i): strictly better scores, and equal scores when h < g
+            const float* Dh = p.D_in + ((size_t)h * p.nq + q) * p.k;
             int lo = 0, hi = s_len[h];
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (di_before(p.D_in[base + mid], p.I_in[base + mid], d, id, l2)) lo = mid + 1;
+                const float dm = Dh[mid];
+                const bool before = (dm != d) ? (l2 ? dm < d : dm > d) : (h < g);
+                if (before) lo = mid + 1;
                 else hi = mid;
             }
             pos += lo;
         }
         if (pos < p.k) {
             p.D_out[(size_t)q * p.k + pos] = d;
-            p.I_out[(size_t)q * p.k + pos] = id;
+            p.I_out[(size_t)q * p.k + pos] = p.I_in[off];
         }
     }
     for (int i = total_valid + t; i < p.k; i += kSelThreads) {

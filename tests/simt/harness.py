@@ -190,7 +190,6 @@ def build_select_emu(workdir, drop=None):
         extract(sel, "struct MergeDIParams {"),
         extract(sel, "pq_merge_di_kernel(const MergeDIParams p)"),
         extract(sel, "constexpr int kMergeRankMaxLists = 64;", upto="constexpr int kMergeRankMaxLists = 64;"),
-        extract(sel, "bool di_before(float da, long long ia, float db, long long ib, bool l2)"),
         extract(sel, "pq_merge_di_rank_kernel(const MergeDIParams p)"),
         extract(sel, "pq_prep_rows_kernel(const float* __restrict__ rows"),
         extract(sel, "cudaError_t prep_rows_launch(const float* rows"),

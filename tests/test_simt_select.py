@@ -115,6 +115,26 @@ def test_merge_shard_results_kernel(sel, G, nq, k, metric):
     np.testing.assert_array_equal(D.view(np.uint32), Dr.view(np.uint32))
 
 
+@pytest.mark.parametrize("G,k", [(2, 64), (2, 10000), (3, 6000)])
+def test_merge_l2_equal_distances_with_unsorted_ids(sel, G, k):
+    """L2 lists are ordered by the engine's key 2<q,x> - |x|^2 before D = max(0, |q|^2 - key) is rounded, so equal D values can
+    carry ids that are not ascending.  Both merge kernels break such ties by (list, position): every output slot is written once."""
+    rng = np.random.default_rng(k + G)
+    nq = 2
+    D_all = np.sort(np.round(np.abs(rng.standard_normal((G, nq, k))), 1).astype(np.float32), axis=2)
+    I_all = np.empty((G, nq, k), np.int64)
+    for g in range(G):
+        for q in range(nq):
+            I_all[g, q] = rng.permutation(k) + g * k          # ids in arbitrary order inside runs of equal D
+    D, I = harness.merge_di(sel, D_all, I_all, k, 1)
+    Dc = D_all.transpose(1, 0, 2).reshape(nq, -1)
+    Ic = I_all.transpose(1, 0, 2).reshape(nq, -1)
+    for q in range(nq):
+        order = np.argsort(Dc[q], kind="stable")[:k]           # stable: (list, position) decides ties
+        np.testing.assert_array_equal(I[q], Ic[q, order])
+        np.testing.assert_array_equal(D[q], Dc[q, order])
+
+
 def test_merge_refuses_more_lists_than_the_ranking_kernel_takes(sel):
     G, k = 65, 300                                     # 65 x 300 keys do not fit the in-CTA sort, and 65 lists exceed the ranking kernel
     D_all = np.zeros((G, 1, k), np.float32)
