@@ -92,8 +92,9 @@ int pq_index_set_profile(pq_index* idx, int on);
 /* Counters of the last search: [0]=queries served by the tensor-core tier, [1]=queries re-run by the
  * fp32 scan after a failed certificate, [2]=fp32-scan launches, [3]=tensor-core filter launches,
  * [4]=select/merge/rescore launches, [5]=total kernel launches, [6]=device microseconds (CUDA events),
- * [7]=microseconds inside the dominant kernel (only with pq_index_set_profile), [8]=second attempts at an epoch (queries
- * whose candidate slabs overflowed: rows in document order can bring a whole cluster above the threshold at once). */
+ * [7]=microseconds inside the dominant kernel (only with pq_index_set_profile), [8]=(query, epoch) pairs repaired after the
+ * last epoch (candidate slabs overflowed: rows in document order can bring a whole cluster above the threshold at once),
+ * [9]=threshold exchanges between row shards in which every shard's values had arrived in time. */
 int pq_index_last_stats(const pq_index* idx, int64_t* out, int n);
 
 /* Merge G per-shard result lists (each [nq,k], best-first, global ids) into one — the kernel run
@@ -158,6 +159,34 @@ int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* 
 int pq_plan_describe_large_k(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len);
 
 const char* pq_last_error(void);
+/* ---- corpus row-sharded over several GPUs: threshold exchange over peer memory ----------------------------------------
+ * north_star (4) shards the rows of IndexFlatIP (eval_retrieval.py:102-104) over the GPUs of a box.  Each shard searches its
+ * rows; to keep the per-query work from being repeated blindly on every shard, the shards tell each other after every epoch
+ * how good their k-th (and ceil(k/n)-th) best local score is, by plain stores into each other's HBM over NVLink, and each
+ * admits only what can still reach the global top-k.  A shard's result list then holds the local rows that can be in the
+ * global top-k (at most k, best first, padded with -1); pq_merge_shard_results of all lists is the exact global result.
+ *   pq_index_share_alloc    allocate this shard's mailbox (device memory of the index's GPU); returns its address
+ *   pq_index_share_connect  the n mailbox addresses as seen from THIS process/device, in shard order (own one included):
+ *                           peer-enabled pointers within one process (pq_enable_peer_access), CUDA IPC mappings across
+ *                           processes (pq_ipc_export / pq_ipc_open)
+ *   pq_index_share_begin    before every search: a sequence number, the same on every shard of that search
+ *   pq_index_share_close    back to independent shards
+ * The exchange needs no barrier and cannot deadlock: every value carries the sequence number of its search, readers wait a
+ * bounded time (PROQA_B200_SHARE_WAIT_US, default 200) and then use what has arrived. */
+int pq_index_share_alloc(pq_index* idx, int n_shards, int shard, int64_t max_queries_per_search, void** mailbox_dev_out, int64_t* bytes_out);
+int pq_index_share_connect(pq_index* idx, const void* const* mailboxes_dev);
+int pq_index_share_begin(pq_index* idx, uint32_t seq);
+int pq_index_share_close(pq_index* idx);
+/* The filter's error bound uses max |x|^2 and max |x - bf16(x)|^2 over the rows: shards that exchange thresholds must all use
+ * the maxima over the WHOLE corpus (all-reduce the two floats once after add()).  set folds by maximum. */
+int pq_index_get_bound_scalars(const pq_index* idx, float* out2);
+int pq_index_set_bound_scalars(pq_index* idx, float max_norm2, float max_resid2);
+/* CUDA IPC plumbing for the one-process-per-GPU layout (64-byte handles), and peer access for one process driving several GPUs. */
+int pq_ipc_export(const void* dev_ptr, void* handle_out64);
+int pq_ipc_open(const void* handle64, int device, void** dev_ptr_out);
+int pq_ipc_close(int device, void* dev_ptr);
+int pq_enable_peer_access(int device, int peer_device);
+
 /* "proqa_b200 <version> sm_100a" */
 const char* pq_version(void);
 

@@ -48,6 +48,16 @@ SIGNATURES = {
                                               _vp, _vp]),
     "pq_merge_shard_results_async": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp,
                                                     _vp, _vp, _vp]),
+    "pq_index_share_alloc": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(_vp), _i64p]),
+    "pq_index_share_connect": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "pq_index_share_begin": (ctypes.c_int, [_vp, ctypes.c_uint32]),
+    "pq_index_share_close": (ctypes.c_int, [_vp]),
+    "pq_index_get_bound_scalars": (ctypes.c_int, [_vp, _f32p]),
+    "pq_index_set_bound_scalars": (ctypes.c_int, [_vp, ctypes.c_float, ctypes.c_float]),
+    "pq_ipc_export": (ctypes.c_int, [_vp, _vp]),
+    "pq_ipc_open": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "pq_ipc_close": (ctypes.c_int, [ctypes.c_int, _vp]),
+    "pq_enable_peer_access": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "pq_kmeans_default_params": (None, [ctypes.POINTER(KMeansParams)]),
     "pq_kmeans_train": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.POINTER(KMeansParams), ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int64, _i64p]),
     "pq_rand_perm": (None, [ctypes.c_int64, ctypes.c_int64, _vp]),

@@ -3,6 +3,7 @@
 
 #include <stdint.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/proqa_b200.h"
@@ -36,7 +37,21 @@ constexpr long long kMmaMinPairs = 1LL << 24;  // ... unless the query side is l
 
 }  // namespace pq
 
+// Cross-shard threshold exchange (corpus row-sharded over several GPUs; pq_mma.cu: ShareParams): this shard's
+// mailbox in its own HBM and the device addresses of every shard's mailbox (peer access within a process, CUDA IPC across).
+struct pq_share_state {
+    int n = 0, rank = 0;
+    uint32_t seq = 0;            // search sequence number: every shard of a search passes the same one
+    int cap_q = 0;               // queries a mailbox slot holds
+    int wait_us = 200;           // longest wait for the peers' announcement of an epoch
+    bool connected = false;
+    pq::DevBuf mailbox;
+    uint64_t* peer[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 struct pq_index {
+    std::mutex mu;  // serialises the C-ABI calls on THIS index; different indexes (other GPUs, other threads) run concurrently
     int d = 128;
     int metric = 0;
     int tier = 0;
@@ -58,9 +73,9 @@ struct pq_index {
     pq::DevBuf rows_f32, rows_bf16, norms, scalars;
     CUtensorMap tmap_f32, tmap_bf16;
 
-    // large-k tier (off unless PROQA_B200_LARGEK=1): compact bf16 copy of every sample_step-th row (+ norms) the thresholds
+    // large-k tier (1024 < k; PROQA_B200_LARGEK=0 turns it off): compact bf16 copy of every sample_step-th row (+ norms) the thresholds
     // are estimated on; rebuilt lazily after add()/reset() (sample_rows < 0 = stale)
-    bool largek = false;
+    bool largek = true;
     pq::DevBuf sample_bf16, sample_norms;
     CUtensorMap tmap_sample;
     int64_t sample_rows = -1;
@@ -74,6 +89,7 @@ struct pq_index {
     pq::DevBuf ws_km[10];  // staged k-means (multi-GPU training): centroids, assignment, sort buffers
 
     int64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    pq_share_state share;
 
     // optional per-kernel timing of the dominant kernel (fp32 scan / tensor-core filter): event pairs on the stream
     bool profile = false;
@@ -117,13 +133,13 @@ struct pq_index {
         sample_bf16.release();
         sample_norms.release();
         sample_rows = -1;
+        share.mailbox.release();
+        share.connected = false;
     }
 };
 
-#include <mutex>
 namespace pq {
-// One lock for all device work of the process (C ABI entry points take it; the *_locked helpers expect it held).
-extern std::mutex g_device_mutex;
+// (the *_locked helpers expect the index's own lock, pq_index::mu, held by the C-ABI entry point)
 int index_init_device(pq_index* ix);
 int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device);
 int index_reset_locked(pq_index* ix);

@@ -40,8 +40,9 @@ int cuda_fail(cudaError_t e, const char* file, int line) {
 
 static int cuda_ok_or_fail(cudaError_t e) { return e == cudaSuccess ? PQ_OK : cuda_fail(e, __FILE__, __LINE__); }
 
-// Device work is serialised process-wide (shared staging buffers, one stream per index).
-std::mutex g_device_mutex;
+// Locking: every index has its own lock (pq_index::mu) held across a C-ABI call, so one host thread per GPU can drive the
+// shards of a row-sharded corpus concurrently.  Process-wide state is small and has its own locks: the pinned staging
+// buffers (one pair per device), the per-device table of validated ordinals, the shared-memory attribute cache (pq_mma.cu).
 
 // ------------------------------------------------------------------------------------------------
 // tensor maps
@@ -104,7 +105,9 @@ void DevBuf::release() {
 
 static int pick_device(int requested, int* out) {
     // cudaGetDeviceProperties costs milliseconds: validate each ordinal once per process
+    static std::mutex mu;
     static int validated[64];
+    std::lock_guard<std::mutex> lock(mu);
     if (requested >= 0 && requested < 64 && validated[requested]) {
         *out = requested;
         return PQ_OK;
@@ -224,7 +227,9 @@ struct StagingBuffers {
         return true;
     }
 };
-static StagingBuffers g_staging;  // guarded by g_device_mutex
+// One pair per device (the events belong to a device); held for the length of one staged add() through its lock.
+static StagingBuffers g_staging_of[64];
+static std::mutex g_staging_mu[64];
 
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     const int n_threads = 4;
@@ -242,7 +247,11 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
 static int staged_add_rows(pq_index* ix, float* dst_dev, const float* x_host, int64_t n, int64_t first_row) {
     uint32_t* sc = (uint32_t*)ix->scalars.p;
     const int64_t rows_per_chunk = (int64_t)(StagingBuffers::kBytes / (kDim * 4));
-    if (n * kDim * 4 < (int64_t)(8u << 20) || !g_staging.init()) {  // small (k-means centroids, tests): one plain copy
+    std::unique_lock<std::mutex> staging_lock(g_staging_mu[ix->device & 63], std::defer_lock);
+    StagingBuffers& g_staging = g_staging_of[ix->device & 63];
+    const bool small = n * kDim * 4 < (int64_t)(8u << 20);
+    if (!small) staging_lock.lock();
+    if (small || !g_staging.init()) {  // small (k-means centroids, tests): one plain copy
         PQ_CUDA(cudaMemcpyAsync(dst_dev, x_host, (size_t)n * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
         return cuda_ok_or_fail(prep_rows_launch(dst_dev, n, (uint16_t*)ix->rows_bf16.p + (size_t)first_row * kDim, (float*)ix->norms.p + first_row,
                                                 sc + 0, sc + 1, nullptr, nullptr, sc + 2, ix->stream));
@@ -258,6 +267,7 @@ static int staged_add_rows(pq_index* ix, float* dst_dev, const float* x_host, in
         PQ_CUDA(prep_rows_launch(d, rows, (uint16_t*)ix->rows_bf16.p + (size_t)(first_row + a) * kDim, (float*)ix->norms.p + first_row + a, sc + 0,
                                  sc + 1, nullptr, nullptr, sc + 2, ix->stream));
     }
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));  // the pinned buffers are free again before the lock is
     return PQ_OK;
 }
 
@@ -276,7 +286,7 @@ __global__ void pq_half_to_float_kernel(const __half* __restrict__ in, float* __
     }
 }
 
-// Caller holds g_device_mutex.  x_host: n rows of 128 IEEE half values.
+// Caller holds the index's lock.  x_host: n rows of 128 IEEE half values.
 int index_add_f16_locked(pq_index* ix, int64_t n, const void* x_host) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
     if (n < 0 || (n > 0 && !x_host)) return set_error(PQ_ERR_INVALID, "add_f16: bad arguments");
@@ -287,6 +297,8 @@ int index_add_f16_locked(pq_index* ix, int64_t n, const void* x_host) {
     PQ_CUDA(cudaSetDevice(ix->device));
     rc = index_grow(ix, ix->ntotal + n);
     if (rc) return rc;
+    std::lock_guard<std::mutex> staging_lock(g_staging_mu[ix->device & 63]);  // (released after the final stream synchronise below)
+    StagingBuffers& g_staging = g_staging_of[ix->device & 63];
     if (!g_staging.init()) return set_error(PQ_ERR_OOM, "add_f16: pinned staging buffers unavailable");
     DevBuf tmp[2];
     const int64_t rows_per_chunk = (int64_t)(StagingBuffers::kBytes / (kDim * 2));
@@ -332,7 +344,7 @@ int index_add_f16_locked(pq_index* ix, int64_t n, const void* x_host) {
     return index_refresh_maps(ix);
 }
 
-// Caller holds g_device_mutex.
+// Caller holds the index's lock.
 int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
     if (n < 0 || (n > 0 && !x)) return set_error(PQ_ERR_INVALID, "add: bad arguments (n=%lld, x=%p)", (long long)n, (const void*)x);
@@ -440,8 +452,8 @@ __global__ void pq_scatter_results_kernel(const float* __restrict__ Ds, const lo
     }
 }
 
-// 1024 < k: the tensor tier needs the sample-threshold path, which is opt-in (PROQA_B200_LARGEK=1) until it has been
-// validated on hardware; otherwise such requests are answered by the fp32 scan.
+// 1024 < k: the tensor tier takes the sample-threshold path (pq_mma_largek.inl) when the corpus is large enough for a
+// sample to mean something; PROQA_B200_LARGEK=0 sends such requests to the fp32 scan instead.
 static bool tier_uses_largek(const pq_index* ix, int64_t nq, int64_t k) {
     if (!ix->largek || ix->has_nonfinite || ix->tier == PQ_TIER_FP32) return false;
     return k > kMmaMaxK && k <= PQ_MAX_K && nq >= kMmaMinQueries && plan_large_k_applies(ix->ntotal, (int)k);
@@ -555,7 +567,7 @@ int pq_index_create(int d, int metric, int device, pq_index** out) {
         else if (!strcmp(t, "bf16")) ix->tier = PQ_TIER_BF16;
     }
     const char* lk = getenv("PROQA_B200_LARGEK");
-    ix->largek = lk && !strcmp(lk, "1");
+    ix->largek = !(lk && !strcmp(lk, "0"));  // tensor tier for 1024 < k unless switched off
     *out = ix;  // CUDA is touched lazily (first add/search): the reference forks after importing faiss
     return PQ_OK;
 }
@@ -563,7 +575,7 @@ int pq_index_create(int d, int metric, int device, pq_index** out) {
 void pq_index_free(pq_index* ix) {
     if (!ix) return;
     if (ix->device_ready) {
-        std::lock_guard<std::mutex> lock(g_device_mutex);
+        std::lock_guard<std::mutex> lock(ix->mu);
         cudaSetDevice(ix->device);
         cudaStreamSynchronize(ix->stream);
         ix->release_all();
@@ -576,15 +588,18 @@ void pq_index_free(pq_index* ix) {
 }
 
 int pq_index_add(pq_index* ix, int64_t n, const float* x_host) {
-    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lock(ix->mu);
     return index_add_locked(ix, n, x_host, false);
 }
 int pq_index_add_device(pq_index* ix, int64_t n, const float* x_dev) {
-    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lock(ix->mu);
     return index_add_locked(ix, n, x_dev, true);
 }
 int pq_index_add_f16(pq_index* ix, int64_t n, const void* x_host_f16) {
-    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lock(ix->mu);
     return index_add_f16_locked(ix, n, x_host_f16);
 }
 
@@ -592,7 +607,7 @@ int pq_index_search(pq_index* ix, int64_t nq, const float* xq, int64_t k, float*
     int rc = check_search_args(ix, nq, xq, k, D, I);
     if (rc) return rc;
     if (nq == 0) return PQ_OK;
-    std::lock_guard<std::mutex> lock(g_device_mutex);
+    std::lock_guard<std::mutex> lock(ix->mu);
     rc = index_init_device(ix);
     if (rc) return rc;
     PQ_CUDA(cudaSetDevice(ix->device));
@@ -613,7 +628,7 @@ int pq_index_search_device(pq_index* ix, int64_t nq, const float* xq_dev, int64_
     int rc = check_search_args(ix, nq, xq_dev, k, D_dev, I_dev);
     if (rc) return rc;
     if (nq == 0) return PQ_OK;
-    std::lock_guard<std::mutex> lock(g_device_mutex);
+    std::lock_guard<std::mutex> lock(ix->mu);
     rc = index_init_device(ix);
     if (rc) return rc;
     PQ_CUDA(cudaSetDevice(ix->device));
@@ -625,7 +640,7 @@ int pq_index_search_device(pq_index* ix, int64_t nq, const float* xq_dev, int64_
 
 int pq_index_reset(pq_index* ix) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
-    std::lock_guard<std::mutex> lock(g_device_mutex);
+    std::lock_guard<std::mutex> lock(ix->mu);
     return pq::index_reset_locked(ix);
 }
 }  // extern "C"
@@ -663,7 +678,7 @@ int pq_index_set_tier(pq_index* ix, int tier) {
 }
 int pq_index_set_stream(pq_index* ix, void* cuda_stream, int is_external) {
     if (!ix) return set_error(PQ_ERR_INVALID, "null index");
-    std::lock_guard<std::mutex> lock(g_device_mutex);
+    std::lock_guard<std::mutex> lock(ix->mu);
     if (ix->device_ready) {
         PQ_CUDA(cudaSetDevice(ix->device));
         PQ_CUDA(cudaStreamSynchronize(ix->stream));
@@ -710,6 +725,120 @@ int pq_merge_shard_results(int device, int metric, int n_lists, int64_t nq, int6
 int pq_merge_shard_results_async(int device, int metric, int n_lists, int64_t nq, int64_t k, const float* D_lists, const int64_t* I_lists,
                                  float* D_out, int64_t* I_out, void* cuda_stream) {
     return merge_shard_results_impl(device, metric, n_lists, nq, k, D_lists, I_lists, D_out, I_out, (cudaStream_t)cuda_stream, false);
+}
+
+// ---- cross-shard threshold exchange (pq_mma.cu: ShareParams; proqa_b200/sharded.py sets it up) ---------------------------
+int pq_index_share_alloc(pq_index* ix, int n_ranks, int rank, int64_t cap_queries, void** mailbox_out, int64_t* bytes_out) {
+    if (!ix || n_ranks < 1 || n_ranks > 16 || rank < 0 || rank >= n_ranks || cap_queries < 1 || cap_queries > (1 << 18))
+        return set_error(PQ_ERR_INVALID, "share_alloc: bad arguments (n_ranks=%d, rank=%d, cap_queries=%lld)", n_ranks, rank, (long long)cap_queries);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    int rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    pq_share_state& ss = ix->share;
+    ss.connected = false;
+    const size_t bytes = ((size_t)n_ranks * (size_t)cap_queries * 2 + (size_t)n_ranks) * 8;
+    rc = ss.mailbox.ensure(bytes);
+    if (rc) return rc;
+    PQ_CUDA(cudaMemsetAsync(ss.mailbox.p, 0, bytes, ix->stream));   // tag 0 is never used by a search
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    ss.n = n_ranks;
+    ss.rank = rank;
+    ss.cap_q = (int)cap_queries;
+    ss.seq = 0;
+    const char* w = getenv("PROQA_B200_SHARE_WAIT_US");
+    if (w && *w) ss.wait_us = std::max(0, atoi(w));
+    if (mailbox_out) *mailbox_out = ss.mailbox.p;
+    if (bytes_out) *bytes_out = (int64_t)bytes;
+    return PQ_OK;
+}
+int pq_index_share_connect(pq_index* ix, const void* const* peer_mailboxes) {
+    if (!ix || !peer_mailboxes) return set_error(PQ_ERR_INVALID, "share_connect: bad arguments");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    pq_share_state& ss = ix->share;
+    if (ss.n < 1 || !ss.mailbox.p) return set_error(PQ_ERR_INVALID, "share_connect: call pq_index_share_alloc first");
+    for (int i = 0; i < ss.n; ++i) {
+        if (!peer_mailboxes[i]) return set_error(PQ_ERR_INVALID, "share_connect: mailbox %d is null", i);
+        ss.peer[i] = (uint64_t*)peer_mailboxes[i];
+    }
+    if (ss.peer[ss.rank] != (uint64_t*)ss.mailbox.p) return set_error(PQ_ERR_INVALID, "share_connect: entry %d must be this index's own mailbox", ss.rank);
+    ss.connected = true;
+    return PQ_OK;
+}
+int pq_index_share_begin(pq_index* ix, uint32_t seq) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    ix->share.seq = (seq % 0x0ffffffeu) + 1u;   // 28 bits, never 0
+    return PQ_OK;
+}
+int pq_index_share_close(pq_index* ix) {
+    if (!ix) return set_error(PQ_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    ix->share.connected = false;
+    ix->share.n = 0;
+    return PQ_OK;
+}
+int pq_index_get_bound_scalars(const pq_index* ix, float* out2) {
+    if (!ix || !out2) return set_error(PQ_ERR_INVALID, "get_bound_scalars: bad arguments");
+    out2[0] = ix->max_norm2;
+    out2[1] = ix->max_resid2;
+    return PQ_OK;
+}
+int pq_index_set_bound_scalars(pq_index* ix, float max_norm2, float max_resid2) {
+    if (!ix || !(max_norm2 >= 0.f) || !(max_resid2 >= 0.f)) return set_error(PQ_ERR_INVALID, "set_bound_scalars: bad arguments");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    int rc = index_init_device(ix);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(ix->device));
+    ix->max_norm2 = std::max(ix->max_norm2, max_norm2);
+    ix->max_resid2 = std::max(ix->max_resid2, max_resid2);
+    // the running maxima live on the device as well (later add() calls fold into them): non-negative floats order as uints
+    uint32_t* sc = (uint32_t*)ix->scalars.p;
+    PQ_CUDA(cudaMemcpyAsync(sc + 0, &ix->max_norm2, 4, cudaMemcpyHostToDevice, ix->stream));
+    PQ_CUDA(cudaMemcpyAsync(sc + 2, &ix->max_resid2, 4, cudaMemcpyHostToDevice, ix->stream));
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));
+    return PQ_OK;
+}
+int pq_ipc_export(const void* dev_ptr, void* handle_out64) {
+    if (!dev_ptr || !handle_out64) return set_error(PQ_ERR_INVALID, "ipc_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    PQ_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle_out64, &h, 64);
+    return PQ_OK;
+}
+int pq_ipc_open(const void* handle64, int device, void** dev_ptr_out) {
+    if (!handle64 || !dev_ptr_out) return set_error(PQ_ERR_INVALID, "ipc_open: bad arguments");
+    int dev = -1;
+    int rc = pick_device(device, &dev);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(dev));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PQ_CUDA(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PQ_OK;
+}
+int pq_ipc_close(int device, void* dev_ptr) {
+    int dev = -1;
+    int rc = pick_device(device, &dev);
+    if (rc) return rc;
+    PQ_CUDA(cudaSetDevice(dev));
+    PQ_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return PQ_OK;
+}
+int pq_enable_peer_access(int device, int peer_device) {
+    int dev = -1, peer = -1;
+    int rc = pick_device(device, &dev);
+    if (!rc) rc = pick_device(peer_device, &peer);
+    if (rc) return rc;
+    if (dev == peer) return PQ_OK;
+    int can = 0;
+    PQ_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer));
+    if (!can) return set_error(PQ_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", dev, peer);
+    PQ_CUDA(cudaSetDevice(dev));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, __FILE__, __LINE__);
+    cudaGetLastError();
+    return PQ_OK;
 }
 
 const char* pq_last_error(void) { return g_err; }

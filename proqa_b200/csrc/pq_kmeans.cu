@@ -486,7 +486,7 @@ void pq_rand_perm(int64_t n, int64_t seed, int32_t* out) {
 
 int pq_kmeans_set_centroids(pq_index* index, int64_t k, const float* centroids_host, int spherical) {
     if (!index || !centroids_host || k < 1) return pq::set_error(PQ_ERR_INVALID, "kmeans_set_centroids: bad argument");
-    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    std::lock_guard<std::mutex> lock(index->mu);
     return pq::kmeans_set_centroids_locked(index, k, centroids_host, spherical);
 }
 
@@ -494,14 +494,14 @@ int pq_kmeans_partial_device(pq_index* index, int64_t k, int64_t n_local, const 
                              double* objective_out) {
     if (!index || !sums_dev || !counts_dev || !objective_out || (n_local > 0 && !x_dev) || k < 1)
         return pq::set_error(PQ_ERR_INVALID, "kmeans_partial_device: bad argument");
-    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    std::lock_guard<std::mutex> lock(index->mu);
     return pq::kmeans_partial_locked(index, k, n_local, x_dev, sums_dev, (int*)counts_dev, objective_out);
 }
 
 int pq_kmeans_finish_device(pq_index* index, int64_t k, int64_t n_total, int spherical, const float* sums_dev, const int32_t* counts_dev,
                             float* centroids_out_host, int* nsplit_out) {
     if (!index || !sums_dev || !counts_dev || k < 1) return pq::set_error(PQ_ERR_INVALID, "kmeans_finish_device: bad argument");
-    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    std::lock_guard<std::mutex> lock(index->mu);
     return pq::kmeans_finish_locked(index, k, n_total, spherical, sums_dev, (const int*)counts_dev, centroids_out_host, nsplit_out);
 }
 
@@ -519,7 +519,7 @@ void pq_kmeans_default_params(pq_kmeans_params* p) {
 int pq_kmeans_train(pq_index* index, int64_t k, const pq_kmeans_params* params, int64_t n, const float* x_host, float* centroids_out, float* obj_out,
                     int64_t obj_cap, int64_t* n_obj) {
     if (!index || !params || !x_host || !centroids_out) return pq::set_error(PQ_ERR_INVALID, "kmeans_train: null argument");
-    std::lock_guard<std::mutex> lock(pq::g_device_mutex);
+    std::lock_guard<std::mutex> lock(index->mu);
     return pq::kmeans_train_locked(index, k, *params, n, x_host, centroids_out, obj_out, obj_cap, n_obj);
 }
 

@@ -35,6 +35,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 namespace pq {
 
@@ -79,10 +80,10 @@ struct MmaParams {
     int cap;
     int n_sub;               // candidate slabs per query = max(s1, s0) * 2 (one per epilogue warp set)
     int k1_adapt;
-    // second attempt at an epoch ("redo"): only queries whose slabs overflowed the first time (redo[q] != 0) take part,
-    // with the tighter threshold the first attempt produced; the kernel returns at once when no query asked for it
+    // second attempt at an epoch ("repair", launched after the last epoch and only when some slab overflowed): only the
+    // queries whose slabs overflowed in that epoch (redo[q] & redo_bit) take part, with their final thresholds
     const uint32_t* redo;      // [nq_pad] or null
-    const uint32_t* any_redo;  // device counter, read at kernel start when redo != null
+    uint32_t redo_bit;
 };
 
 // D[tmem] (+)= A[tmem] * B[smem desc]^T: the stationary operand (queries) is read from tensor memory, so shared
@@ -232,7 +233,6 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
     const int mt0 = group * p.base + min(group, p.rem);
     const int m = min(M_TILES, p.base + (group < p.rem ? 1 : 0));
 
-    if (p.redo != nullptr && *p.any_redo == 0) return;  // redo launch with nothing to redo (block-uniform, before any setup)
     // Row tiles are dealt to the slices round-robin (slice s takes tiles s, s + n_slices, ...): a run of consecutive rows that
     // all beat the threshold — a topic cluster in a corpus stored in document order — spreads over every slab of the query
     // instead of flooding one.
@@ -351,7 +351,7 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         const int sub = slice * 2 + set;
         for (int mi = 0; mi < m; ++mi) {
             const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
-            s_thr[mi * 256 + tid_e] = (p.redo == nullptr || p.redo[q] != 0u) ? p.thr[q] : INFINITY;
+            s_thr[mi * 256 + tid_e] = (p.redo == nullptr || (p.redo[q] & p.redo_bit) != 0u) ? p.thr[q] : INFINITY;
             s_2e[mi * 256 + tid_e] = p.two_e[q];
             s_cnt[mi * 256 + tid_e] = 0;
         }
@@ -426,9 +426,10 @@ struct QState {
     float* two_e;        // [nq_pad]
     float* dropmax;      // [nq_pad]
     uint32_t* overflow;  // [nq_pad]
-    uint64_t* carry;     // [nq_pad][kp]
-    uint32_t* redo;      // [nq_pad] this epoch's slabs overflowed: run the epoch again for this query with the new threshold
-    uint32_t* any_redo;  // [1] number of queries with redo set
+    uint64_t* carry;     // [nq_pad][kp] candidates kept between epochs: a compacted prefix, zero keys after it
+    uint32_t* redo;      // [nq_pad] bit e set: the slabs of epoch e overflowed for this query (repaired after the last epoch)
+    uint32_t* counters;  // [0] OR of all redo masks, [1] (query, epoch) overflows, [2] failed queries, [3] threshold exchanges
+                         //     in which every peer shard's values had arrived
 };
 
 // Error bound of the bf16 filter, per query:
@@ -455,23 +456,114 @@ __global__ void pq_mma_init_state_kernel(QState st, const float* __restrict__ q_
     st.thr[q] = live ? PQ_THR_FLOOR : INFINITY;
     st.dropmax[q] = -INFINITY;
     st.overflow[q] = (live && isfinite(e2)) ? 0u : (q < nq ? 1u : 0u);
+    st.redo[q] = 0u;
+}
+
+// Cross-shard threshold exchange over peer memory (NVLink): corpus row-sharded over n GPUs (north_star (4)).  After every
+// epoch each shard writes, for every query, two bf16-domain scores into the mailbox of every shard:
+//     a = its k-th best local score         (k local rows score at least a)
+//     b = its ceil(k/n)-th best local score (that many local rows score at least b)
+// The k-th best score over ALL rows is at least max over shards of a, and at least min over shards of b (n x ceil(k/n) >= k rows
+// reach it) — on exchangeable rows the latter is the k-th best of n times as many rows as one shard has seen.  Every word
+// carries the tag of the search it belongs to, so a reader uses only values of its own search; values of any epoch of that
+// search are valid lower bounds, hence no barrier: the fold kernel waits a bounded time for the peers' epoch headers and
+// then takes what is there.  Results never depend on what arrives — only how much the filter admits.
+constexpr int kShareMaxPeers = 16;
+struct ShareParams {
+    int n, rank;       // row shards (0 or 1: exchange off), this shard
+    int kr;            // ceil(k / n)
+    uint32_t tag;      // (search sequence << 4) | query batch
+    int cap_q;         // queries per mailbox slot
+    int wait_ns;       // longest wait for the peers' headers
+    uint64_t* peer[kShareMaxPeers];   // peer[p]: shard p's mailbox — [n][cap_q][2] value words, then [n] header words
+};
+__device__ __forceinline__ uint64_t share_word(uint32_t tag, float v) { return ((uint64_t)tag << 32) | (uint64_t)__float_as_uint(v); }
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void share_publish(const ShareParams& sh, int q, float a, float b, int lane) {
+    if (lane < sh.n) {
+        uint64_t* dst = sh.peer[lane] + ((size_t)sh.rank * sh.cap_q + q) * 2;
+        dst[0] = share_word(sh.tag, a);
+        dst[1] = share_word(sh.tag, b);
+    }
+}
+
+// Announces this shard's values of `epoch` (the select kernel that wrote them precedes this launch on the stream), waits —
+// bounded — for the peers' announcements, then raises every query's threshold to what the shards know together.
+__global__ void __launch_bounds__(256) pq_share_fold_kernel(const ShareParams sh, QState st, int nq, int epoch) {
+    uint64_t* mine = sh.peer[sh.rank];
+    uint64_t* hdr = mine + (size_t)sh.n * sh.cap_q * 2;
+    const uint64_t want = ((uint64_t)sh.tag << 32) | (uint64_t)(uint32_t)(epoch + 1);
+    if (blockIdx.x == 0 && (int)threadIdx.x < sh.n) {
+        __threadfence_system();
+        st_volatile_u64(sh.peer[threadIdx.x] + (size_t)sh.n * sh.cap_q * 2 + sh.rank, want);
+    }
+    if (threadIdx.x == 0) {
+        const uint64_t t0 = global_timer_ns();
+        const uint32_t full = sh.n >= 32 ? 0xffffffffu : ((1u << sh.n) - 1u);
+        uint32_t fresh;
+        do {
+            fresh = 0u;
+            for (int g = 0; g < sh.n; ++g) {
+                const uint64_t v = ld_volatile_u64(hdr + g);
+                if ((uint32_t)(v >> 32) == sh.tag && (uint32_t)v >= (uint32_t)(epoch + 1)) fresh |= 1u << g;
+            }
+        } while (fresh != full && global_timer_ns() - t0 < (uint64_t)sh.wait_ns);
+        if (blockIdx.x == 0 && fresh == full) atomicAdd(st.counters + 3, 1u);
+    }
+    __syncthreads();
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        float amax = -INFINITY, bmin = INFINITY;
+        bool all = true;
+        for (int g = 0; g < sh.n; ++g) {
+            const uint64_t wa = ld_volatile_u64(mine + ((size_t)g * sh.cap_q + q) * 2);
+            const uint64_t wb = ld_volatile_u64(mine + ((size_t)g * sh.cap_q + q) * 2 + 1);
+            if ((uint32_t)(wa >> 32) == sh.tag && (uint32_t)(wb >> 32) == sh.tag) {
+                amax = fmaxf(amax, __uint_as_float((uint32_t)wa));
+                bmin = fminf(bmin, __uint_as_float((uint32_t)wb));
+            } else {
+                all = false;
+            }
+        }
+        const float best = all ? fmaxf(amax, bmin) : amax;
+        if (best > -INFINITY) st.thr[q] = fmaxf(st.thr[q], best - st.two_e[q]);
+    }
 }
 
 struct EpochSelParams {
     QState st;
     const uint64_t* cand_keys;
     const uint32_t* cand_cnt;
-    int n_sub, cap, kp, k, lmax;  // lmax: keys the shared pool holds (old carry + one chunk of candidates)
-    int is_redo;                  // second attempt at this epoch: only queries with st.redo set take part
-    int allow_redo;               // first attempt: a slab overflow asks for a second attempt instead of failing the query
-    long long row_begin;          // first row of the epoch (a redo drops the carry entries the first attempt took from it)
+    int n_sub, cap, kp, k, lmax;  // n_sub: slab stride per query; lmax: keys the CTA kernel's shared pool holds
+    int nq;
+    int base, rem, s1, s0;        // the filter's grid shape: a query of a group with s row slices has 2 s slabs, the rest is unwritten
+    int is_redo;                  // repair of this epoch: only queries with (st.redo & epoch_bit) take part
+    int allow_redo;               // first attempt: a slab overflow asks for a repair instead of failing the query
+    uint32_t epoch_bit;
+    long long row_begin, row_end; // rows of the epoch (a repair replaces the carry entries the first attempt took from them)
+    ShareParams share;
 };
 
-// One CTA per query: carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
+// slabs the filter kernel wrote for query q
+__device__ __forceinline__ int sel_slabs_of_query(const EpochSelParams& p, int q) {
+    const int mt = q / kPlanQueryTile;
+    return 2 * (mt < p.rem * (p.base + 1) ? p.s1 : p.s0);
+}
+
+// One CTA per query (any K'): carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
 // Slab counts are staged and prefix-summed in shared memory, candidates gathered coalesced (one warp per slab) into a
 // pool next to the old carry; when the pool exceeds K' an MSB-first radix select over the 64-bit keys (8-bit digits, bytes
 // common to all keys skipped) finds the K'-th largest key and the survivors are compacted — no sort of the pool.  Only the
-// K' survivors are sorted at the end (the next epoch and the rescoring kernel read the k-th entry).
+// K' survivors are sorted at the end (the threshold is read off the k-th entry).
 __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* pool, int n, int want, int* hist, uint64_t* s_u64, int* s_int) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // bytes on which all keys agree need no pass
@@ -553,33 +645,61 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
     __shared__ uint64_t s_u64[16];
     __shared__ int s_int[2];
     __shared__ int s_total, s_ovf, s_nc, s_slot;
+    __shared__ int s_wbase[8];
     __shared__ unsigned long long s_dropkey;
     const int q = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (p.is_redo && p.st.redo[q] == 0u) return;  // block-uniform: this query's first attempt was fine
+    const uint32_t redo_mask = p.st.redo[q];
+    if (p.is_redo && (redo_mask & p.epoch_bit) == 0u) return;  // block-uniform: this query's first attempt was fine
+    const int n_sub = sel_slabs_of_query(p, q);
     uint64_t* carry = p.st.carry + (size_t)q * p.kp;
     const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
     const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
     if (t == 0) {
         s_ovf = 0;
         s_nc = 0;
+        s_slot = 0;
         s_dropkey = 0ull;
     }
     __syncthreads();
-    for (int s = t; s < p.n_sub; s += 256) {
+    for (int s = t; s < n_sub; s += 256) {
         const uint32_t c = cnts[s];
         if (c > (uint32_t)p.cap) s_ovf = 1;
         s_cnt[s] = (int)min(c, (uint32_t)p.cap);
     }
-    for (int i = t; i < p.kp; i += 256) {  // the carry is sorted: its non-empty entries form a prefix
-        const uint64_t k = carry[i];
-        pool[i] = k;
-        if (k != 0ull) atomicMax(&s_nc, i + 1);
+    if (!p.is_redo) {
+        for (int i = t; i < p.kp; i += 256) {  // the carry's non-empty entries form a prefix
+            const uint64_t k = carry[i];
+            pool[i] = k;
+            if (k != 0ull) atomicMax(&s_nc, i + 1);
+        }
+    } else {
+        // repair: the entries the first attempt took from this epoch's rows are regenerated below — all of them, against the
+        // final threshold; ordered compaction of the others, 256 entries at a time
+        for (int i0 = 0; i0 < p.kp; i0 += 256) {
+            const int i = i0 + t;
+            const uint64_t key = i < p.kp ? carry[i] : 0ull;
+            const long long row = (long long)key_row(key);
+            const bool keep = key != 0ull && !(row >= p.row_begin && row < p.row_end);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_wbase[warp] = __popc(m);
+            __syncthreads();
+            int before = s_nc;
+            for (int w = 0; w < warp; ++w) before += s_wbase[w];
+            if (keep) pool[before + __popc(m & ((1u << lane) - 1u))] = key;
+            __syncthreads();
+            if (t == 0) {
+                int tot = 0;
+                for (int w = 0; w < 8; ++w) tot += s_wbase[w];
+                s_nc += tot;
+            }
+            __syncthreads();
+        }
     }
     __syncthreads();
     if (warp == 0) {  // exclusive prefix sum of the slab counts: lane owns a contiguous run, warp scan across lanes
-        const int per = (p.n_sub + 31) / 32;
-        const int a = lane * per, b = min(p.n_sub, a + per);
+        const int per = (n_sub + 31) / 32;
+        const int a = lane * per, b = min(n_sub, a + per);
         int run = 0;
         for (int s = a; s < b; ++s) run += s_cnt[s];
         int incl = run;
@@ -600,7 +720,7 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
     int nc = s_nc;
     for (int c0 = 0; c0 < total;) {  // almost always a single chunk
         const int chunk = min(total - c0, p.lmax - nc);
-        for (int s = warp; s < p.n_sub; s += 8) {
+        for (int s = warp; s < n_sub; s += 8) {
             const int base = s_off[s] - c0, n = s_cnt[s];
             if (base + n <= 0 || base >= chunk) continue;
             const uint64_t* src = keys + (size_t)s * p.cap;
@@ -615,13 +735,14 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
             const uint64_t pivot = block_radix_select(pool, n, p.kp, hist, s_u64, s_int);
             if (t == 0) s_slot = 0;
             __syncthreads();
-            // truncation bookkeeping: when this epoch is going to be run again, its own rows are regenerated, not lost
+            // truncation bookkeeping: when this epoch is going to be repaired, its own rows are regenerated, not lost
             const bool redo_coming = s_ovf && p.allow_redo;
             uint64_t dropped = 0ull;
             for (int i = t; i < n; i += 256) {
                 const uint64_t k = pool[i];
+                const long long row = (long long)key_row(k);
                 if (k >= pivot) out[atomicAdd(&s_slot, 1)] = k;
-                else if (!redo_coming || (long long)key_row(k) < p.row_begin) dropped = max(dropped, k);
+                else if (!redo_coming || !(row >= p.row_begin && row < p.row_end)) dropped = max(dropped, k);
             }
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) dropped = max(dropped, __shfl_xor_sync(0xffffffffu, dropped, s));
@@ -639,51 +760,237 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
     for (int i = nc + t; i < p.kp; i += 256) pool[i] = 0ull;
     __syncthreads();
     block_sort_desc<256>(pool, p.kp);
-    const bool ask_redo = s_ovf && p.allow_redo;
     if (t == 0) {
         // the k-th best of what fitted is the score of a real row: a valid (and usually much tighter) threshold either way
         const uint64_t kth = pool[p.k - 1];
         if (kth != 0ull) p.st.thr[q] = fmaxf(p.st.thr[q], key_score(kth) - p.st.two_e[q]);
         if (s_dropkey != 0ull) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], key_score((uint64_t)s_dropkey));
-        if (ask_redo) {
-            p.st.redo[q] = 1u;
-            atomicAdd(p.st.any_redo, 1u);
-            atomicAdd(p.st.any_redo + 1, 1u);  // running total of second attempts, reported in the search statistics
+        if (s_ovf && p.allow_redo) {
+            p.st.redo[q] = redo_mask | p.epoch_bit;
+            atomicOr(p.st.counters, p.epoch_bit);
+            atomicAdd(p.st.counters + 1, 1u);  // running total of repairs, reported in the search statistics
         } else if (s_ovf) {
             p.st.overflow[q] = 1u;
         }
     }
-    if (ask_redo) {
-        // Some candidates of this epoch were lost.  Keep only what earlier epochs contributed (rows below row_begin) and
-        // let the second attempt regenerate this epoch's candidates — all of them, now against the tighter threshold.
-        // (Entries of earlier epochs that fell out of the top-K' above did so against real rows: they stay dropped and were
-        // accounted in dropmax like any other truncation.)
-        __syncthreads();
-        if (t == 0) s_slot = 0;
-        __syncthreads();
-        for (int i0 = 0; i0 < p.kp; i0 += 256) {   // ordered compaction, 256 entries at a time
-            const int i = i0 + t;
-            const uint64_t key = i < p.kp ? pool[i] : 0ull;
-            const bool keep = key != 0ull && (long long)key_row(key) < p.row_begin;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            __shared__ int s_wbase[8];
-            if (lane == 0) s_wbase[warp] = __popc(m);
-            __syncthreads();
-            int before = s_slot;
-            for (int w = 0; w < warp; ++w) before += s_wbase[w];
-            if (keep) out[before + __popc(m & ((1u << lane) - 1u))] = key;
-            __syncthreads();
-            if (t == 0) {
-                int tot = 0;
-                for (int w = 0; w < 8; ++w) tot += s_wbase[w];
-                s_slot += tot;
-            }
-            __syncthreads();
+    for (int i = t; i < p.kp; i += 256) carry[i] = pool[i];
+    if (p.share.n > 1 && !p.is_redo && warp == 0) {
+        const uint64_t ka = pool[p.k - 1], kb = pool[p.share.kr - 1];
+        share_publish(p.share, q, ka != 0ull ? key_score(ka) : -INFINITY, kb != 0ull ? key_score(kb) : -INFINITY, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K' <= 256 (k <= 102: every BASELINE search config): one WARP per query, eight queries per CTA, no block barrier.
+// The warp keeps a pool of up to kSelWarpPool keys in its own shared memory: the carry, then the query's slabs, 32 slabs
+// at a time (lane = slab: counts prefix-summed with shuffles, entries copied lane by lane).  Reducing the pool means
+//   A_k = k-th largest key (warp radix select, 8-bit digits, histogram in the warp's shared memory, bytes all keys share
+//         skipped, finished early when the digit bucket is taken whole)            -> threshold = A_k - 2E
+//   keep the keys whose score reaches the new threshold (nothing below it can be in the final top-k): usually ~1.5 k keys;
+//   only if more than K' reach it is the exact top-K' taken and the best dropped score remembered for the certificate.
+// The carry is left unsorted (a compacted prefix): nothing downstream needs its order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelWarpPool = 1024;
+constexpr int kSelWarps = 8;
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// want-th largest of the n keys in pool (1 <= want <= n); hist: 256 ints private to the warp.  All lanes return it.
+__device__ __forceinline__ uint64_t warp_radix_select(const uint64_t* pool, int n, int want, int* hist, int lane) {
+    uint64_t a = ~0ull, o = 0ull;
+    for (int i = lane; i < n; i += 32) {
+        const uint64_t k = pool[i];
+        a &= k;
+        o |= k;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        a &= __shfl_xor_sync(0xffffffffu, a, s);
+        o |= __shfl_xor_sync(0xffffffffu, o, s);
+    }
+    const uint64_t differ = a ^ o;
+    uint64_t prefix = a & ~differ, mask = ~differ;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (((differ >> shift) & 0xffull) == 0ull) continue;  // warp-uniform
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const uint64_t k = pool[i];
+            if (((k ^ prefix) & mask) == 0ull) atomicAdd(&hist[(int)((k >> shift) & 0xffull)], 1);
         }
-        const int kept = s_slot;
-        for (int i = t; i < p.kp; i += 256) carry[i] = i < kept ? out[i] : 0ull;
-    } else {
-        for (int i = t; i < p.kp; i += 256) carry[i] = pool[i];
+        __syncwarp();
+        int loc = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) loc += hist[lane * 8 + b];
+        int suf = loc;  // suffix sum over lanes (lane 31 owns the highest digits)
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, suf, s);
+            if (lane + s < 32) suf += v;
+        }
+        const unsigned ok = __ballot_sync(0xffffffffu, suf >= want);
+        const int L = 31 - __clz((int)ok);
+        int d = 0, rest = 0, bucket = 0;
+        if (lane == L) {
+            int above = suf - loc;
+            d = lane * 8 + 7;
+            for (; d > lane * 8; --d) {
+                if (above + hist[d] >= want) break;
+                above += hist[d];
+            }
+            rest = want - above;
+            bucket = hist[d];
+        }
+        d = __shfl_sync(0xffffffffu, d, L);
+        rest = __shfl_sync(0xffffffffu, rest, L);
+        bucket = __shfl_sync(0xffffffffu, bucket, L);
+        prefix = (prefix & ~(0xffull << shift)) | ((uint64_t)d << shift);
+        mask |= 0xffull << shift;
+        want = rest;
+        __syncwarp();
+        if (bucket == want) {  // the whole bucket is taken: the answer is its smallest key
+            uint64_t m = ~0ull;
+            for (int i = lane; i < n; i += 32) {
+                const uint64_t k = pool[i];
+                if (((k ^ prefix) & mask) == 0ull) m = min(m, k);
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, s));
+            return m;
+        }
+    }
+    return prefix;  // every byte decided: the key itself
+}
+
+struct WarpSelState {
+    float thr, two_e, a_score;   // a_score: best k-th-largest score seen (or -inf)
+    uint64_t dropkey;
+    bool redo_coming;
+};
+
+// pool[0, n) -> pool[0, m): what can still matter (m <= kp); returns m.
+__device__ __forceinline__ int warp_sel_reduce(const EpochSelParams& p, uint64_t* pool, int n, WarpSelState& w, int* hist, int lane) {
+    if (n >= p.k) {
+        const float ak = key_score(warp_radix_select(pool, n, p.k, hist, lane));
+        w.a_score = fmaxf(w.a_score, ak);
+        w.thr = fmaxf(w.thr, ak - w.two_e);
+    }
+    int reach = 0;
+    for (int i = lane; i < n; i += 32) reach += key_score(pool[i]) >= w.thr ? 1 : 0;
+    reach = warp_sum(reach);
+    uint64_t pivot = 0ull;
+    if (reach > p.kp) pivot = warp_radix_select(pool, n, p.kp, hist, lane);  // the kp best keys all reach the threshold
+    int m = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {  // ordered compaction: a chunk is read by the whole warp before it writes at or below it
+        const int i = i0 + lane;
+        const uint64_t key = i < n ? pool[i] : 0ull;
+        const bool reaches = i < n && key_score(key) >= w.thr;
+        const bool keep = reaches && key >= pivot;
+        if (reaches && !keep) {
+            const long long row = (long long)key_row(key);
+            if (!w.redo_coming || !(row >= p.row_begin && row < p.row_end)) w.dropkey = max(w.dropkey, key);
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) pool[m + __popc(km & ((1u << lane) - 1u))] = key;
+        m += __popc(km);
+        __syncwarp();
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(const EpochSelParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * kSelWarps + warp;
+    if (q >= p.nq) return;  // (whole warp; this kernel has no block-wide barrier)
+    uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * kSelWarpPool;
+    int* hist = reinterpret_cast<int*>(reinterpret_cast<uint64_t*>(smem_raw) + (size_t)kSelWarps * kSelWarpPool) + warp * 256;
+    const uint32_t redo_mask = p.st.redo[q];
+    if (p.is_redo && (redo_mask & p.epoch_bit) == 0u) return;
+    const int n_sub = sel_slabs_of_query(p, q);
+    uint64_t* carry = p.st.carry + (size_t)q * p.kp;
+    const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
+    const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
+
+    bool ovf = false;
+    for (int s = lane; s < n_sub; s += 32) ovf |= cnts[s] > (uint32_t)p.cap;
+    ovf = __any_sync(0xffffffffu, ovf);
+
+    WarpSelState w;
+    w.thr = p.st.thr[q];
+    w.two_e = p.st.two_e[q];
+    w.a_score = -INFINITY;
+    w.dropkey = 0ull;
+    w.redo_coming = ovf && p.allow_redo;
+
+    // carry -> pool (a repair drops what the first attempt took from this epoch's rows: regenerated below)
+    int fill = 0;
+    for (int i0 = 0; i0 < p.kp; i0 += 32) {
+        const uint64_t key = carry[i0 + lane];
+        const long long row = (long long)key_row(key);
+        const bool keep = key != 0ull && !(p.is_redo && row >= p.row_begin && row < p.row_end);
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) pool[fill + __popc(km & ((1u << lane) - 1u))] = key;
+        fill += __popc(km);
+    }
+    __syncwarp();
+
+    for (int s0 = 0; s0 < n_sub; s0 += 32) {
+        const int s = s0 + lane;
+        const int c = s < n_sub ? (int)min(cnts[s], (uint32_t)p.cap) : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        if (fill + total > kSelWarpPool && fill > p.kp) fill = warp_sel_reduce(p, pool, fill, w, hist, lane);
+        if (fill + total <= kSelWarpPool) {
+            const uint64_t* src = keys + (size_t)s * p.cap;
+            uint64_t* dst = pool + fill + incl - c;
+            for (int i = 0; i < c; ++i) dst[i] = src[i];
+            fill += total;
+            __syncwarp();
+        } else {  // 32 slabs hold more than the pool has room for (rows in document order): slab by slab, warp-wide copies
+            for (int j = 0; j < 32; ++j) {
+                const int cj = __shfl_sync(0xffffffffu, c, j);
+                const uint64_t* src = keys + (size_t)(s0 + j) * p.cap;
+                for (int done = 0; done < cj;) {
+                    if (fill == kSelWarpPool) fill = warp_sel_reduce(p, pool, fill, w, hist, lane);
+                    const int take = min(cj - done, kSelWarpPool - fill);
+                    for (int i = lane; i < take; i += 32) pool[fill + i] = src[done + i];
+                    fill += take;
+                    done += take;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    const int m = warp_sel_reduce(p, pool, fill, w, hist, lane);
+    for (int i = lane; i < p.kp; i += 32) carry[i] = i < m ? pool[i] : 0ull;
+    if (lane == 0) {
+        p.st.thr[q] = w.thr;
+        if (w.dropkey != 0ull) p.st.dropmax[q] = fmaxf(p.st.dropmax[q], key_score(w.dropkey));
+        if (ovf && p.allow_redo) {
+            p.st.redo[q] = redo_mask | p.epoch_bit;
+            atomicOr(p.st.counters, p.epoch_bit);
+            atomicAdd(p.st.counters + 1, 1u);
+        } else if (ovf) {
+            p.st.overflow[q] = 1u;
+        }
+    }
+    if (p.share.n > 1 && !p.is_redo) {
+        float b = -INFINITY;
+        if (m >= p.share.kr) b = key_score(warp_radix_select(pool, m, p.share.kr, hist, lane));
+        share_publish(p.share, q, w.a_score, b, lane);
     }
 }
 
@@ -694,7 +1001,7 @@ struct RescoreParams {
     const float* row_norms;
     const float* q_norms;
     const uint8_t* q_bad;
-    int kp, k, metric, work;
+    int kp, k, metric, work, nq;
     long long id_base;
     float* D;
     long long* I;
@@ -702,7 +1009,30 @@ struct RescoreParams {
     uint32_t* fail_count;
 };
 
-// One CTA per query: exact fp32 scores for the carry list, final order, certificate.
+// Exactness certificate: the carry was only ever truncated below the final admission threshold.
+__device__ __forceinline__ bool rescore_certificate_fails(const RescoreParams& p, int q) {
+    bool fail = p.q_bad[q] != 0 || p.st.overflow[q] != 0;
+    const float two_e = p.st.two_e[q];
+    const float dropmax = p.st.dropmax[q];
+    if (dropmax > -INFINITY && two_e > 0.f && dropmax >= p.st.thr[q]) fail = true;
+    return fail;
+}
+__device__ __forceinline__ void rescore_emit(const RescoreParams& p, int q, int i, uint64_t key) {
+    float d;
+    long long id;
+    if (key == 0ull) {
+        id = -1;
+        d = (p.metric == kMetricL2) ? FLT_MAX : -FLT_MAX;
+    } else {
+        id = (long long)key_row(key) + p.id_base;
+        const float s = key_score(key);
+        d = (p.metric == kMetricL2) ? fmaxf(0.f, p.q_norms[q] - s) : s;
+    }
+    p.D[(size_t)q * p.k + i] = d;
+    p.I[(size_t)q * p.k + i] = id;
+}
+
+// One CTA per query (any K'): exact fp32 scores for the carry list, final order, certificate.
 __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw);
@@ -712,9 +1042,9 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) 
     const uint64_t* carry = p.st.carry + (size_t)q * p.kp;
     if (t < kDim) s_q[t] = p.queries[(size_t)q * kDim + t];
     __syncthreads();
-    // a carry entry whose bf16 score is more than 2E below the k-th best bf16 score cannot be in the exact top-k: skip it
-    const uint64_t kth_key = carry[p.k - 1];
-    const float bar = kth_key != 0ull ? key_score(kth_key) - p.st.two_e[q] : -INFINITY;
+    // a carry entry whose bf16 score is below the final admission threshold (the best known k-th best bf16 score - 2E)
+    // cannot be in the exact top-k: skip it
+    const float bar = p.st.thr[q];
     for (int i = t; i < p.work; i += 256) {
         uint64_t out = 0ull;
         if (i < p.kp) {
@@ -746,34 +1076,85 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) 
     }
     __syncthreads();
     block_sort_desc<256>(work, p.work);
-    for (int i = t; i < p.k; i += 256) {
-        const uint64_t key = work[i];
-        float d;
-        long long id;
-        if (key == 0ull) {
-            id = -1;
-            d = (p.metric == kMetricL2) ? FLT_MAX : -FLT_MAX;
-        } else {
-            id = (long long)key_row(key) + p.id_base;
-            const float s = key_score(key);
-            d = (p.metric == kMetricL2) ? fmaxf(0.f, p.q_norms[q] - s) : s;
-        }
-        p.D[(size_t)q * p.k + i] = d;
-        p.I[(size_t)q * p.k + i] = id;
-    }
+    for (int i = t; i < p.k; i += 256) rescore_emit(p, q, i, work[i]);
     if (t == 0) {
-        bool fail = p.q_bad[q] != 0 || p.st.overflow[q] != 0;
-        const float two_e = p.st.two_e[q];
-        const float dropmax = p.st.dropmax[q];
-        const uint64_t kth = carry[p.k - 1];
-        if (dropmax > -INFINITY && two_e > 0.f) {
-            const float bar = (kth != 0ull) ? key_score(kth) - two_e : -INFINITY;
-            if (dropmax >= bar) fail = true;
-        }
+        const bool fail = rescore_certificate_fails(p, q);
         p.fail[q] = fail ? 1 : 0;
         if (fail) atomicAdd(p.fail_count, 1u);
     }
 }
+
+// K' <= 256: one warp per query.  Rows are read by the whole warp (one coalesced 512-B read per row, four rows in flight),
+// the score is the engine's defined one (warp_engine_dot), the K' exact keys are sorted by a warp-level bitonic network.
+__global__ void __launch_bounds__(kSelWarps * 32) pq_rescore_warp_kernel(const RescoreParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * kSelWarps + warp;
+    if (q >= p.nq) return;
+    uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * p.kp;
+    const uint64_t* carry = p.st.carry + (size_t)q * p.kp;
+    const float bar = p.st.thr[q];
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
+    for (int i0 = 0; i0 < p.kp; i0 += 32) {
+        const uint64_t key = carry[i0 + lane];
+        unsigned live = __ballot_sync(0xffffffffu, key != 0ull && key_score(key) >= bar);
+        uint64_t mine = 0ull;
+        while (live) {  // warp-uniform
+            int src[4];
+            uint32_t row[4];
+            float4 rv[4];
+            int n = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                src[u] = -1;
+                if (live) {
+                    src[u] = __ffs(live) - 1;
+                    live &= live - 1;
+                    ++n;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u < n) {
+                    row[u] = key_row(__shfl_sync(0xffffffffu, key, src[u]));
+                    rv[u] = __ldg(reinterpret_cast<const float4*>(p.rows + (size_t)row[u] * kDim) + lane);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u < n) {
+                    float acc = warp_engine_dot(rv[u], qv, lane);
+                    if (p.metric == kMetricL2) acc = fmaf(2.f, acc, -__ldg(p.row_norms + row[u]));
+                    if (lane == src[u] && acc >= PQ_THR_FLOOR) mine = make_key(acc, row[u]);
+                }
+            }
+        }
+        work[i0 + lane] = mine;
+    }
+    __syncwarp();
+    for (int size = 2; size <= p.kp; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = lane; i < (p.kp >> 1); i += 32) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t x = work[lo], y = work[hi];
+                if ((x < y) == desc) {
+                    work[lo] = y;
+                    work[hi] = x;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < p.k; i += 32) rescore_emit(p, q, i, work[i]);
+    if (lane == 0) {
+        const bool fail = rescore_certificate_fails(p, q);
+        p.fail[q] = fail ? 1 : 0;
+        if (fail) atomicAdd(p.fail_count, 1u);
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // k = 1 (k-means assignment, group_paras.py:45,51): one warp per query folds its slabs directly — no carry list,
@@ -871,23 +1252,102 @@ static int next_pow2i(int v) {
     return p;
 }
 
+// cudaFuncSetAttribute costs microseconds of host time per call: a kernel's dynamic shared-memory limit is raised only when
+// a launch needs more than the kernel was last given on that device.
+static cudaError_t ensure_dyn_smem_impl(const void* fn, size_t smem, int device, cudaError_t (*set)(const void*, int)) {
+    struct Slot {
+        const void* fn;
+        int dev;
+        size_t granted;
+    };
+    static Slot slots[256];
+    static int n_slots = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Slot* sl = nullptr;
+    for (int i = 0; i < n_slots; ++i)
+        if (slots[i].fn == fn && slots[i].dev == device) sl = &slots[i];
+    if (sl && sl->granted >= smem) return cudaSuccess;
+    const cudaError_t e = set(fn, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (!sl && n_slots < 256) {
+        sl = &slots[n_slots++];
+        sl->fn = fn;
+        sl->dev = device;
+        sl->granted = 0;
+    }
+    if (sl) sl->granted = smem;
+    return cudaSuccess;
+}
+template <typename K>
+static cudaError_t ensure_dyn_smem(K* kernel, size_t smem, int device) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return ensure_dyn_smem_impl((const void*)kernel, smem, device,
+                                [](const void* f, int v) { return cudaFuncSetAttribute((K*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, v); });
+}
+
 template <int M, bool L2, bool K1>
-static cudaError_t launch_filter(const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
+static cudaError_t launch_filter(const CUtensorMap& tc, const MmaParams& p, int n_ctas, int device, cudaStream_t stream) {
     const size_t smem = (size_t)kStages * kStageBytes + 256 + (size_t)kMaxMTiles * kEpiWarps * 32 * 12;  // ring + control + epilogue state
-    cudaError_t e = cudaFuncSetAttribute(pq_mma_filter_kernel<M, L2, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dyn_smem(pq_mma_filter_kernel<M, L2, K1>, smem, device);
     if (e != cudaSuccess) return e;
     pq_mma_filter_kernel<M, L2, K1><<<n_ctas, kMmaThreads, smem, stream>>>(tc, p);
     return cudaGetLastError();
 }
 template <bool L2, bool K1>
-static cudaError_t launch_filter_m(int m_max, const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
-    if (m_max == 1) return launch_filter<1, L2, K1>(tc, p, n_ctas, stream);
-    if (m_max == 2) return launch_filter<2, L2, K1>(tc, p, n_ctas, stream);
-    return launch_filter<4, L2, K1>(tc, p, n_ctas, stream);
+static cudaError_t launch_filter_m(int m_max, const CUtensorMap& tc, const MmaParams& p, int n_ctas, int device, cudaStream_t stream) {
+    if (m_max == 1) return launch_filter<1, L2, K1>(tc, p, n_ctas, device, stream);
+    if (m_max == 2) return launch_filter<2, L2, K1>(tc, p, n_ctas, device, stream);
+    return launch_filter<4, L2, K1>(tc, p, n_ctas, device, stream);
 }
-static cudaError_t launch_filter_any(int m_max, bool l2, bool k1, const CUtensorMap& tc, const MmaParams& p, int n_ctas, cudaStream_t stream) {
-    if (l2) return k1 ? launch_filter_m<true, true>(m_max, tc, p, n_ctas, stream) : launch_filter_m<true, false>(m_max, tc, p, n_ctas, stream);
-    return k1 ? launch_filter_m<false, true>(m_max, tc, p, n_ctas, stream) : launch_filter_m<false, false>(m_max, tc, p, n_ctas, stream);
+static cudaError_t launch_filter_any(int m_max, bool l2, bool k1, const CUtensorMap& tc, const MmaParams& p, int n_ctas, int device,
+                                     cudaStream_t stream) {
+    if (l2) return k1 ? launch_filter_m<true, true>(m_max, tc, p, n_ctas, device, stream) : launch_filter_m<true, false>(m_max, tc, p, n_ctas, device, stream);
+    return k1 ? launch_filter_m<false, true>(m_max, tc, p, n_ctas, device, stream) : launch_filter_m<false, false>(m_max, tc, p, n_ctas, device, stream);
+}
+
+// Epoch select and rescoring: one warp per query while the carry list fits a warp's pool (K' <= 256), one CTA per query beyond.
+static cudaError_t launch_epoch_select(const EpochSelParams& sp, int device, cudaStream_t stream) {
+    if (sp.kp <= 256) {
+        const size_t smem = (size_t)kSelWarps * (kSelWarpPool * 8 + 256 * 4);
+        cudaError_t e = ensure_dyn_smem(pq_epoch_select_warp_kernel, smem, device);
+        if (e != cudaSuccess) return e;
+        pq_epoch_select_warp_kernel<<<(sp.nq + kSelWarps - 1) / kSelWarps, kSelWarps * 32, smem, stream>>>(sp);
+    } else {
+        const size_t smem = ((size_t)sp.lmax + sp.kp) * 8 + (size_t)sp.n_sub * 8;
+        cudaError_t e = ensure_dyn_smem(pq_epoch_select_kernel, smem, device);
+        if (e != cudaSuccess) return e;
+        pq_epoch_select_kernel<<<sp.nq, 256, smem, stream>>>(sp);
+    }
+    return cudaGetLastError();
+}
+static cudaError_t launch_rescore(const RescoreParams& rp, int device, cudaStream_t stream) {
+    if (rp.kp <= 256) {
+        const size_t smem = (size_t)kSelWarps * rp.kp * 8;
+        pq_rescore_warp_kernel<<<(rp.nq + kSelWarps - 1) / kSelWarps, kSelWarps * 32, smem, stream>>>(rp);
+    } else {
+        const size_t smem = (size_t)rp.work * 8;
+        cudaError_t e = ensure_dyn_smem(pq_rescore_kernel, smem, device);
+        if (e != cudaSuccess) return e;
+        pq_rescore_kernel<<<rp.nq, 256, smem, stream>>>(rp);
+    }
+    return cudaGetLastError();
+}
+
+// Cross-shard threshold exchange for this batch, or n = 0 when it is off (pq_index_share_connect).
+static ShareParams make_share_params(const pq_index* ix, int nq, int k, int batch) {
+    ShareParams sh;
+    memset(&sh, 0, sizeof(sh));
+    const pq_share_state& ss = ix->share;
+    if (!ss.connected || ss.n < 2 || ss.n > kShareMaxPeers || nq > ss.cap_q || k == 1) return sh;
+    sh.n = ss.n;
+    sh.rank = ss.rank;
+    sh.kr = (k + ss.n - 1) / ss.n;
+    sh.tag = (ss.seq << 4) | ((uint32_t)batch & 15u);
+    sh.cap_q = ss.cap_q;
+    sh.wait_ns = ss.wait_us * 1000;
+    for (int i = 0; i < ss.n; ++i) sh.peer[i] = ss.peer[i];
+    return sh;
 }
 
 int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, float* dD_all, long long* dI_all,
@@ -895,9 +1355,10 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
     const long long N = ix->ntotal;
     const int kp = carry_size_for_k(k);
     const bool k1 = (k == 1);
+    const bool l2 = ix->metric == kMetricL2;
     const int kMaxBatch = k1 ? (1 << 20) : (1 << 18);  // queries per pass (bounds the candidate slabs)
 
-    for (int qb = 0; qb < nq_total; qb += kMaxBatch) {
+    for (int qb = 0, batch = 0; qb < nq_total; qb += kMaxBatch, ++batch) {
         const int nq = std::min(kMaxBatch, nq_total - qb);
         const int nq_pad = (nq + kBM - 1) / kBM * kBM;
         const int n_mtiles = nq_pad / kBM;
@@ -906,9 +1367,11 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         const uint16_t* dq_bf16 = (const uint16_t*)ix->ws_qbf16.p + (size_t)qb * kDim;
         const float* dq_norm = (const float*)ix->ws_qnorm.p + qb;
         const uint8_t* dq_bad = (const uint8_t*)ix->ws_qbad.p + qb;
+        const ShareParams share = make_share_params(ix, nq, k, batch);
 
         // ---- epoch plan (pq_plan.h) -----------------------------------------------------------
-        const std::vector<EpochPlan> plan = plan_epochs(N, k, nq_pad, gs, ix->n_sms);
+        const std::vector<EpochPlan> plan = plan_epochs(N, k, nq_pad, gs, ix->n_sms, share.n > 1 ? share.n : 1);
+        if (plan.size() > 31) return set_error(PQ_ERR_UNSUPPORTED, "search: %zu epochs", plan.size());
         size_t max_slab = 0, max_cnt = 0;
         for (const EpochPlan& ep : plan) {
             const size_t n_sub = (size_t)plan_n_sub(gs, ep);
@@ -926,7 +1389,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         if (!rc) rc = w[5].ensure(max_slab);                      // candidate slabs
         if (!rc) rc = w[6].ensure(max_cnt);                       // slab counts
         if (!rc) rc = w[7].ensure((size_t)nq_pad);                // fail flags
-        if (!rc) rc = w[8].ensure((size_t)nq_pad * 4 + 256);      // redo flags, then the any_redo counter
+        if (!rc) rc = w[8].ensure((size_t)nq_pad * 4 + 256);      // per-query repair masks, then the counters
         if (rc) return rc;
         QState st;
         st.thr = (float*)w[0].p;
@@ -935,43 +1398,65 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         st.overflow = (uint32_t*)w[3].p;
         st.carry = (uint64_t*)w[4].p;
         st.redo = (uint32_t*)w[8].p;
-        st.any_redo = st.redo + nq_pad;
+        st.counters = st.redo + nq_pad;
 
         if (!k1) PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
-        PQ_CUDA(cudaMemsetAsync(st.any_redo, 0, 12, ix->stream));  // any_redo, total second attempts, failed queries
+        PQ_CUDA(cudaMemsetAsync(st.counters, 0, 16, ix->stream));
         pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, (const float*)ix->ws_qresid.p + qb, dq_bad, nq, nq_pad, kp,
                                                                              ix->max_norm2, ix->max_resid2, ix->metric);
         PQ_CUDA(cudaGetLastError());
         ix->stats[5] += 1;
 
-        // ---- epochs ---------------------------------------------------------------------------
-        for (const EpochPlan& ep : plan) {
-            MmaParams mp;
-            mp.q_bf16 = dq_bf16;
-            mp.cand_keys = (uint64_t*)w[5].p;
-            mp.cand_cnt = (uint32_t*)w[6].p;
-            mp.row_norms = (const float*)ix->norms.p;
-            mp.thr = st.thr;
-            mp.two_e = st.two_e;
+        MmaParams mp;
+        mp.q_bf16 = dq_bf16;
+        mp.cand_keys = (uint64_t*)w[5].p;
+        mp.cand_cnt = (uint32_t*)w[6].p;
+        mp.row_norms = (const float*)ix->norms.p;
+        mp.thr = st.thr;
+        mp.two_e = st.two_e;
+        mp.n_mtiles = n_mtiles;
+        mp.base = gs.base;
+        mp.rem = gs.rem;
+        mp.k1_adapt = k1 ? 1 : 0;
+        EpochSelParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.st = st;
+        sp.cand_keys = mp.cand_keys;
+        sp.cand_cnt = mp.cand_cnt;
+        sp.kp = kp;
+        sp.k = k;
+        sp.lmax = std::max(2 * kp, 4096);  // pool of the CTA kernel: old carry + one chunk of candidates
+        sp.nq = nq;
+        sp.base = gs.base;
+        sp.rem = gs.rem;
+        auto set_epoch = [&](const EpochPlan& ep, int e) {
             mp.row_begin = ep.begin;
             mp.row_end = ep.end;
-            mp.n_mtiles = n_mtiles;
-            mp.base = gs.base;
-            mp.rem = gs.rem;
             mp.s1 = ep.s1;
             mp.s0 = ep.s0;
             mp.cap = ep.cap;
             mp.n_sub = plan_n_sub(gs, ep);
-            mp.k1_adapt = k1 ? 1 : 0;
+            sp.n_sub = mp.n_sub;
+            sp.cap = ep.cap;
+            sp.s1 = ep.s1;
+            sp.s0 = ep.s0;
+            sp.epoch_bit = 1u << e;
+            sp.row_begin = ep.begin;
+            sp.row_end = ep.end;
+        };
+
+        // ---- epochs: filter (every slab count a query's group owns is written by it), then select -------------------
+        for (int e = 0; e < (int)plan.size(); ++e) {
+            const EpochPlan& ep = plan[e];
+            set_epoch(ep, e);
             mp.redo = nullptr;
-            mp.any_redo = nullptr;
+            mp.redo_bit = 0u;
             const int n_ctas = plan_n_ctas(gs, ep);
-            // slabs a CTA never touches (unequal slice counts, query tiles owned by the other warp set) must read as empty
-            PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
+            if (k1) PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));  // (its finalize reads every slab)
             ix->prof_begin();
-            const cudaError_t e = launch_filter_any(gs.m_max, ix->metric == kMetricL2, k1, ix->tmap_bf16, mp, n_ctas, ix->stream);
+            const cudaError_t fe = launch_filter_any(gs.m_max, l2, k1, ix->tmap_bf16, mp, n_ctas, ix->device, ix->stream);
             ix->prof_end();
-            PQ_CUDA(e);
+            PQ_CUDA(fe);
             ix->stats[3] += 1;
             ix->stats[5] += 1;
             if (k1) {  // single pass: fold the slabs straight into (D, I)
@@ -993,52 +1478,39 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
                 kp1.D = dD_all + (size_t)qb;
                 kp1.I = dI_all + (size_t)qb;
                 kp1.fail = (uint8_t*)w[7].p;
-                kp1.fail_count = st.any_redo + 2;
+                kp1.fail_count = st.counters + 2;
                 pq_k1_finalize_kernel<<<(nq + 7) / 8, 256, 0, ix->stream>>>(kp1);
                 PQ_CUDA(cudaGetLastError());
                 ix->stats[4] += 1;
                 ix->stats[5] += 1;
                 continue;
             }
-
-            const bool can_overflow = ep.begin > 0;  // the bootstrap epoch's slabs hold every row they can see
-            EpochSelParams sp;
-            sp.st = st;
-            sp.cand_keys = mp.cand_keys;
-            sp.cand_cnt = mp.cand_cnt;
-            sp.n_sub = mp.n_sub;
-            sp.cap = ep.cap;
-            sp.kp = kp;
-            sp.k = k;
-            sp.lmax = std::max(2 * kp, 4096);  // pool: old carry + one chunk of candidates
             sp.is_redo = 0;
-            sp.allow_redo = can_overflow ? 1 : 0;
-            sp.row_begin = ep.begin;
-            const size_t smem = ((size_t)sp.lmax + kp) * 8 + (size_t)sp.n_sub * 8;
-            PQ_CUDA(cudaFuncSetAttribute(pq_epoch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (can_overflow) PQ_CUDA(cudaMemsetAsync(st.redo, 0, (size_t)nq_pad * 4 + 4, ix->stream));
-            pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
-            PQ_CUDA(cudaGetLastError());
+            sp.allow_redo = ep.begin > 0 ? 1 : 0;  // the bootstrap epoch's slabs hold every row they can see
+            sp.share = share;
+            PQ_CUDA(launch_epoch_select(sp, ix->device, ix->stream));
             ix->stats[4] += 1;
             ix->stats[5] += 1;
-            if (can_overflow) {
-                // Second attempt for the queries whose slabs overflowed (rows in document order: a whole cluster above the
-                // threshold), against the threshold their first attempt produced.  Both kernels return at once when no
-                // query asked for it — the common case costs two empty launches, no host synchronisation.
-                mp.redo = st.redo;
-                mp.any_redo = st.any_redo;
-                PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
-                PQ_CUDA(launch_filter_any(gs.m_max, ix->metric == kMetricL2, false, ix->tmap_bf16, mp, n_ctas, ix->stream));
-                sp.is_redo = 1;
-                sp.allow_redo = 0;
-                pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
+            if (share.n > 1 && e + 1 < (int)plan.size()) {  // what the row shards know together, before the next epoch admits on it
+                pq_share_fold_kernel<<<(nq + 255) / 256, 256, 0, ix->stream>>>(share, st, nq, e);
                 PQ_CUDA(cudaGetLastError());
-                ix->stats[5] += 2;
+                ix->stats[5] += 1;
             }
+        }
+        if (k1) {
+            uint32_t counts[4] = {0, 0, 0, 0};
+            PQ_CUDA(cudaMemcpyAsync(counts, st.counters, 16, cudaMemcpyDeviceToHost, ix->stream));
+            PQ_CUDA(cudaStreamSynchronize(ix->stream));
+            if (counts[2] != 0) {
+                std::vector<uint8_t> fail((size_t)nq);
+                PQ_CUDA(cudaMemcpy(fail.data(), w[7].p, (size_t)nq, cudaMemcpyDeviceToHost));
+                for (int q = 0; q < nq; ++q)
+                    if (fail[q]) rerun->push_back(qb + q);
+            }
+            continue;
         }
 
         // ---- exact rescoring + certificate ------------------------------------------------------
-        if (!k1) {
         RescoreParams rp;
         rp.st = st;
         rp.queries = dq;
@@ -1050,23 +1522,49 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         rp.k = k;
         rp.metric = ix->metric;
         rp.work = std::max(kp, next_pow2i(k));
+        rp.nq = nq;
         rp.id_base = ix->id_base;
         rp.D = dD_all + (size_t)qb * k;
         rp.I = dI_all + (size_t)qb * k;
         rp.fail = (uint8_t*)w[7].p;
-        rp.fail_count = st.any_redo + 2;
-        const size_t rsmem = (size_t)rp.work * 8;
-        PQ_CUDA(cudaFuncSetAttribute(pq_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-        pq_rescore_kernel<<<nq, 256, rsmem, ix->stream>>>(rp);
-        PQ_CUDA(cudaGetLastError());
+        rp.fail_count = st.counters + 2;
+        PQ_CUDA(launch_rescore(rp, ix->device, ix->stream));
         ix->stats[4] += 1;
         ix->stats[5] += 1;
-        }
 
-        uint32_t counts[3] = {0, 0, 0};  // any_redo (last epoch), total second attempts, failed queries
-        PQ_CUDA(cudaMemcpyAsync(counts, st.any_redo, 12, cudaMemcpyDeviceToHost, ix->stream));
+        uint32_t counts[4] = {0, 0, 0, 0};  // OR of the repair masks, (query, epoch) overflows, failed queries, full exchanges
+        PQ_CUDA(cudaMemcpyAsync(counts, st.counters, 16, cudaMemcpyDeviceToHost, ix->stream));
         PQ_CUDA(cudaStreamSynchronize(ix->stream));
+        if (counts[0] != 0u) {
+            // Some slabs overflowed (rows in document order: a whole cluster above the threshold at once).  What fitted was
+            // used — real rows, valid thresholds — and every other epoch is complete, so only the overflowed epochs are run
+            // again, for the queries concerned (the others filter at +inf), against their FINAL thresholds; then the
+            // rescoring is redone.  The common case pays nothing for this: no launch, no flag check.
+            for (int e = 0; e < (int)plan.size(); ++e) {
+                if (!(counts[0] & (1u << e))) continue;
+                set_epoch(plan[e], e);
+                mp.redo = st.redo;
+                mp.redo_bit = 1u << e;
+                PQ_CUDA(launch_filter_any(gs.m_max, l2, false, ix->tmap_bf16, mp, plan_n_ctas(gs, plan[e]), ix->device, ix->stream));
+                sp.is_redo = 1;
+                sp.allow_redo = 0;
+                sp.share.n = 0;
+                PQ_CUDA(launch_epoch_select(sp, ix->device, ix->stream));
+                ix->stats[3] += 1;
+                ix->stats[4] += 1;
+                ix->stats[5] += 2;
+            }
+            PQ_CUDA(cudaMemsetAsync(st.counters + 2, 0, 4, ix->stream));
+            PQ_CUDA(launch_rescore(rp, ix->device, ix->stream));
+            ix->stats[4] += 1;
+            ix->stats[5] += 1;
+            uint32_t again[4] = {0, 0, 0, 0};
+            PQ_CUDA(cudaMemcpyAsync(again, st.counters, 16, cudaMemcpyDeviceToHost, ix->stream));
+            PQ_CUDA(cudaStreamSynchronize(ix->stream));
+            counts[2] = again[2];
+        }
         ix->stats[8] += counts[1];
+        ix->stats[9] += counts[3];
         if (counts[2] != 0) {  // rare: fetch the per-query flags
             std::vector<uint8_t> fail((size_t)nq);
             PQ_CUDA(cudaMemcpy(fail.data(), w[7].p, (size_t)nq, cudaMemcpyDeviceToHost));

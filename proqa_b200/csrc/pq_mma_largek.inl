@@ -1,10 +1,10 @@
 // proqa_b200 — tensor-core tier for 1024 < k <= PQ_MAX_K (included by pq_mma.cu inside namespace pq).
 //
-// STATUS: written and cross-compiled in round 1 after the GPU budget was spent — NOT yet run on hardware.  It is reached
-// only when PROQA_B200_LARGEK=1 (pq_index.cu: tier_uses_largek); by default k > 1024 is answered by the fp32 scan.  The
-// statistics it relies on (rank of the sample threshold, survivors per query, slab occupancy, size of the rescored set,
-// certificate) were replayed on CPU for 8.8M rows / k = 10000 on exchangeable and on document-ordered rows:
-// tools/sim_largek.py, results in DESIGN.md §5.6.
+// Default for 1024 < k on corpora of at least 64 k rows (pq_index.cu: tier_uses_largek; PROQA_B200_LARGEK=0 sends such k back
+// to the fp32 scan).  Validated on a B200 in round 2 (tests/test_gpu_largek.py, compute-sanitizer memcheck + racecheck clean;
+// 256 queries x 8.8M rows x k = 10000: 3.8 ms on the device against ~6 ms per query on the scan).  The statistics it relies
+// on (rank of the sample threshold, survivors per query, slab occupancy, size of the rescored set, certificate) were replayed
+// on CPU for 8.8M rows / k = 10000 on exchangeable and on document-ordered rows: tools/sim_largek.py, DESIGN.md §5.6.
 //
 // Call site served: retrieval/trec_process.py:76 — index.search(xq, 10000) over the MS MARCO passages.
 //
@@ -362,10 +362,10 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         st.overflow = (uint32_t*)w[3].p;
         st.carry = (uint64_t*)w[4].p;
         st.redo = (uint32_t*)w[8].p;
-        st.any_redo = st.redo + nq_pad;
+        st.counters = st.redo + nq_pad;
 
         PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp_s * 8, ix->stream));
-        PQ_CUDA(cudaMemsetAsync(st.redo, 0, (size_t)nq_pad * 4 + 12, ix->stream));
+        PQ_CUDA(cudaMemsetAsync(st.counters, 0, 16, ix->stream));
         pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, (const float*)ix->ws_qresid.p + qb, dq_bad, nq, nq_pad, kp_s,
                                                                              ix->max_norm2, ix->max_resid2, ix->metric);
         PQ_CUDA(cudaGetLastError());
@@ -382,7 +382,7 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         mp.rem = gs.rem;
         mp.k1_adapt = 0;
         mp.redo = nullptr;
-        mp.any_redo = nullptr;
+        mp.redo_bit = 0u;
 
         // ---- A. thresholds from the sample ----------------------------------------------------
         for (const EpochPlan& ep : plan_s) {
@@ -393,9 +393,9 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.s0 = ep.s0;
             mp.cap = ep.cap;
             mp.n_sub = plan_n_sub(gs, ep);
-            PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
-            PQ_CUDA(launch_filter_any(gs.m_max, l2, false, ix->tmap_sample, mp, plan_n_ctas(gs, ep), ix->stream));
+            PQ_CUDA(launch_filter_any(gs.m_max, l2, false, ix->tmap_sample, mp, plan_n_ctas(gs, ep), ix->device, ix->stream));
             EpochSelParams sp;
+            memset(&sp, 0, sizeof(sp));
             sp.st = st;
             sp.cand_keys = mp.cand_keys;
             sp.cand_cnt = mp.cand_cnt;
@@ -404,13 +404,17 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.kp = kp_s;
             sp.k = lp.k_sample;
             sp.lmax = std::max(2 * kp_s, 4096);
+            sp.nq = nq;
+            sp.base = gs.base;
+            sp.rem = gs.rem;
+            sp.s1 = ep.s1;
+            sp.s0 = ep.s0;
             sp.is_redo = 0;
             sp.allow_redo = 0;   // a slab overflow only loosens the estimate (the k-th best of what fitted is still a real score)
+            sp.epoch_bit = 0u;
             sp.row_begin = ep.begin;
-            const size_t smem = ((size_t)sp.lmax + kp_s) * 8 + (size_t)sp.n_sub * 8;
-            PQ_CUDA(cudaFuncSetAttribute(pq_epoch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pq_epoch_select_kernel<<<nq, 256, smem, ix->stream>>>(sp);
-            PQ_CUDA(cudaGetLastError());
+            sp.row_end = ep.end;
+            PQ_CUDA(launch_epoch_select(sp, ix->device, ix->stream));
             ix->stats[3] += 1;
             ix->stats[4] += 1;
             ix->stats[5] += 2;
@@ -426,7 +430,7 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         mp.n_sub = plan_n_sub(gs, pass);
         PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
         ix->prof_begin();
-        const cudaError_t e = launch_filter_any(gs.m_max, l2, false, ix->tmap_bf16, mp, plan_n_ctas(gs, pass), ix->stream);
+        const cudaError_t e = launch_filter_any(gs.m_max, l2, false, ix->tmap_bf16, mp, plan_n_ctas(gs, pass), ix->device, ix->stream);
         ix->prof_end();
         PQ_CUDA(e);
         ix->stats[3] += 1;
@@ -453,16 +457,16 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         fp.D = dD_all + (size_t)qb * k;
         fp.I = dI_all + (size_t)qb * k;
         fp.fail = (uint8_t*)w[7].p;
-        fp.fail_count = st.any_redo + 2;
+        fp.fail_count = st.counters + 2;
         const size_t fsmem = (size_t)std::max(lp.pool, lp.sort_n) * 8 + (size_t)fp.n_sub * 4;
-        PQ_CUDA(cudaFuncSetAttribute(pq_largek_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        PQ_CUDA(ensure_dyn_smem(pq_largek_finalize_kernel, fsmem, ix->device));
         pq_largek_finalize_kernel<<<nq, 256, fsmem, ix->stream>>>(fp);
         PQ_CUDA(cudaGetLastError());
         ix->stats[4] += 1;
         ix->stats[5] += 1;
 
         uint32_t counts[3] = {0, 0, 0};
-        PQ_CUDA(cudaMemcpyAsync(counts, st.any_redo, 12, cudaMemcpyDeviceToHost, ix->stream));
+        PQ_CUDA(cudaMemcpyAsync(counts, st.counters, 12, cudaMemcpyDeviceToHost, ix->stream));
         PQ_CUDA(cudaStreamSynchronize(ix->stream));
         if (counts[2] != 0) {
             std::vector<uint8_t> fail((size_t)nq);

@@ -78,7 +78,9 @@ inline void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n
 }
 
 // Epochs of one search over rows [0, N): contiguous, in order, covering every row once.
-inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const GridShape& gs, int n_sms) {
+// share_n > 1: the corpus is row-sharded over share_n GPUs that exchange thresholds after every epoch (pq_mma.cu:
+// ShareParams), so a threshold reflects share_n times the rows this shard has seen: epochs grow faster, slabs stay small.
+inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const GridShape& gs, int n_sms, int share_n = 1) {
     std::vector<EpochPlan> plan;
     const int n_mtiles = nq_pad / kPlanQueryTile;
     const int kp = carry_size_for_k(k);
@@ -94,7 +96,8 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
     // Epoch growth: every epoch costs a fixed ~0.1-0.2 ms (launches, select) and about 1.5 k (growth - 1) survivors per
     // query; small batches are dominated by the fixed part, large ones by the survivors
     // (measured: nq=16 1.19 ms at 64x; nq=256 1.66 ms at 8x vs 1.81 at 64x).
-    const long long growth = nq_pad <= 128 ? 64 : (nq_pad <= 512 ? 16 : 8);
+    const int share_f = share_n >= 4 ? 4 : (share_n >= 2 ? 2 : 1);
+    const long long growth = std::min(64LL, (nq_pad <= 128 ? 64LL : (nq_pad <= 512 ? 16LL : 8LL)) * share_f);
     const long long n0 = std::min<long long>(N, std::max(1024, plan_next_pow2(2 * kp)));
     long long begin = 0, end = n0;
     while (begin < N) {
@@ -111,7 +114,7 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
             // ~1.5 for the 2E margin, on exchangeable rows; three times that is provisioned (rows in document order
             // bring whole clusters above the threshold at once — beyond the provision the epoch is run a second time)
             const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
-            const double expect = 1.5 * (double)k * ((double)(ep.end - ep.begin) / (double)ep.begin) / slabs;
+            const double expect = 1.5 * (double)k * ((double)(ep.end - ep.begin) / (double)ep.begin) / slabs / share_f;
             ep.cap = std::min(4096, std::max(64, plan_next_pow2((int)(3.0 * expect) + 64)));
         }
         plan.push_back(ep);

@@ -23,6 +23,7 @@ the product.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -62,6 +63,12 @@ class ShardedIndexFlat:
         self._merge_fn = merge_fn
         self.ntotal = 0
         self._first_add = True
+        # threshold exchange between the row shards of a group (peer mailboxes over NVLink, include/proqa_b200.h); on by default
+        # for the CUDA engine, PROQA_B200_SHARE=0 leaves the shards independent
+        self._share_on = (merge_fn is None and local_factory is None and os.environ.get("PROQA_B200_SHARE", "1") != "0")
+        self._share_cap = 0
+        self._share_peers = []
+        self._seq = 0
         # process groups: every rank creates every group, in the same order (new_group is collective)
         self.row_group = group
         self.col_group = None
@@ -112,6 +119,67 @@ class ShardedIndexFlat:
         self._local.reset()
         self.ntotal = 0
         self._first_add = True
+        self._share_close()
+
+    # ---- threshold exchange between row shards ----------------------------------------------------
+    def _share_close(self):
+        L = _lib.lib()
+        if self._share_cap:
+            L.pq_index_share_close(self._local._h)
+            for ptr in self._share_peers:
+                L.pq_ipc_close(self._dev_index(), ctypes.c_void_p(ptr))
+        self._share_cap, self._share_peers = 0, []
+
+    def _dev_index(self):
+        import torch
+        return torch.cuda.current_device() if self.device is None else int(self.device)
+
+    def _share_setup(self, nq):
+        """Collective over the row group: (re)allocate the mailboxes for up to nq queries per search, exchange their CUDA IPC
+        handles, map the peers' mailboxes, agree on the error-bound scalars of the whole corpus."""
+        import torch
+        L = _lib.lib()
+        dist, dev = self._dist, torch.device("cuda", self._dev_index())
+        self._share_close()
+        cap = 1024
+        while cap < min(nq, 1 << 18):
+            cap *= 2
+        sc = (ctypes.c_float * 2)()
+        _lib.check(L.pq_index_get_bound_scalars(self._local._h, sc), "get_bound_scalars")
+        t = torch.tensor([sc[0], sc[1]], dtype=torch.float32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.row_group)
+        mx = t.cpu().tolist()
+        _lib.check(L.pq_index_set_bound_scalars(self._local._h, mx[0], mx[1]), "set_bound_scalars")
+        box, nbytes = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(L.pq_index_share_alloc(self._local._h, self.R, self.rr, cap, ctypes.byref(box), ctypes.byref(nbytes)), "share_alloc")
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(L.pq_ipc_export(box, handle), "ipc_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        every = torch.empty(self.R * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(every, mine, group=self.row_group)
+        every = every.cpu().numpy().reshape(self.R, 64)
+        ptrs = (ctypes.c_void_p * self.R)()
+        for r in range(self.R):
+            if r == self.rr:
+                ptrs[r] = box.value
+                continue
+            h = (ctypes.c_ubyte * 64)(*every[r].tolist())
+            out = ctypes.c_void_p()
+            _lib.check(L.pq_ipc_open(h, self._dev_index(), ctypes.byref(out)), "ipc_open")
+            ptrs[r] = out.value
+            self._share_peers.append(out.value)
+        _lib.check(L.pq_index_share_connect(self._local._h, ptrs), "share_connect")
+        dist.barrier(group=self.row_group)   # nobody searches before every mailbox is mapped everywhere
+        self._share_cap = cap
+
+    def _share_begin(self, nq_local):
+        """Before every search of this rank's query slice (same on all ranks of the row group)."""
+        if not (self._share_on and self.R > 1 and self.world > 1):
+            return
+        if min(nq_local, 1 << 18) > self._share_cap:
+            self._share_setup(nq_local)
+        self._seq += 1
+        _lib.check(_lib.lib().pq_index_share_begin(self._local._h, self._seq), "share_begin")
 
     @property
     def local(self):
@@ -125,6 +193,7 @@ class ShardedIndexFlat:
         k = int(k)
         nq = xq.shape[0]
         qlo, qhi = self.query_bounds(nq)
+        self._share_begin(qhi - qlo)
         D, I = self._local.search(xq[qlo:qhi], k)
         if self.world == 1:
             return D, I
@@ -145,6 +214,7 @@ class ShardedIndexFlat:
         n_loc = qhi - qlo
         per = (nq + self.Q - 1) // self.Q   # padded slice length (all_gather needs equal pieces)
         Dl, Il = D_local[:n_loc], I_local[:n_loc]
+        self._share_begin(n_loc)
         if n_loc:
             self._local.search_device(q[qlo:qhi].data_ptr(), n_loc, k, Dl.data_ptr(), Il.data_ptr())
         if self.world == 1:

@@ -91,21 +91,43 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
         extract(mma, "struct MmaParams {"),
         extract(mma, "struct QState {"),
         extract(mma, "__global__ void pq_mma_init_state_kernel(QState st"),
+        extract(mma, "constexpr int kShareMaxPeers = 16;", upto="constexpr int kShareMaxPeers = 16;"),
+        extract(mma, "struct ShareParams {"),
+        extract(mma, "uint64_t share_word(uint32_t tag, float v)", upto="uint64_t share_word(uint32_t tag, float v)"),
+        extract(mma, "void share_publish(const ShareParams& sh, int q, float a, float b, int lane)"),
+        extract(mma, "pq_share_fold_kernel(const ShareParams sh, QState st, int nq, int epoch)"),
         extract(mma, "struct EpochSelParams {"),
+        extract(mma, "int sel_slabs_of_query(const EpochSelParams& p, int q)"),
         extract(mma, "uint64_t block_radix_select(const uint64_t* pool"),
         extract(mma, "pq_epoch_select_kernel(const EpochSelParams p)"),
+        extract(mma, "constexpr int kSelWarpPool = 1024;", upto="constexpr int kSelWarps = 8;"),
+        extract(mma, "int warp_sum(int v)"),
+        extract(mma, "uint64_t warp_radix_select(const uint64_t* pool, int n, int want, int* hist, int lane)"),
+        extract(mma, "struct WarpSelState {"),
+        extract(mma, "int warp_sel_reduce(const EpochSelParams& p"),
+        extract(mma, "pq_epoch_select_warp_kernel(const EpochSelParams p)"),
         extract(mma, "struct RescoreParams {"),
+        extract(mma, "bool rescore_certificate_fails(const RescoreParams& p, int q)"),
+        extract(mma, "void rescore_emit(const RescoreParams& p, int q, int i, uint64_t key)"),
         extract(mma, "pq_rescore_kernel(const RescoreParams p)"),
+        extract(mma, "pq_rescore_warp_kernel(const RescoreParams p)"),
         extract(mma, "struct K1Params {"),
         extract(mma, "pq_k1_finalize_kernel(const K1Params p)"),
     ])
-    host = extract(mma, "static int next_pow2i(int v)") + extract(mma, "int search_mma_filter(pq_index* ix")
+    host = (extract(mma, "static int next_pow2i(int v)") + extract(mma, "static cudaError_t ensure_dyn_smem_impl(const void* fn")
+            + extract(mma, "static cudaError_t ensure_dyn_smem(K* kernel, size_t smem, int device)")
+            + extract(mma, "static cudaError_t launch_epoch_select(const EpochSelParams& sp")
+            + extract(mma, "static cudaError_t launch_rescore(const RescoreParams& rp")
+            + extract(mma, "static ShareParams make_share_params(const pq_index* ix")
+            + extract(mma, "int search_mma_filter(pq_index* ix"))
     tmpl = open(os.path.join(SIMT, "mma_host_emu.cpp.in")).read()
     text = (tmpl.replace("@EXTRACTED_DEVICE@", to_host(device)).replace("@FILTER_IMPL@", filter_impl)
             .replace("@EXTRACTED_HOST@", to_host(host)).replace("@EXTRACTED_LARGEK@", to_host(inl)))
     # -Bsymbolic: our fake CUDA runtime, not a libcudart some other module of the test process has loaded
     lib = compile_so(text, workdir, "mma_host_emu_real" if real_filter else "mma_host_emu", opt="-O2", extra=("-I", CSRC, "-I", "/usr/local/cuda/include", "-Wl,-Bsymbolic"))
     vp = ctypes.c_void_p
+    lib.emu_set_share.restype = None
+    lib.emu_set_share.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_longlong, vp]
     lib.emu_search_mma.restype = ctypes.c_char_p
     lib.emu_search_mma.argtypes = [vp, vp, vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
@@ -138,7 +160,7 @@ def resid2(x):
     return (((x - bf16_round(x)).astype(np.float64) ** 2).sum(1) * 1.0001).astype(np.float32)
 
 
-def run_host_emu(lib, xb, xq, k, metric, n_sms=8, schedule=0):
+def run_host_emu(lib, xb, xq, k, metric, n_sms=8, schedule=0, share=None, bound=None):
     """-> D, I, sorted list of queries the driver wants re-run by the fp32 scan, the driver's statistics.
     schedule != 0: the emulator resumes the threads of a block in a different pseudo-random order at every pass."""
     lib.emu_set_schedule(schedule)
@@ -161,7 +183,14 @@ def run_host_emu(lib, xb, xq, k, metric, n_sms=8, schedule=0):
     rerun = np.zeros(nq, np.int32)
     n_rerun = ctypes.c_int(0)
     stats = np.zeros(10, np.int64)
-    msg = lib.emu_search_mma(xb.ctypes.data, xb_b.ctypes.data, norms.ctypes.data, len(xb), float(norms.max()), float(resid2(xb).max()),
+    if share is not None:   # (n, rank, cap_q, wait_us, seq, id_base, [mailbox arrays]): this call is one row shard of n
+        n_sh, rank, cap_q, wait_us, seq, id_base, boxes = share
+        arr = (ctypes.c_void_p * 16)(*[b.ctypes.data for b in boxes])
+        lib.emu_set_share(n_sh, rank, cap_q, wait_us, seq, id_base, arr)
+    else:
+        lib.emu_set_share(0, 0, 0, 0, 0, 0, None)
+    max_norm2, max_resid2 = bound if bound is not None else (float(norms.max()), float(resid2(xb).max()))
+    msg = lib.emu_search_mma(xb.ctypes.data, xb_b.ctypes.data, norms.ctypes.data, len(xb), max_norm2, max_resid2,
                              xq.ctypes.data, xq_b.ctypes.data, q_norm.ctypes.data, q_resid.ctypes.data, q_bad.ctypes.data, nq, k, metric,
                              n_sms, D.ctypes.data, I.ctypes.data, rerun.ctypes.data, ctypes.byref(n_rerun), stats.ctypes.data)
     assert msg is None, msg.decode()

@@ -379,6 +379,8 @@ inline T atomicOr(T* p, T v) {
     return old;
 }
 inline unsigned __float_as_uint(float f) { return simt::from_bits<unsigned>(simt::to_bits(f)); }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline void __threadfence_system() {}
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

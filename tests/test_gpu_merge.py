@@ -21,7 +21,7 @@ def _lists(G, nq, k, metric, seed, coarse):
             ids = np.sort(rng.choice(per, n_valid, replace=False)) + g * per
             sc = rng.standard_normal(n_valid).astype(np.float32)
             if coarse:
-                sc = np.round(sc, 1)
+                sc = np.round(sc, 1) + np.float32(0.0)       # (+0.0: the kernels order by bit pattern, -0.0 below +0.0; the engine never emits -0.0)
             if metric == 1:
                 sc = np.abs(sc)
             order = np.lexsort((ids, -sc if metric == 0 else sc))

@@ -86,3 +86,63 @@ def test_results_do_not_depend_on_the_thread_schedule(host_emu, schedule):
             _exact(D, I, xq, xb, k, metric, rows=list(range(min(nq, 6))))
     finally:
         host_emu.emu_set_schedule(0)
+
+
+# ---- corpus row-sharded over several GPUs: threshold exchange through peer mailboxes (pq_mma.cu: ShareParams) ----------------
+def _merge_lists(Ds, Is, k, metric):
+    """numpy statement of pq_merge_shard_results: best first, ties to the lower id, -1 padding last."""
+    D = np.concatenate(Ds, axis=1)
+    I = np.concatenate(Is, axis=1)
+    Do, Io = np.empty((len(D), k), np.float32), np.empty((len(D), k), np.int64)
+    for q in range(len(D)):
+        valid = I[q] >= 0
+        order = np.lexsort((I[q], -D[q] if metric == 0 else D[q], ~valid))[:k]
+        Do[q], Io[q] = D[q, order], I[q, order]
+        pad = ~valid[order]
+        Do[q, pad] = oracle.FLT_MAX if metric == 1 else -oracle.FLT_MAX
+        Io[q, pad] = -1
+    return Do, Io
+
+
+@pytest.mark.parametrize("metric,nb,nq,k,R,ordered", [(0, 60_000, 9, 80, 2, False), (0, 90_000, 6, 100, 3, False), (1, 60_000, 7, 20, 4, False),
+                                                       (0, 80_000, 6, 100, 2, True), (0, 40_000, 5, 256, 2, False)])
+def test_row_shards_exchanging_thresholds_merge_to_the_exact_result(host_emu, metric, nb, nq, k, R, ordered):
+    """Every shard filters at what the shards know TOGETHER (max of the k-th best, min of the ceil(k/R)-th best local scores):
+    its list may hold fewer than k rows, but the merge of the lists is the exact global top-k.  The emulator runs the shards
+    one after the other, so in the first round shard r sees the final values of shards < r only (and nothing of the others:
+    the bounded wait runs out); in the second round (same sequence number) it sees every other shard's final values next to
+    its own early ones — the k-th-best rule bites when the shards differ (rows in document order), the ceil(k/R) rule needs
+    the shards in step, which only real GPUs give (tests/test_gpu_sharded.py)."""
+    if ordered:
+        rng = np.random.default_rng(21)
+        cent = rng.standard_normal((3, 128)).astype(np.float32)
+        lab = np.sort(rng.integers(0, 3, nb))
+        xb = (cent[lab] + 2.0 * rng.standard_normal((nb, 128))).astype(np.float32)
+        xq = (cent[rng.integers(0, 3, nq)] + 0.3 * rng.standard_normal((nq, 128))).astype(np.float32)
+    else:
+        xb, xq = data.corpus(nb), data.queries(nq)
+    Dr, Ir = oracle.engine_spec(xq, xb, k, metric)
+    bound = (float(harness.engine_norms(xb).max()), float(harness.resid2(xb).max()))     # maxima over the WHOLE corpus
+    cap_q = 64
+    boxes = [np.zeros(R * cap_q * 2 + R, np.uint64) for _ in range(R)]
+    per = (nb + R - 1) // R
+    tightened = 0
+    for rnd in range(2):
+        Ds, Is = [], []
+        for r in range(R):
+            lo, hi = r * per, min(nb, (r + 1) * per)
+            D, I, rerun, st = harness.run_host_emu(host_emu, xb[lo:hi], xq, k, metric, n_sms=6,
+                                                   share=(R, r, cap_q, 3, 77, lo, boxes), bound=bound)
+            assert rerun == []
+            Ds.append(D)
+            Is.append(I)
+            tightened += int((I == -1).any())
+        D, I = _merge_lists(Ds, Is, k, metric)
+        np.testing.assert_array_equal(I, Ir)
+        np.testing.assert_array_equal(D.view(np.uint32), Dr.view(np.uint32))
+    if ordered:
+        assert tightened > 0, "no shard ever used a peer's threshold (lists were all complete local top-k lists)"
+    # values of another search (a different sequence number) are ignored: a lone shard then returns its full local top-k
+    D, I, rerun, _ = harness.run_host_emu(host_emu, xb[:per], xq, k, metric, n_sms=6, share=(R, 0, cap_q, 3, 78, 0, boxes), bound=bound)
+    Dl, Il = oracle.engine_spec(xq, xb[:per], k, metric)
+    np.testing.assert_array_equal(I, Il)
