@@ -236,12 +236,14 @@ def build_shard(index, lo, hi, dev, sharded=None, n_global=None):
         del x, part
 
 
-def truth_topk_fp64(xq_dev, lo, hi, n_global, k, dev):
-    """fp64 ground truth for a query slice over rows [lo, hi) — checker only (torch matmul in float64)."""
+def truth_topk_fp64(xq_dev, lo, hi, n_global, k, dev, ids=None):
+    """fp64 ground truth for a query slice over rows [lo, hi) — checker only (torch matmul in float64).  With `ids` [nq, k] also
+    returns the fp64 score of every id that falls into [lo, hi) (0 elsewhere) — what the engine's answer is REALLY worth."""
     import torch
     q = xq_dev.double()
     best_d = torch.full((q.shape[0], k), -float("inf"), dtype=torch.float64, device=dev)
     best_i = torch.full((q.shape[0], k), -1, dtype=torch.int64, device=dev)
+    own = torch.zeros(ids.shape, dtype=torch.float64, device=dev) if ids is not None else None
     for c in range(lo // CHUNK, (hi + CHUNK - 1) // CHUNK):
         g = torch.Generator(device=dev)
         g.manual_seed(1234 + c)
@@ -254,30 +256,155 @@ def truth_topk_fp64(xq_dev, lo, hi, n_global, k, dev):
         cat_d, cat_i = torch.cat([best_d, d], 1), torch.cat([best_i, i], 1)
         top = torch.topk(cat_d, k, dim=1)
         best_d, best_i = top.values, torch.gather(cat_i, 1, top.indices)
+        if ids is not None:
+            inside = (ids >= c * CHUNK + a) & (ids < c * CHUNK + b)
+            loc = torch.where(inside, ids - (c * CHUNK + a), torch.zeros_like(ids))
+            own += torch.where(inside, torch.gather(s, 1, loc), torch.zeros_like(own))
         del x, s
-    return best_d, best_i
+    return best_d, best_i, own
 
 
-def parity_gate(D, I, Dt, It, rtol=1e-4):
-    """Scores within rtol of the fp64 truth position by position; ids equal except inside near-ties."""
+def parity_gate(D, I, Dt, It, own, rtol=1e-4):
+    """north_star tolerance, checked on what was RETURNED: (1) every reported score is within rtol of the fp64 score of the id
+    reported with it; (2) the fp64 scores of the returned ids are, rank by rank, within rtol of the true top-k scores (so the
+    set is the true top-k up to near-ties and the order is best-first up to near-ties); (3) where an id differs from the fp64
+    ranking, the gap between the two candidates' fp64 scores is reported (largest one: `max_near_tie_gap_rel`)."""
     import torch
     D64 = D.double()
     scale = torch.maximum(Dt.abs(), torch.full_like(Dt, 1e-3))
-    score_ok = bool(((D64 - Dt).abs() <= rtol * scale + 1e-6).all())
+    tol = rtol * scale + 1e-6
+    score_ok = bool(((D64 - own).abs() <= tol).all())
+    rank_ok = bool(((own - Dt).abs() <= tol).all())
     neq = I != It
     frac_equal = 1.0 - float(neq.double().mean())
-    # where ids differ the two candidates must be a near-tie: their fp64 scores (same rank) agree within tolerance
-    tie_ok = bool((((D64 - Dt).abs() <= rtol * scale + 1e-6) | ~neq).all())
-    # an id swap inside a near-tie is allowed by the north star; frac_equal only guards against wholesale disagreement
-    return score_ok and tie_ok and frac_equal > 0.98, frac_equal
+    gap = float((((own - Dt).abs() / scale) * neq.double()).max()) if bool(neq.any()) else 0.0
+    return score_ok and rank_ok, {"ids_equal_frac": frac_equal, "max_near_tie_gap_rel": gap, "scores_match_returned_ids": score_ok,
+                                   "returned_ids_are_topk_within_tol": rank_ok}
+
+
+def device_roofline(ix, run, flops_per_step, bytes_per_step, t_dev_hint, traffic_name=None):
+    """Dominant-kernel time from CUDA events around it on its launching stream (pq_index_set_profile), against the measured peaks."""
+    ix.set_profile(True)
+    kern_us = []
+    for _ in range(3):
+        run()
+        kern_us.append(ix.last_stats[7])
+    ix.set_profile(False)
+    st = ix.last_stats
+    kernel_s = float(np.mean(kern_us)) * 1e-6
+    peaks = load_peaks()
+    if st[3] > 0:
+        long_run = t_dev_hint > 1.0
+        peak = peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]
+        achieved = flops_per_step / kernel_s / 1e12 if kernel_s > 0 else 0.0
+        tr = load_traffic("pq_mma_filter_kernel") if traffic_name else None
+        return {"bound": "tensor", "kernel": "pq_mma_filter_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": tr,
+                "traffic_note": "archived ncu --set full capture of the last epoch of a C2 search (profiles/), not measured in this run" if tr else None,
+                "peak_source": f"{peaks['source']} cuBLAS bf16 ({'sustained' if long_run else 'burst'})",
+                "frac_of_burst": achieved / peaks["bf16_tflops"], "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
+                "algorithmic": "256 flop per (query,row) score",
+                "launches_per_step": int(st[3]), "kernel_ms_per_step": kernel_s * 1e3}
+    nbytes = bytes_per_step * max(1, st[2])
+    achieved = nbytes / kernel_s / 1e9 if kernel_s > 0 else 0.0
+    tr = load_traffic("pq_ffma_scan_kernel") if traffic_name else None
+    return {"bound": "hbm", "kernel": "pq_ffma_scan_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": tr,
+            "traffic_note": "archived ncu --set full capture of one scan over 21M rows (profiles/), not measured in this run" if tr else None,
+            "peak_source": f"{peaks['source']} copy bandwidth", "algorithmic": "512 B of corpus per row per pass",
+            "launches_per_step": int(st[2]), "kernel_ms_per_step": kernel_s * 1e3}
+
+
+def timed(stream, fn, steps, warmup):
+    """ms per call: CUDA events on the launching stream around `steps` calls, after `warmup` calls."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def sweep_lines(args, ix, dev, stream, N, local_rank):
+    """Driver-visible lines for the other tiers, on the resident corpus where possible (single GPU): S0 small-batch sweep
+    (north_star: >= 70 % of the HBM roofline), C1 (BASELINE configs[0]) and a slice of C4 (k-means assignment).  A few steps each."""
+    import torch
+    import proqa_b200 as pq
+    out = {}
+    peaks = load_peaks()
+    k = 80
+    for nq in (1, 4, 8, 16, 64, 256):
+        q = torch.from_numpy(host_queries(nq)).to(dev)
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        run = lambda: ix.search_device(q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr())  # noqa: E731
+        ms = timed(stream, run, 10, 3)
+        Dt, It, own = truth_topk_fp64(q, 0, N, N, k, dev, ids=I)
+        ok, _ = parity_gate(D, I, Dt, It, own)
+        rf = device_roofline(ix, run, 2.0 * nq * N * 128, 512.0 * N, 0.0)
+        # what the batch costs against streaming the corpus once: fp32 rows for the scan, the bf16 copy for the tensor tier
+        hbm_bytes = N * (512.0 if rf["bound"] == "hbm" else 256.0)
+        out[f"s0_nq{nq}"] = {"nq": nq, "rows": N, "k": k, "ms": ms, "queries_per_s": nq / ms * 1e3, "corpus_gbs_fp32_equiv": N * 512 / ms / 1e6,
+                             "tier": rf["bound"], "kernel_frac_of_its_roofline": rf["frac"],
+                             "step_frac_of_hbm": hbm_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "step_frac_of_hbm_note": "bytes the tier must stream once (fp32 rows: scan; bf16 copy: tensor tier) / whole-step time / measured copy bandwidth",
+                             "parity_ok": ok}
+    # C1: eval_retrieval.py shape, its own 1M-row index
+    wl = WORKLOADS["c1"]
+    c1 = pq.IndexFlatIP(128, local_rank)
+    build_shard(c1, 0, wl["rows"], dev, n_global=wl["rows"])
+    c1.set_stream(stream.cuda_stream)
+    q = torch.from_numpy(host_queries(wl["nq"])).to(dev)
+    D = torch.empty((wl["nq"], wl["k"]), dtype=torch.float32, device=dev)
+    I = torch.empty((wl["nq"], wl["k"]), dtype=torch.int64, device=dev)
+    run = lambda: c1.search_device(q.data_ptr(), wl["nq"], wl["k"], D.data_ptr(), I.data_ptr())  # noqa: E731
+    ms = timed(stream, run, 10, 3)
+    Dt, It, own = truth_topk_fp64(q[:256], 0, wl["rows"], wl["rows"], wl["k"], dev, ids=I[:256])
+    ok, _ = parity_gate(D[:256], I[:256], Dt, It, own)
+    rf = device_roofline(c1, run, 2.0 * wl["nq"] * wl["rows"] * 128, 512.0 * wl["rows"], 0.0)
+    out["c1"] = {"nq": wl["nq"], "rows": wl["rows"], "k": wl["k"], "ms": ms, "queries_per_s": wl["nq"] / ms * 1e3,
+                 "kernel_frac_of_its_roofline": rf["frac"], "tier": rf["bound"], "parity_ok": ok}
+    del c1, q, D, I
+    # C4 slice: 2M points against 10,000 centroids, k = 1, both metrics
+    g = torch.Generator(device=dev)
+    g.manual_seed(777)
+    cents = torch.randn((10_000, 128), generator=g, device=dev, dtype=torch.float32)
+    g.manual_seed(4321)
+    pts = torch.randn((2_000_000, 128), generator=g, device=dev, dtype=torch.float32)
+    for name, metric in (("c4_l2_2m", pq.METRIC_L2), ("c4_ip_2m", pq.METRIC_INNER_PRODUCT)):
+        km = pq.IndexFlat(128, metric, local_rank)
+        torch.cuda.synchronize()
+        km.add_device(cents.data_ptr(), 10_000)
+        km.set_stream(stream.cuda_stream)
+        D = torch.empty((len(pts), 1), dtype=torch.float32, device=dev)
+        I = torch.empty((len(pts), 1), dtype=torch.int64, device=dev)
+        run = lambda: km.search_device(pts.data_ptr(), len(pts), 1, D.data_ptr(), I.data_ptr())  # noqa: E731
+        ms = timed(stream, run, 5, 2)
+        p64, c64 = pts[:4096].double(), cents.double()
+        S = p64 @ c64.T
+        if metric == pq.METRIC_L2:
+            best, arg = ((p64 * p64).sum(1, keepdim=True) + (c64 * c64).sum(1)[None, :] - 2.0 * S).min(1)
+        else:
+            best, arg = S.max(1)
+        scale = torch.maximum(best.abs(), torch.full_like(best, 1e-3))
+        ok = bool(((D[:4096, 0].double() - best).abs() <= 1e-4 * scale + 1e-6).all()) and float((I[:4096, 0] == arg).double().mean()) > 0.995
+        rf = device_roofline(km, run, 2.0 * len(pts) * 10_000 * 128, 0.0, 0.0)
+        out[name] = {"points": len(pts), "centroids": 10_000, "k": 1, "ms": ms, "points_per_s": len(pts) / ms * 1e3,
+                     "kernel_frac_of_its_roofline": rf["frac"], "parity_ok": ok}
+        del km, D, I
+    return out
 
 
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
     import proqa_b200 as pq
-    from proqa_b200 import _lib
-    from proqa_b200.sharded import ShardedIndexFlat, shard_bounds
+    from proqa_b200.sharded import ShardedIndexFlat, auto_row_shards
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -289,164 +416,179 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-
     nq, N, k = wl["nq"], wl["rows"], wl["k"]
-    from proqa_b200.sharded import auto_row_shards
-    R = auto_row_shards(world, N) if args.row_shards in (None, "auto") else (world if args.row_shards == "rows" else int(args.row_shards))
-    sh = ShardedIndexFlat(128, pq.METRIC_INNER_PRODUCT, device=local_rank, row_shards=R)
-    lo, hi = sh.row_bounds(N)
-    qlo, qhi = sh.query_bounds(nq)
-    ix = sh.local
-    if args.tier:
-        ix.set_tier(args.tier)
-    t_build = time.perf_counter()
-    build_shard(ix, lo, hi, dev, sharded=sh, n_global=N)
-    sh._first_add, sh.ntotal = False, N
-    torch.cuda.synchronize()
-    t_build = time.perf_counter() - t_build
-
     stream = torch.cuda.current_stream()
-    ix.set_stream(stream.cuda_stream)
-
-    xq_host = torch.from_numpy(host_queries(nq)).pin_memory()
+    xq_np = host_queries(nq)                                   # pageable, as eval_retrieval.py:99 hands it over
+    xq_host = torch.from_numpy(xq_np).pin_memory()
     q = xq_host.to(dev)
-    D_loc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    I_loc = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    D_all = torch.empty((world, nq, k), dtype=torch.float32, device=dev) if world > 1 else None
-    I_all = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
-    D_out, I_out = torch.empty_like(D_loc), torch.empty_like(I_loc)
-    D_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    I_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
-
-    def step_device():
-        sh.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
-        return ix.last_stats[5] + (1 if world > 1 else 0)
-
-    def step_e2e():
-        if world == 1:
-            rc = _lib.lib().pq_index_search(ix._h, nq, ctypes.c_void_p(xq_host.data_ptr()), k, ctypes.c_void_p(D_host.data_ptr()),
-                                           ctypes.c_void_p(I_host.data_ptr()))
-            _lib.check(rc, "search")
-        else:
-            if rank == 0:
-                q.copy_(xq_host, non_blocking=True)
-            dist.broadcast(q, 0)
-            sh.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
-            if rank == 0:
-                D_host.copy_(D_out, non_blocking=True)
-                I_host.copy_(I_out, non_blocking=True)
-            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- parity gate: >= 256 queries against the fp64 ground truth (checker: torch float64) ---------
-    step_device()
-    torch.cuda.synchronize()
-    nchk = min(nq, 256)
-    Dt, It = truth_topk_fp64(q[:nchk], lo, hi, N, k, dev)
-    if world > 1:
-        Dt_all = torch.empty((world, nchk, k), dtype=torch.float64, device=dev)
-        It_all = torch.empty((world, nchk, k), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(Dt_all.view(world * nchk, k), Dt.contiguous())
-        dist.all_gather_into_tensor(It_all.view(world * nchk, k), It.contiguous())
-        # ranks 0..R-1 (query group 0) together hold every row shard exactly once
-        cat_d = Dt_all[:sh.R].permute(1, 0, 2).reshape(nchk, -1)
-        cat_i = It_all[:sh.R].permute(1, 0, 2).reshape(nchk, -1)
-        top = torch.topk(cat_d, k, dim=1)
-        Dt, It = top.values, torch.gather(cat_i, 1, top.indices)
-    parity_ok, frac_equal = parity_gate(D_out[:nchk], I_out[:nchk], Dt, It)
+    def max_over_ranks(t):
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return t
 
-    # ---- timed region: device-resident -------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    rerun_q = 0
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        launches += step_device()
-        rerun_q += ix.last_stats[1]
-    ev1.record(stream)
-    barrier()
-    t_dev = ev0.elapsed_time(ev1) / 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev = float(tt.item())
-
-    # ---- end to end: host buffers in, host buffers out ----------------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
-
-    # ---- phase breakdown of one multi-GPU step (CUDA events on the launching stream; diagnostic) ----
-    phases = None
-    if world > 1 and sh.Q == 1:
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        acc = [0.0, 0.0, 0.0]
-        for _ in range(3):
-            barrier()
-            evs[0].record(stream)
-            ix.search_device(q.data_ptr(), nq, k, D_loc.data_ptr(), I_loc.data_ptr())
-            evs[1].record(stream)
-            dist.all_gather_into_tensor(D_all.view(world * nq, k), D_loc)
-            dist.all_gather_into_tensor(I_all.view(world * nq, k), I_loc)
-            evs[2].record(stream)
-            sh._merge_device(D_all, I_all, nq, k, D_out, I_out)
-            evs[3].record(stream)
-            torch.cuda.synchronize()
-            for j in range(3):
-                acc[j] += evs[j].elapsed_time(evs[j + 1]) / 3.0
-        phases = {"local_search_ms": acc[0], "all_gather_ms": acc[1], "merge_ms": acc[2]}
-
-    # ---- dominant-kernel time (CUDA events around the kernel on its launching stream) --------------
-    ix.set_profile(True)
-    kern_us = []
-    for _ in range(3):
-        step_device()
-        kern_us.append(ix.last_stats[7])
-    ix.set_profile(False)
-    st = ix.last_stats
-    kernel_s = float(np.mean(kern_us)) * 1e-6
-    peaks = load_peaks()
-    local_rows = hi - lo
-    tensor_path = st[3] > 0
-    if tensor_path:
-        flops = 2.0 * (qhi - qlo) * local_rows * 128
-        long_run = t_dev > 1.0
-        peak = peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]
-        achieved = flops / kernel_s / 1e12 if kernel_s > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "pq_mma_filter_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": load_traffic("pq_mma_filter_kernel"),
-                    "peak_source": f"{peaks['source']} cuBLAS bf16 ({'sustained' if long_run else 'burst'})",
-                    "frac_of_burst": achieved / peaks["bf16_tflops"], "algorithmic": "256 flop per (query,row) score",
-                    "launches_per_step": int(st[3]), "kernel_ms_per_step": kernel_s * 1e3}
+    # layouts to measure: the requested one; with several GPUs and no explicit request, both pure row sharding (north_star (4))
+    # and the fewest-row-shards layout — the faster one is the headline, both are reported
+    if world == 1:
+        layouts = [1]
+    elif args.row_shards is None:
+        layouts = sorted({world, auto_row_shards(world, N)}, reverse=True)
     else:
-        nbytes = 512.0 * local_rows * max(1, st[2])
-        achieved = nbytes / kernel_s / 1e9 if kernel_s > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "pq_ffma_scan_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("pq_ffma_scan_kernel"),
-                    "peak_source": f"{peaks['source']} copy bandwidth", "algorithmic": "512 B of corpus per row per pass",
-                    "launches_per_step": int(st[2]), "kernel_ms_per_step": kernel_s * 1e3}
+        layouts = [auto_row_shards(world, N) if args.row_shards == "auto" else (world if args.row_shards == "rows" else int(args.row_shards))]
 
+    results = {}
+    for R in layouts:
+        sh = ShardedIndexFlat(128, pq.METRIC_INNER_PRODUCT, device=local_rank, row_shards=R)
+        lo, hi = sh.row_bounds(N)
+        qlo, qhi = sh.query_bounds(nq)
+        ix = sh.local
+        if args.tier:
+            ix.set_tier(args.tier)
+        t_build = time.perf_counter()
+        build_shard(ix, lo, hi, dev, sharded=sh, n_global=N)
+        sh._first_add, sh.ntotal = False, N
+        torch.cuda.synchronize()
+        t_build = time.perf_counter() - t_build
+        ix.set_stream(stream.cuda_stream)
+        D_loc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I_loc = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        D_all = torch.empty((world, nq, k), dtype=torch.float32, device=dev) if world > 1 else None
+        I_all = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
+        D_out, I_out = torch.empty_like(D_loc), torch.empty_like(I_loc)
+        D_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        I_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+
+        def step_device():
+            if world == 1:   # results land where the caller asked: no extra copy inside the timed region
+                ix.search_device(q.data_ptr(), nq, k, D_out.data_ptr(), I_out.data_ptr())
+            else:
+                sh.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
+            return ix.last_stats[5] + (1 if (world > 1 and sh.R > 1) else 0)
+
+        def step_e2e_numpy():
+            """The call the reference makes: index.search(pageable float32 array, k) -> new numpy (D, I)  (eval_retrieval.py:104)."""
+            return ix.search(xq_np, k) if world == 1 else sh.search(xq_np, k)
+
+        def step_e2e_pinned():
+            if world == 1:
+                rc = _libmod().lib().pq_index_search(ix._h, nq, ctypes.c_void_p(xq_host.data_ptr()), k, ctypes.c_void_p(D_host.data_ptr()),
+                                                     ctypes.c_void_p(I_host.data_ptr()))
+                _libmod().check(rc, "search")
+            else:
+                if rank == 0:
+                    q.copy_(xq_host, non_blocking=True)
+                dist.broadcast(q, 0)
+                sh.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
+                if rank == 0:
+                    D_host.copy_(D_out, non_blocking=True)
+                    I_host.copy_(I_out, non_blocking=True)
+                torch.cuda.synchronize()
+
+        # ---- parity gate: >= 256 queries against the fp64 ground truth (checker: torch float64) ---------
+        step_device()
+        torch.cuda.synchronize()
+        nchk = min(nq, 256 if k <= 1024 else 32)
+        contributes = sh.rq == 0                      # the ranks of query group 0 together hold every row exactly once
+        Dt, It, own = truth_topk_fp64(q[:nchk], lo, hi, N, k, dev, ids=I_out[:nchk])
+        if world > 1:
+            if not contributes:
+                own.zero_()
+            dist.all_reduce(own)
+            Dt_all = torch.empty((world, nchk, k), dtype=torch.float64, device=dev)
+            It_all = torch.empty((world, nchk, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(Dt_all.view(world * nchk, k), Dt.contiguous())
+            dist.all_gather_into_tensor(It_all.view(world * nchk, k), It.contiguous())
+            cat_d = Dt_all[:sh.R].permute(1, 0, 2).reshape(nchk, -1)
+            cat_i = It_all[:sh.R].permute(1, 0, 2).reshape(nchk, -1)
+            top = torch.topk(cat_d, k, dim=1)
+            Dt, It = top.values, torch.gather(cat_i, 1, top.indices)
+        parity_ok, parity_info = parity_gate(D_out[:nchk], I_out[:nchk], Dt, It, own)
+
+        # ---- timed region: device-resident -------------------------------------------------------------
+        for _ in range(args.warmup):
+            step_device()
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches, rerun_q, exchanges = 0, 0, 0
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            launches += step_device()
+            rerun_q += ix.last_stats[1]
+            exchanges += ix.last_stats[9]
+        ev1.record(stream)
+        barrier()
+        t_dev = max_over_ranks(ev0.elapsed_time(ev1) / 1e3)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- end to end: host buffers in, host buffers out ----------------------------------------------
+        e2e = {}
+        for name, fn in (("numpy_pageable", step_e2e_numpy), ("pinned", step_e2e_pinned)):
+            for _ in range(max(1, args.warmup // 2)):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fn()
+            barrier()
+            e2e[name] = max_over_ranks(time.perf_counter() - t0)
+
+        # ---- phase breakdown of one multi-GPU step (CUDA events on the launching stream; diagnostic) ----
+        phases = None
+        if world > 1:
+            n_loc = qhi - qlo
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            acc = [0.0, 0.0, 0.0, 0.0]
+            reps = 3
+            for _ in range(reps):
+                barrier()
+                sh._share_begin(n_loc)
+                evs[0].record(stream)
+                ix.search_device(q[qlo:qhi].data_ptr(), n_loc, k, D_loc.data_ptr(), I_loc.data_ptr())
+                evs[1].record(stream)
+                if sh.R > 1:
+                    Da = D_all.view(-1)[: sh.R * n_loc * k].view(sh.R * n_loc, k)
+                    Ia = I_all.view(-1)[: sh.R * n_loc * k].view(sh.R * n_loc, k)
+                    dist.all_gather_into_tensor(Da, D_loc[:n_loc], group=sh.row_group)
+                    dist.all_gather_into_tensor(Ia, I_loc[:n_loc], group=sh.row_group)
+                evs[2].record(stream)
+                if sh.R > 1:
+                    sh._merge_device(Da, Ia, n_loc, k, D_out[:n_loc], I_out[:n_loc])
+                evs[3].record(stream)
+                if sh.Q > 1:
+                    sh._gather_slices(D_loc[:n_loc], I_loc[:n_loc], nq, k)
+                evs[4].record(stream)
+                torch.cuda.synchronize()
+                for j in range(4):
+                    acc[j] += evs[j].elapsed_time(evs[j + 1]) / reps
+            phases = {"local_search_ms": max_over_ranks(acc[0]), "row_group_all_gather_ms": max_over_ranks(acc[1]),
+                      "merge_kernel_ms": max_over_ranks(acc[2]), "query_group_all_gather_ms": max_over_ranks(acc[3]),
+                      "local_search_launches": int(ix.last_stats[5]), "threshold_exchanges_in_time_per_search": int(ix.last_stats[9]),
+                      "note": "max over ranks of CUDA-event times on the launching stream, one step taken apart"}
+
+        roofline = device_roofline(ix, step_device, 2.0 * (qhi - qlo) * (hi - lo) * 128, 512.0 * (hi - lo), t_dev,
+                                   traffic_name=("c2" if (args.workload == "c2" and world == 1) else None))
+        results[R] = dict(R=R, Q=world // R, t_dev=t_dev, launches=launches, rerun_q=rerun_q, exchanges=exchanges, e2e=e2e, phases=phases,
+                          roofline=roofline, parity_ok=parity_ok, parity_info=parity_info, nchk=nchk, clocks=clocks, t_build=t_build,
+                          tensor_path=ix.last_stats[3] > 0)
+        if R != layouts[-1]:
+            del sh, ix, D_loc, I_loc, D_all, I_all, D_out, I_out
+            torch.cuda.empty_cache()
+
+    best = min(results.values(), key=lambda r: r["t_dev"] if r["parity_ok"] else float("inf"))
+    sweep = None
+    if world == 1 and args.workload == "c2" and not args.no_sweep and args.rows is None:
+        sweep = sweep_lines(args, ix, dev, stream, N, local_rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -459,41 +601,64 @@ def run_ours(args, wl):
         scratch = pq.IndexFlatIP(128, local_rank)
         scratch.add(xh[:1000])          # device init, allocations
         scratch.reset()
-        best = None
+        t_best = None
         for _ in range(2):
             scratch.reset()
             t0 = time.perf_counter()
             scratch.add(xh)
             dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        add_info = {"rows": rows_add, "seconds": best, "host_gbs": rows_add * 512 / best / 1e9,
+            t_best = dt if t_best is None else min(t_best, dt)
+        add_info = {"rows": rows_add, "seconds": t_best, "host_gbs": rows_add * 512 / t_best / 1e9,
                     "note": "pageable numpy array -> pinned double-buffered H2D + norms/bf16 preparation, per index.add call"}
         del scratch, xh
     cpu = cpu_baseline(wl) if (world == 1 and not args.no_cpu_baseline) else None
+    t_dev, parity_ok = best["t_dev"], best["parity_ok"]
     ms = t_dev / args.steps * 1e3
+    cfg = workload_config(args, wl)
+    if world > 1:
+        cfg["parallelism"] = f"{best['R']} row shards x {best['Q']} query groups"
+    t_e2e = best["e2e"]["numpy_pageable"]
     out = {
         "metric": "queries_per_sec", "value": (nq * args.steps / t_dev) if parity_ok else None, "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "bf16 filter + f32 rescoring" if tensor_path else "f32",
-        "data": "synthetic", "config": workload_config(args, wl),
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16 filter + f32 rescoring" if best["tensor_path"] else "f32",
+        "data": "synthetic", "config": cfg,
         "corpus_gbs": N * 512 * args.steps / t_dev / 1e9,
         "e2e": {"value": nq * args.steps / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * 512, "d2h_bytes_per_step": nq * k * 12,
-                "ms_per_step": t_e2e / args.steps * 1e3},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
+                "ms_per_step": t_e2e / args.steps * 1e3,
+                "call": "IndexFlat.search(pageable numpy float32 [nq,128], k) -> new numpy (D, I), as eval_retrieval.py:104 calls it"
+                        if world == 1 else "ShardedIndexFlat.search(pageable numpy queries, k) on every rank -> numpy (D, I)",
+                "pinned_buffers_ms_per_step": best["e2e"]["pinned"] / args.steps * 1e3},
+        "gpu_launches": int(best["launches"]),
+        "roofline": best["roofline"],
         "cpu_baseline": cpu,
-        "clocks": clocks,
-        "parity": {"queries_checked": nchk, "ok": parity_ok, "ids_equal_frac": frac_equal, "against": "fp64 brute force (torch, checker only)",
-                   "fp32_rerun_queries_per_step": rerun_q / max(1, args.steps)},
-        "index_build_s": t_build,
+        "clocks": best["clocks"],
+        "parity": dict(best["parity_info"], queries_checked=best["nchk"], ok=parity_ok, against="fp64 brute force (torch, checker only)",
+                       fp32_rerun_queries_per_step=best["rerun_q"] / max(1, args.steps)),
+        "index_build_s": best["t_build"],
         "index_add": add_info,
-        "multi_gpu_phases": phases,
+        "multi_gpu_phases": best["phases"],
     }
+    if world > 1:
+        out["layouts"] = {("rows" if r["R"] == world else f"R{r['R']}xQ{r['Q']}"): {
+            "row_shards": r["R"], "query_groups": r["Q"], "ms_per_step": r["t_dev"] / args.steps * 1e3,
+            "value": nq * args.steps / r["t_dev"] if r["parity_ok"] else None, "parity_ok": r["parity_ok"],
+            "e2e_ms_per_step": r["e2e"]["numpy_pageable"] / args.steps * 1e3, "phases": r["phases"],
+            "kernel_frac": r["roofline"]["frac"], "gpu_launches": int(r["launches"]),
+            "threshold_exchanges_in_time": int(r["exchanges"])} for r in results.values()}
+        out["layouts"]["headline"] = "rows" if best["R"] == world else f"R{best['R']}xQ{best['Q']}"
+    if sweep is not None:
+        out["sweep"] = sweep
     if not parity_ok:
         out["error"] = "parity gate failed: no speed reported"
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _libmod():
+    from proqa_b200 import _lib
+    return _lib
 
 
 def run_kmeans_assign(args, wl):
@@ -672,9 +837,11 @@ def main():
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--tier", default=None, choices=[None, "auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the S0 / C1 / C4 lines the default (c2, 1 GPU) run adds")
     ap.add_argument("--row-shards", default=None,
-                    help="multi-GPU layout: number of corpus row shards R (world = R x query groups); 'auto' (default) = fewest shards whose "
-                         "slice of the corpus fits the per-GPU budget, 'rows' = one shard per GPU (pure row sharding + NCCL merge)")
+                    help="multi-GPU layout: number of corpus row shards R (world = R x query groups); 'rows' = one shard per GPU (pure row "
+                         "sharding + NCCL merge, north_star (4)), 'auto' = fewest shards whose slice of the corpus fits the per-GPU budget; "
+                         "default: measure both, headline the faster, report both under \"layouts\"")
     ap.add_argument("--metric", default="l2", choices=["ip", "l2"], help="c4 only (group_paras.py default is L2; --spherical is IP)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

@@ -187,6 +187,25 @@ int pq_ipc_open(const void* handle64, int device, void** dev_ptr_out);
 int pq_ipc_close(int device, void* dev_ptr);
 int pq_enable_peer_access(int device, int peer_device);
 
+/* ---- one process, several GPUs (proqa_b200/csrc/pq_multi.cu) ------------------------------------------------------------
+ * The same four calls as above for an index spread over the GPUs of a box, driven from the single host process the reference
+ * runs in (eval_retrieval.py:102-104): the faiss shim creates one of these instead of a pq_index when PROQA_B200_DEVICES lists
+ * more than one device.  A first add() of more than 2^20 rows shards the rows contiguously over the devices (queries
+ * replicated, per-shard search with threshold exchange over peer memory, lists gathered and merged on the first device);
+ * a smaller first add() (k-means centroids, group_paras.py:49-51) replicates the rows and splits the QUERIES instead.
+ * ids are insertion order either way; -1 / -+FLT_MAX padding as pq_index_search. */
+typedef struct pq_multi pq_multi;
+int pq_multi_create(int d, int metric, int n_devices, const int* devices, pq_multi** out);
+void pq_multi_free(pq_multi* m);
+int pq_multi_add(pq_multi* m, int64_t n, const float* x_host);
+int pq_multi_search(pq_multi* m, int64_t nq, const float* xq_host, int64_t k, float* D_host, int64_t* I_host);
+int pq_multi_reset(pq_multi* m);
+int64_t pq_multi_ntotal(const pq_multi* m);
+int pq_multi_n_devices(const pq_multi* m);
+int pq_multi_mode(const pq_multi* m);            /* 0 empty, 1 rows sharded, 2 rows replicated */
+int pq_multi_last_stats(const pq_multi* m, int64_t* out, int n);   /* sums over the shards ([6], [7]: maxima) */
+pq_index* pq_multi_first_shard(pq_multi* m);     /* the shard on the first device (k-means training runs there) */
+
 /* "proqa_b200 <version> sm_100a" */
 const char* pq_version(void);
 

@@ -10,6 +10,7 @@ from .index import (METRIC_INNER_PRODUCT, METRIC_L2, IndexFlat, IndexFlatIP, Ind
 from .clustering import Clustering, ClusteringParameters, vector_float_to_array  # noqa: F401
 from ._lib import library_path, version  # noqa: F401
 from .idmap import IdMap  # noqa: F401
+from .multi import MultiGpuIndexFlat  # noqa: F401
 
 __all__ = ["IndexFlat", "IndexFlatIP", "IndexFlatL2", "METRIC_INNER_PRODUCT", "METRIC_L2", "library_path", "version",
-           "last_search_stats", "Clustering", "ClusteringParameters", "vector_float_to_array", "IdMap"]
+           "last_search_stats", "Clustering", "ClusteringParameters", "vector_float_to_array", "IdMap", "MultiGpuIndexFlat"]

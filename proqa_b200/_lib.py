@@ -58,6 +58,16 @@ SIGNATURES = {
     "pq_ipc_open": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(_vp)]),
     "pq_ipc_close": (ctypes.c_int, [ctypes.c_int, _vp]),
     "pq_enable_peer_access": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "pq_multi_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_vp)]),
+    "pq_multi_free": (None, [_vp]),
+    "pq_multi_add": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
+    "pq_multi_search": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, ctypes.c_int64, _vp, _vp]),
+    "pq_multi_reset": (ctypes.c_int, [_vp]),
+    "pq_multi_ntotal": (ctypes.c_int64, [_vp]),
+    "pq_multi_n_devices": (ctypes.c_int, [_vp]),
+    "pq_multi_mode": (ctypes.c_int, [_vp]),
+    "pq_multi_last_stats": (ctypes.c_int, [_vp, _i64p, ctypes.c_int]),
+    "pq_multi_first_shard": (_vp, [_vp]),
     "pq_kmeans_default_params": (None, [ctypes.POINTER(KMeansParams)]),
     "pq_kmeans_train": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.POINTER(KMeansParams), ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int64, _i64p]),
     "pq_rand_perm": (None, [ctypes.c_int64, ctypes.c_int64, _vp]),

@@ -41,14 +41,20 @@ class Clustering(ClusteringParameters):
         self.d, self.k = int(d), int(k)
         self.centroids = np.zeros(0, dtype=np.float32)   # faiss: std::vector<float>, k*d after training
         self.obj = np.zeros(0, dtype=np.float32)         # objective per iteration
+        self._own_result = None                          # the centroids array the last train() of this object produced
 
     def train(self, x, index):
-        assert isinstance(index, IndexFlat), "proqa_b200.Clustering trains on the engine's IndexFlatL2 / IndexFlatIP"
+        from .multi import MultiGpuIndexFlat
+        multi = index if isinstance(index, MultiGpuIndexFlat) else None
+        assert multi is not None or isinstance(index, IndexFlat), "proqa_b200.Clustering trains on the engine's IndexFlatL2 / IndexFlatIP"
+        handle = multi._first_shard_handle() if multi is not None else index._h
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2, "train expects a 2-D array"
         n, d = x.shape
         assert d == self.d, f"dimension mismatch: got {d}, clustering has {self.d}"
-        if self.frozen_centroids or len(self.centroids):
+        # FAISS treats centroids present before train() as input centroids.  ProQA never supplies any; what a previous train()
+        # of this object left there is simply replaced (training starts afresh).
+        if self.frozen_centroids or (len(self.centroids) and self.centroids is not self._own_result):
             raise NotImplementedError("proqa_b200.Clustering: input / frozen centroids are not supported (unused by ProQA)")
         prm = _lib.KMeansParams()
         _lib.lib().pq_kmeans_default_params(ctypes.byref(prm))
@@ -59,14 +65,19 @@ class Clustering(ClusteringParameters):
         cent = np.empty(self.k * self.d, dtype=np.float32)
         obj = np.zeros(max(1, prm.niter), dtype=np.float32)
         n_obj = ctypes.c_int64(0)
-        rc = _lib.lib().pq_kmeans_train(index._h, self.k, ctypes.byref(prm), n, x.ctypes.data, cent.ctypes.data, obj.ctypes.data, len(obj),
+        if multi is not None:
+            multi.reset()          # (the shard on the first device trains; the replicas are refilled below)
+        rc = _lib.lib().pq_kmeans_train(handle, self.k, ctypes.byref(prm), n, x.ctypes.data, cent.ctypes.data, obj.ctypes.data, len(obj),
                                         ctypes.byref(n_obj))
         if rc == -4:
             raise MemoryError(f"proqa_b200: Clustering.train failed ({rc}): {_lib.last_error()}")
         if rc != 0:   # FAISS_THROW_IF_NOT_* (too few points, NaN input) reaches Python as RuntimeError through the SWIG layer
             raise RuntimeError(f"proqa_b200: Clustering.train failed ({rc}): {_lib.last_error()}")
-        self.centroids = cent
+        self.centroids = self._own_result = cent
         self.obj = obj[:n_obj.value].copy()
+        if multi is not None:      # FAISS leaves the index holding the final centroids: on every GPU here
+            multi.reset()
+            multi.add(cent.reshape(self.k, self.d))
 
 
 def vector_float_to_array(v):

@@ -5,16 +5,19 @@
 // GEMM with K = 128.  This file runs it on the 5th-generation tensor cores and never writes the
 // score matrix:
 //
-//   pq_mma_filter_kernel  (one CTA per SM, warp-specialised, 320 threads)
+//   pq_mma_filter_kernel  (one CTA per SM, warp-specialised, 576 threads)
 //     warp 0      TMA producer: corpus tiles (128 rows x 256 B bf16, SWIZZLE_128B; L2 also the tile's 128 row norms)
 //                 through a 6-stage shared-memory ring, mbarrier completion
 //     warp 1      issues tcgen05.mma in the TS form: the stationary operand — up to 4 query tiles of 128 queries, written
 //                 once per CTA into tensor memory with tcgen05.st — times the streamed corpus tile from shared memory;
 //                 M=128 queries x N=128 rows x K=16, bf16 -> fp32, into two 128-column TMEM accumulators
-//     warps 2-9   epilogue, two sets of four warps (one warp per TMEM lane quarter): set h drains the 64 columns of row
-//                 half h of every accumulator (tcgen05.ld 32 lanes x 32 columns -> registers); one thread owns one
-//                 query (a TMEM lane), so the admission threshold is a register compare; survivors are appended to the
-//                 query's private candidate slab in global memory (warp-uniform votes + predicated stores)
+//     warps 2-17  epilogue, four sets of four warps (one warp per TMEM lane quarter): set h drains columns 32h..32h+31 of
+//                 every accumulator (tcgen05.ld 32 lanes x 32 columns -> registers); one thread owns one query (a TMEM
+//                 lane), so the admission threshold is a register compare; survivors are appended to the query's private
+//                 candidate slab in global memory (warp-uniform votes + predicated stores).  (Round 1 ran two sets of 64
+//                 columns: per accumulator a warp then needed ~140 instructions behind a tcgen05.ld round trip — longer
+//                 than the 540 cycles the tensor pipe takes for it, pipe 80 % busy; in the early epochs, where nearly every
+//                 32-column chunk has a survivor, the two warps per scheduler were issue-bound at 2.4x the steady time.)
 //   pq_epoch_select_kernel  folds the slabs of one epoch into a per-query carry list (top-K' by bf16 score, radix select)
 //                 and raises the query's admission threshold to  A_k - 2E
 //   pq_rescore_kernel       recomputes the carry list's scores with the engine's defined fp32 score, sorts, emits (D, I)
@@ -41,17 +44,19 @@ namespace pq {
 
 constexpr int kBM = 128;            // queries per M tile (TMEM lanes)
 constexpr int kBN = 128;            // corpus rows per B tile (one TMA stage)
-constexpr int kSubN = 64;           // accumulator columns (corpus rows) one epilogue warp set drains: half of a tile
+constexpr int kEpiWarps = PQ_EPI_WARPS;        // 4 TMEM lane quarters x kEpiSets column sets
+constexpr int kEpiSets = kEpiWarps / 4;
+constexpr int kSubN = kBN / kEpiSets;          // accumulator columns (corpus rows) one epilogue warp set drains
+constexpr int kSubChunks = kSubN / 32;         // 32-column register chunks per warp and accumulator
 constexpr int kStages = 6;          // B ring depth
 constexpr int kAccBufs = 2;         // TMEM accumulators of kBN = 128 columns (UMMA N = 128): one per (B tile, M tile), double-buffered
 constexpr int kTmemACol = kAccBufs * kBN;      // first TMEM column of the stationary query operand
 constexpr int kPanelBytes = 128 * 128;         // 128 rows x 128 B (64 bf16): one swizzle-128B K panel
 constexpr int kTileBytes = 2 * kPanelBytes;    // K = 128 -> two panels, 32 KB
 constexpr int kStageBytes = kTileBytes + 1024; // + the tile's 128 squared row norms (L2 only), padded to keep 1024-B alignment
-constexpr int kEpiWarps = 8;
 constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
 constexpr int kMaxMTiles = 4;       // 4 x 64 TMEM columns of bf16 queries + 2 x 128 columns of accumulators = 512
-static_assert(kBM == kPlanQueryTile && kBN == kPlanTileRows && kMaxMTiles == kPlanMaxMTiles, "pq_plan.h must describe this kernel");
+static_assert(kBM == kPlanQueryTile && kBN == kPlanTileRows && kMaxMTiles == kPlanMaxMTiles && kEpiSets == kPlanSubsPerSlice && (kEpiSets == 2 || kEpiSets == 4), "pq_plan.h must describe this kernel");
 
 
 struct MmaCtrl {
@@ -78,7 +83,7 @@ struct MmaParams {
     // the tiles owned, so every CTA carries the same number of (query tile x row tile) products)
     int base, rem, s1, s0;
     int cap;
-    int n_sub;               // candidate slabs per query = max(s1, s0) * 2 (one per epilogue warp set)
+    int n_sub;               // candidate slabs per query = max(s1, s0) * kEpiSets (one per epilogue warp set)
     int k1_adapt;
     // second attempt at an epoch ("repair", launched after the last epoch and only when some slab overflowed): only the
     // queries whose slabs overflowed in that epoch (redo[q] & redo_bit) take part, with their final thresholds
@@ -197,9 +202,9 @@ __device__ __forceinline__ void mma_filter32_k1(float (&v)[32], float& thr, floa
 }
 
 // Accumulator schedule shared by the MMA issuer and the epilogue.  For row tile t and query tile mi (< m) one accumulator
-// of 128 columns is produced, sequence number j = t*m + mi, in TMEM buffer j & 1 (use number j >> 1).  The eight epilogue
-// warps form two sets of four (one warp per TMEM lane quarter); set h drains columns h*64 .. h*64+63 (row half h of the
-// tile).  Every warp consumes every accumulator, in order — an mbarrier parity wait can only tell adjacent phases apart,
+// of 128 columns is produced, sequence number j = t*m + mi, in TMEM buffer j & 1 (use number j >> 1).  The epilogue
+// warps form kEpiSets sets of four (one warp per TMEM lane quarter); set h drains columns h*kSubN .. (h+1)*kSubN-1 (those rows
+// of the tile).  Every warp consumes every accumulator, in order — an mbarrier parity wait can only tell adjacent phases apart,
 // so a consumer must never be able to run two uses ahead of a buffer (a round-robin over four buffers whose consumers
 // changed from use to use aliased and hung).  N = 128 per instruction measured ~5 % faster end to end than two N = 64
 // accumulators per tile (half the instructions, half the reads of the stationary operand from tensor memory).
@@ -265,10 +270,10 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
 
     const int e = warp - 2;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
-    const int set = e >> 2;         // epilogue warp set (0/1); meaningless for warps 0 and 1
+    const int set = e >> 2;         // epilogue warp set (column range of every accumulator); meaningless for warps 0 and 1
     if (warp >= 2) {
         // ---- queries -> tensor memory: lane = query, 64 columns of packed bf16 pairs per query tile ----
-        for (int mi = set; mi < m; mi += 2) {
+        for (int mi = set; mi < m; mi += kEpiSets) {
             const uint4* src = reinterpret_cast<const uint4*>(p.q_bf16 + ((size_t)(mt0 + mi) * kBM + quarter * 32 + lane) * kDim);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemACol + mi * 64);
 #pragma unroll
@@ -344,16 +349,17 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         // per (query tile, thread) state in shared memory — threshold, 2E, slab fill — so the loop over query tiles
         // below needs no unrolling (each thread reads and writes only its own slots: no synchronisation)
         const int tid_e = (int)threadIdx.x - 64;
+        constexpr int kEpiThreads = kEpiWarps * 32;
         float* s_thr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctrl) + 256);
         float* s_2e = s_thr + kMaxMTiles * kEpiWarps * 32;
         uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_2e + kMaxMTiles * kEpiWarps * 32);
         const int lane_q = quarter * 32 + lane;
-        const int sub = slice * 2 + set;
+        const int sub = slice * kEpiSets + set;
         for (int mi = 0; mi < m; ++mi) {
             const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
-            s_thr[mi * 256 + tid_e] = (p.redo == nullptr || (p.redo[q] & p.redo_bit) != 0u) ? p.thr[q] : INFINITY;
-            s_2e[mi * 256 + tid_e] = p.two_e[q];
-            s_cnt[mi * 256 + tid_e] = 0;
+            s_thr[mi * kEpiThreads + tid_e] = (p.redo == nullptr || (p.redo[q] & p.redo_bit) != 0u) ? p.thr[q] : INFINITY;
+            s_2e[mi * kEpiThreads + tid_e] = p.two_e[q];
+            s_cnt[mi * kEpiThreads + tid_e] = 0;
         }
         const uint32_t row_end32 = (uint32_t)p.row_end;
         const uint32_t cap = (uint32_t)p.cap;
@@ -371,42 +377,42 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
                 mbar_wait(&ctrl->tmem_full[b], aph);
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kBN + set * kSubN);
-                float v0[32], v1[32];
-                tmem_ld_32x32(taddr, v0);
-                tmem_ld_32x32(taddr + 32, v1);
+                float v[kSubChunks][32];
+#pragma unroll
+                for (int c = 0; c < kSubChunks; ++c) tmem_ld_32x32(taddr + 32 * c, v[c]);
                 tmem_ld_wait();
                 // The accumulator is in registers now: hand the TMEM buffer back before filtering.
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);
                 if (kL2) {
-                    mma_apply_l2_bias(v0, norms);
-                    mma_apply_l2_bias(v1, norms + 8);
+#pragma unroll
+                    for (int c = 0; c < kSubChunks; ++c) mma_apply_l2_bias(v[c], norms + 8 * c);
                     if (mi == m - 1) {  // last read of this stage's norms by this warp
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&ctrl->empty[s]);
                     }
                 }
-                const int slot = mi * 256 + tid_e;
+                const int slot = mi * kEpiThreads + tid_e;
                 uint64_t* slab = p.cand_keys + (((size_t)(mt0 + mi) * kBM + lane_q) * p.n_sub + sub) * (size_t)cap;
                 uint32_t cnt = s_cnt[slot];
                 const uint32_t cnt_in = cnt;
                 float th = s_thr[slot];
                 if (kK1) {
                     const float two_e = s_2e[slot];
-                    mma_filter32_k1(v0, th, two_e, base_row, row_end32, slab, cnt, cap);
-                    mma_filter32_k1(v1, th, two_e, base_row + 32, row_end32, slab, cnt, cap);
+#pragma unroll
+                    for (int c = 0; c < kSubChunks; ++c) mma_filter32_k1(v[c], th, two_e, base_row + 32 * c, row_end32, slab, cnt, cap);
                     s_thr[slot] = th;
                 } else {
-                    mma_filter32(v0, th, base_row, row_end32, slab, cnt, cap);
-                    mma_filter32(v1, th, base_row + 32, row_end32, slab, cnt, cap);
+#pragma unroll
+                    for (int c = 0; c < kSubChunks; ++c) mma_filter32(v[c], th, base_row + 32 * c, row_end32, slab, cnt, cap);
                 }
                 if (cnt != cnt_in) s_cnt[slot] = cnt;
             }
         }
         for (int mi = 0; mi < m; ++mi) {
             const size_t q = (size_t)(mt0 + mi) * kBM + lane_q;
-            p.cand_cnt[q * p.n_sub + sub] = s_cnt[mi * 256 + tid_e];
+            p.cand_cnt[q * p.n_sub + sub] = s_cnt[mi * kEpiThreads + tid_e];
         }
     }
 
@@ -556,7 +562,7 @@ struct EpochSelParams {
 // slabs the filter kernel wrote for query q
 __device__ __forceinline__ int sel_slabs_of_query(const EpochSelParams& p, int q) {
     const int mt = q / kPlanQueryTile;
-    return 2 * (mt < p.rem * (p.base + 1) ? p.s1 : p.s0);
+    return kPlanSubsPerSlice * (mt < p.rem * (p.base + 1) ? p.s1 : p.s0);
 }
 
 // One CTA per query (any K'): carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
@@ -790,7 +796,7 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
 //   only if more than K' reach it is the exact top-K' taken and the best dropped score remembered for the certificate.
 // The carry is left unsorted (a compacted prefix): nothing downstream needs its order.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSelWarpPool = 1024;
+constexpr int kSelWarpPool = 704;   // keys per warp: 8 x (704 x 8 + 1024) B = 53 KB per CTA, four CTAs = 32 query warps per SM
 constexpr int kSelWarps = 8;
 
 __device__ __forceinline__ int warp_sum(int v) {
@@ -954,9 +960,26 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(co
         if (total == 0) continue;
         if (fill + total > kSelWarpPool && fill > p.kp) fill = warp_sel_reduce(p, pool, fill, w, hist, lane);
         if (fill + total <= kSelWarpPool) {
-            const uint64_t* src = keys + (size_t)s * p.cap;
-            uint64_t* dst = pool + fill + incl - c;
-            for (int i = 0; i < c; ++i) dst[i] = src[i];
+            // warp-wide copies, four slabs in flight (a lane copying its own slab serialises one global round trip per entry)
+            const int off = fill + incl - c;
+            for (int j0 = 0; j0 < 32 && s0 + j0 < n_sub; j0 += 4) {
+                int cj[4], oj[4];
+                uint64_t val[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    cj[u] = __shfl_sync(0xffffffffu, c, (j0 + u) & 31);
+                    oj[u] = __shfl_sync(0xffffffffu, off, (j0 + u) & 31);
+                }
+                const int longest = max(max(cj[0], cj[1]), max(cj[2], cj[3]));
+                for (int i = lane; i < longest; i += 32) {   // (warp-uniform bound: lanes beyond a slab's count just skip it)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i < cj[u]) val[u] = keys[(size_t)(s0 + j0 + u) * p.cap + i];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i < cj[u]) pool[oj[u] + i] = val[u];
+                }
+            }
             fill += total;
             __syncwarp();
         } else {  // 32 slabs hold more than the pool has room for (rows in document order): slab by slab, warp-wide copies
@@ -1306,9 +1329,15 @@ static cudaError_t launch_filter_any(int m_max, bool l2, bool k1, const CUtensor
     return k1 ? launch_filter_m<false, true>(m_max, tc, p, n_ctas, device, stream) : launch_filter_m<false, false>(m_max, tc, p, n_ctas, device, stream);
 }
 
-// Epoch select and rescoring: one warp per query while the carry list fits a warp's pool (K' <= 256), one CTA per query beyond.
+// Epoch select and rescoring: one warp per query when the carry list fits a warp's pool (K' <= 256) and there are enough
+// queries to fill the GPU with warps (1024; PROQA_B200_SELECT_WARP_MIN overrides — the CPU tests run both kernels on small
+// batches through it); one CTA per query otherwise: eight warps on one list finish a lone list sooner.
+static int sel_warp_min_queries() {
+    const char* s = getenv("PROQA_B200_SELECT_WARP_MIN");
+    return (s && *s) ? atoi(s) : 1024;
+}
 static cudaError_t launch_epoch_select(const EpochSelParams& sp, int device, cudaStream_t stream) {
-    if (sp.kp <= 256) {
+    if (sp.kp <= 256 && sp.nq >= sel_warp_min_queries()) {
         const size_t smem = (size_t)kSelWarps * (kSelWarpPool * 8 + 256 * 4);
         cudaError_t e = ensure_dyn_smem(pq_epoch_select_warp_kernel, smem, device);
         if (e != cudaSuccess) return e;
@@ -1322,7 +1351,7 @@ static cudaError_t launch_epoch_select(const EpochSelParams& sp, int device, cud
     return cudaGetLastError();
 }
 static cudaError_t launch_rescore(const RescoreParams& rp, int device, cudaStream_t stream) {
-    if (rp.kp <= 256) {
+    if (rp.kp <= 256 && rp.nq >= sel_warp_min_queries()) {
         const size_t smem = (size_t)kSelWarps * rp.kp * 8;
         pq_rescore_warp_kernel<<<(rp.nq + kSelWarps - 1) / kSelWarps, kSelWarps * 32, smem, stream>>>(rp);
     } else {
@@ -1596,7 +1625,7 @@ extern "C" int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms
     out[4] = gs.m_max;
     out[5] = carry_size_for_k((int)k);
     out[6] = nq_pad;
-    out[7] = 0;
+    out[7] = gs.subs_per_slice;
     for (size_t e = 0; e < plan.size(); ++e) {
         int64_t* o = out + 8 + 8 * e;
         o[0] = plan[e].begin;

@@ -13,6 +13,10 @@ namespace pq {
 constexpr int kPlanTileRows = 128;   // corpus rows per B tile (= kBN in pq_mma.cu)
 constexpr int kPlanQueryTile = 128;  // queries per M tile (= kBM)
 constexpr int kPlanMaxMTiles = 4;    // query tiles one CTA keeps in tensor memory (= kMaxMTiles)
+#ifndef PQ_EPI_WARPS
+#define PQ_EPI_WARPS 16              // epilogue warps of the filter kernel: 4 TMEM lane quarters x (PQ_EPI_WARPS / 4) column sets
+#endif
+constexpr int kPlanSubsPerSlice = PQ_EPI_WARPS / 4;  // every epilogue warp set (a column range of each row tile) keeps its own slab
 
 struct EpochPlan {
     long long begin, end;
@@ -39,7 +43,7 @@ inline GridShape make_grid_shape(int n_mtiles) {
     gs.base = n_mtiles / gs.n_groups;
     gs.rem = n_mtiles % gs.n_groups;
     gs.m_max = gs.base + (gs.rem ? 1 : 0);
-    gs.subs_per_slice = 2;  // the two epilogue warp sets (row halves of every tile) keep separate slabs
+    gs.subs_per_slice = kPlanSubsPerSlice;  // the epilogue warp sets (column ranges of every row tile) keep separate slabs
     return gs;
 }
 
@@ -89,7 +93,7 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
         ep.begin = 0;
         ep.end = N;
         pick_slices(gs, n_mtiles, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
-        ep.cap = 64;  // a thread keeps only rows within 2E of its running maximum: a few dozen at most
+        ep.cap = 128 / gs.subs_per_slice;  // a thread keeps only rows within 2E of its running maximum: a few dozen at most
         plan.push_back(ep);
         return plan;
     }
@@ -115,7 +119,8 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
             // bring whole clusters above the threshold at once — beyond the provision the epoch is run a second time)
             const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
             const double expect = 1.5 * (double)k * ((double)(ep.end - ep.begin) / (double)ep.begin) / slabs / share_f;
-            ep.cap = std::min(4096, std::max(64, plan_next_pow2((int)(3.0 * expect) + 64)));
+            const int floor_cap = 128 / gs.subs_per_slice;  // (the same slab memory per slice whatever the number of warp sets)
+            ep.cap = std::min(4096, std::max(floor_cap, plan_next_pow2((int)(3.0 * expect) + floor_cap)));
         }
         plan.push_back(ep);
         begin = ep.end;
@@ -157,7 +162,7 @@ inline EpochPlan plan_large_k_pass(long long N, int k, int nq_pad, const GridSha
     pick_slices(gs, nq_pad / kPlanQueryTile, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
     const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
     const double expect = 2.2 * (double)k / slabs;
-    ep.cap = std::min(65536, std::max(64, plan_next_pow2((int)(3.0 * expect) + 64)));
+    ep.cap = std::min(65536, std::max(128 / gs.subs_per_slice, plan_next_pow2((int)(3.0 * expect) + 128 / gs.subs_per_slice)));
     return ep;
 }
 // Large enough a corpus for the sample to mean something; otherwise the fp32 scan answers.

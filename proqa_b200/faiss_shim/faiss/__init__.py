@@ -19,7 +19,29 @@ _ROOT = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.
 if _ROOT not in _sys.path:
     _sys.path.insert(0, _ROOT)
 
-from proqa_b200.index import METRIC_INNER_PRODUCT, METRIC_L2, IndexFlat, IndexFlatIP, IndexFlatL2  # noqa: E402,F401
+from proqa_b200 import index as _index  # noqa: E402
+from proqa_b200.index import METRIC_INNER_PRODUCT, METRIC_L2, IndexFlat  # noqa: E402,F401
+from proqa_b200.multi import MultiGpuIndexFlat, make_index as _make_index  # noqa: E402,F401
+
+
+class IndexFlatIP(_index.IndexFlatIP):
+    """faiss.IndexFlatIP(d): one GPU — or, with PROQA_B200_DEVICES=0,1,... (or "all"), every named GPU of the box behind the
+    same object (proqa_b200/multi.py), so that the unmodified scripts scale without a launcher."""
+    def __new__(cls, d, *args):
+        if not args and cls is IndexFlatIP:
+            ix = _make_index(d, METRIC_INNER_PRODUCT)
+            if isinstance(ix, MultiGpuIndexFlat):
+                return ix
+        return super().__new__(cls)
+
+
+class IndexFlatL2(_index.IndexFlatL2):
+    def __new__(cls, d, *args):
+        if not args and cls is IndexFlatL2:
+            ix = _make_index(d, METRIC_L2)
+            if isinstance(ix, MultiGpuIndexFlat):
+                return ix
+        return super().__new__(cls)
 from proqa_b200.clustering import Clustering, ClusteringParameters, vector_float_to_array, vector_to_array  # noqa: E402,F401
 
 __version__ = "1.6.3+proqa_b200"

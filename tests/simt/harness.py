@@ -100,7 +100,7 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
         extract(mma, "int sel_slabs_of_query(const EpochSelParams& p, int q)"),
         extract(mma, "uint64_t block_radix_select(const uint64_t* pool"),
         extract(mma, "pq_epoch_select_kernel(const EpochSelParams p)"),
-        extract(mma, "constexpr int kSelWarpPool = 1024;", upto="constexpr int kSelWarps = 8;"),
+        extract(mma, "constexpr int kSelWarpPool = 704;", upto="constexpr int kSelWarps = 8;"),
         extract(mma, "int warp_sum(int v)"),
         extract(mma, "uint64_t warp_radix_select(const uint64_t* pool, int n, int want, int* hist, int lane)"),
         extract(mma, "struct WarpSelState {"),
@@ -116,6 +116,7 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
     ])
     host = (extract(mma, "static int next_pow2i(int v)") + extract(mma, "static cudaError_t ensure_dyn_smem_impl(const void* fn")
             + extract(mma, "static cudaError_t ensure_dyn_smem(K* kernel, size_t smem, int device)")
+            + extract(mma, "static int sel_warp_min_queries()")
             + extract(mma, "static cudaError_t launch_epoch_select(const EpochSelParams& sp")
             + extract(mma, "static cudaError_t launch_rescore(const RescoreParams& rp")
             + extract(mma, "static ShareParams make_share_params(const pq_index* ix")

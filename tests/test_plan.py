@@ -8,6 +8,17 @@ import pytest
 N_SMS = 148
 
 
+def _sets():
+    """Candidate slabs per row slice = epilogue warp sets of the filter kernel (out[7] of pq_plan_describe)."""
+    from proqa_b200 import _lib
+    out = (ctypes.c_int64 * 64)()
+    assert _lib.lib().pq_plan_describe(100000, 8, 10, N_SMS, out, len(out)) == 0
+    return int(out[7])
+
+
+SETS = _sets()
+
+
 def plan(ntotal, nq, k, n_sms=N_SMS):
     from proqa_b200 import _lib
     out = (ctypes.c_int64 * (8 + 8 * 64))()
@@ -39,15 +50,15 @@ def test_plan_invariants(ntotal, nq, k):
         tiles = -(-(ep["end"] - ep["begin"]) // 128)
         assert 1 <= ep["s1"] <= tiles and 1 <= ep["s0"] <= tiles, "never more slices than row tiles"
         assert ep["ctas"] == head["rem"] * ep["s1"] + (head["groups"] - head["rem"]) * ep["s0"] >= 1
-        assert ep["n_sub"] == 2 * max(ep["s1"], ep["s0"])
-        assert 64 <= ep["cap"] <= 4096 and ep["cap"] & (ep["cap"] - 1) == 0
+        assert ep["n_sub"] == SETS * max(ep["s1"], ep["s0"])
+        assert 128 // SETS <= ep["cap"] <= 4096 and ep["cap"] & (ep["cap"] - 1) == 0
         if ep["begin"] > 0:  # epoch boundaries are multiples of a tile, so a tile never straddles two epochs
             assert ep["begin"] % 128 == 0
         if k > 1 and i == 0:  # bootstrap: every score is a survivor, the slabs must hold a whole row half each
-            assert ep["s1"] == ep["s0"] == tiles and ep["cap"] == 64
+            assert ep["s1"] == ep["s0"] == tiles and ep["cap"] == 128 // SETS
         if k > 1 and i > 0:   # provision: at least twice the survivors expected on exchangeable rows (1.5 k (end/begin - 1))
             expect = 1.5 * k * (ep["end"] - ep["begin"]) / ep["begin"]
-            assert ep["cap"] * 2 * min(ep["s1"], ep["s0"]) >= min(2 * expect, 4096 * 2 * min(ep["s1"], ep["s0"]))
+            assert ep["cap"] * SETS * min(ep["s1"], ep["s0"]) >= min(2 * expect, 4096 * SETS * min(ep["s1"], ep["s0"]))
         # the candidate slabs of one pass stay far below a B200's 180 GB
         assert head["nq_pad"] * ep["n_sub"] * ep["cap"] * 8 <= 48e9
     if k == 1:
@@ -103,8 +114,8 @@ def test_large_k_plan_invariants(ntotal, nq, k):
     assert p["pool"] >= p["sort_n"] and p["pool"] >= min(2 * k, 24576)
     assert p["finalize_smem"] + 2048 <= 227 * 1024
     # single pass: slabs provisioned for at least 3 x 2.2 k survivors per query, and a batch's slabs stay modest
-    assert p["n_sub"] == 2 * max(p["s1"], p["s0"]) and p["cap"] & (p["cap"] - 1) == 0
-    assert p["cap"] * 2 * min(p["s1"], p["s0"]) >= 6.6 * k
+    assert p["n_sub"] == SETS * max(p["s1"], p["s0"]) and p["cap"] & (p["cap"] - 1) == 0
+    assert p["cap"] * SETS * min(p["s1"], p["s0"]) >= 6.6 * k
     assert p["slab_bytes"] <= 16e9
     if p["applies"]:
         assert p["sample_rows"] >= 16 * p["k_sample"] and p["sample_epochs"] >= 2

@@ -17,9 +17,18 @@ from tests.simt import harness
 pytestmark = pytest.mark.timeout(600)   # an emulated kernel that never finishes must not hang the suite
 
 
-@pytest.fixture(scope="module")
-def host_emu(tmp_path_factory):
-    return harness.build_host_emu(tmp_path_factory.mktemp("simt_host"))
+@pytest.fixture(scope="module", params=["warp_per_query", "cta_per_query"])
+def host_emu(request, tmp_path_factory):
+    """Both selection / rescoring kernel families: one warp per query (what large batches use: K' <= 256 and >= 1024 queries)
+    and one CTA per query (small batches, large K')."""
+    import os
+    old = os.environ.get("PROQA_B200_SELECT_WARP_MIN")
+    os.environ["PROQA_B200_SELECT_WARP_MIN"] = "1" if request.param == "warp_per_query" else "1000000000"
+    yield harness.build_host_emu(tmp_path_factory.mktemp("simt_host_" + request.param))
+    if old is None:
+        os.environ.pop("PROQA_B200_SELECT_WARP_MIN", None)
+    else:
+        os.environ["PROQA_B200_SELECT_WARP_MIN"] = old
 
 
 def _exact(D, I, xq, xb, k, metric, rows=None):
