@@ -19,6 +19,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <random>
 #include <vector>
@@ -147,6 +149,44 @@ static double now_s() {
 
 // split_clusters (Clustering.cpp, v1.6.3) — the treatment of void clusters (host; touches only the few affected rows).
 // FAISS keeps the cluster sizes as floats there: a split halves a size as a float, which feeds the probabilities of later splits.
+// Host-side helpers of Clustering::train's input handling, spread over a few threads: the finite check reads the whole
+// training matrix (10.75 GB for the 21M paragraph embeddings), the subsample gather copies 5 GB of scattered rows.
+static int host_threads_for(int64_t work_items, int64_t per_thread_min) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(hw, 16u), work_items / std::max<int64_t>(1, per_thread_min)));
+}
+static bool all_finite_parallel(const float* x, int64_t n) {
+    const int nt = host_threads_for(n, 1 << 22);
+    std::atomic<bool> ok(true);
+    auto scan = [&](int64_t a, int64_t b) {
+        // a value is finite iff its exponent field is not all ones; OR-reduce a block at a time, stop early once something is found
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(x);
+        for (int64_t i = a; i < b && ok.load(std::memory_order_relaxed); i += 4096) {
+            const int64_t e = std::min(b, i + 4096);
+            bool bad = false;
+            for (int64_t j = i; j < e; ++j) bad |= (u[j] & 0x7f800000u) == 0x7f800000u;
+            if (bad) ok.store(false, std::memory_order_relaxed);
+        }
+    };
+    std::vector<std::thread> th;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) th.emplace_back(scan, std::min(n, per * t), std::min(n, per * (t + 1)));
+    scan(0, std::min(n, per));
+    for (std::thread& t : th) t.join();
+    return ok.load();
+}
+static void gather_rows_parallel(float* dst, const float* x, const int* rows, int64_t n) {
+    const int nt = host_threads_for(n, 1 << 13);
+    auto work = [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) memcpy(dst + (size_t)i * kDim, x + (size_t)rows[i] * kDim, sizeof(float) * kDim);
+    };
+    std::vector<std::thread> th;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, std::min(n, per * t), std::min(n, per * (t + 1)));
+    work(0, std::min(n, per));
+    for (std::thread& t : th) t.join();
+}
+
 static int split_void_clusters(std::vector<float>& cent, const std::vector<int>& counts, int64_t k, int64_t n) {
     const float EPS = 1.f / 1024.f;
     int nsplit = 0;
@@ -182,8 +222,7 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
     if (k < 1 || n_in < k) return set_error(PQ_ERR_INVALID, "Number of training points (%lld) should be at least as large as number of clusters (%lld)",
                                             (long long)n_in, (long long)k);
     if (k > (1 << 24) || n_in > 0x7fffff00LL) return set_error(PQ_ERR_UNSUPPORTED, "kmeans: k or n too large");
-    for (int64_t i = 0; i < n_in * kDim; ++i)
-        if (!std::isfinite(x_host[i])) return set_error(PQ_ERR_INVALID, "input contains NaN's or Inf's");
+    if (!all_finite_parallel(x_host, n_in * kDim)) return set_error(PQ_ERR_INVALID, "input contains NaN's or Inf's");
     int rc = index_init_device(ix);
     if (rc) return rc;
     PQ_CUDA(cudaSetDevice(ix->device));
@@ -193,48 +232,16 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
     // ---- subsample (Clustering::train: "Sampling a subset of %ld / %ld for training") ----
     int64_t nx = n_in;
     std::vector<int> perm;
-    DevBuf d_x;
-    const int64_t max_train = k * (int64_t)prm.max_points_per_centroid;
-    if (n_in > max_train) {
-        if (prm.verbose) printf("Sampling a subset of %ld / %ld for training\n", (long)max_train, (long)n_in);
-        rand_perm(perm, (size_t)n_in, prm.seed);
-        nx = max_train;
-    } else if (n_in < k * (int64_t)prm.min_points_per_centroid) {
-        fprintf(stderr, "WARNING clustering %ld points to %ld centroids: please provide at least %ld training points\n", (long)n_in, (long)k,
-                (long)(k * (int64_t)prm.min_points_per_centroid));
-    }
-    rc = d_x.ensure((size_t)nx * kDim * 4);
-    if (rc) return rc;
-    if (n_in > max_train) {  // gather on the host in chunks (the full matrix may not fit beside the index), copy each chunk
-        const int64_t chunk = 1 << 20;
-        std::vector<float> buf((size_t)std::min(chunk, nx) * kDim);
-        for (int64_t a = 0; a < nx; a += chunk) {
-            const int64_t b = std::min(nx, a + chunk);
-            for (int64_t i = a; i < b; ++i) memcpy(&buf[(size_t)(i - a) * kDim], x_host + (size_t)perm[i] * kDim, sizeof(float) * kDim);
-            PQ_CUDA(cudaMemcpyAsync((float*)d_x.p + (size_t)a * kDim, buf.data(), (size_t)(b - a) * kDim * 4, cudaMemcpyHostToDevice, st));
-            PQ_CUDA(cudaStreamSynchronize(st));
-        }
-    } else {
-        PQ_CUDA(cudaMemcpyAsync(d_x.p, x_host, (size_t)nx * kDim * 4, cudaMemcpyHostToDevice, st));
-    }
-    const float* dx = (const float*)d_x.p;
-
-    if (nx == k) {  // "Number of training points same as number of clusters, just copying"
-        PQ_CUDA(cudaMemcpyAsync(centroids_out, dx, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
-        PQ_CUDA(cudaStreamSynchronize(st));
-        rc = index_reset_locked(ix);
-        if (!rc) rc = index_add_locked(ix, k, dx, true);
-        d_x.release();
-        if (n_obj) *n_obj = 0;
-        return rc;
-    }
-    if (prm.verbose)
-        printf("Clustering %d points in %dD to %ld clusters, redo %d times, %d iterations\n", (int)nx, kDim, (long)k, prm.nredo, prm.niter);
-
-    DevBuf d_cent, d_D, d_I, d_keys, d_keys2, d_vals, d_vals2, d_hist, d_off, d_tmp, d_part, d_perm;
+    // every device buffer of this call is released on every way out (an error half-way must not strand gigabytes)
+    DevBuf d_x, d_cent, d_D, d_I, d_keys, d_keys2, d_vals, d_vals2, d_hist, d_off, d_tmp, d_part, d_perm;
+    void* pinned[2] = {nullptr, nullptr};
     auto release = [&]() {
         DevBuf* all[] = {&d_x, &d_cent, &d_D, &d_I, &d_keys, &d_keys2, &d_vals, &d_vals2, &d_hist, &d_off, &d_tmp, &d_part, &d_perm};
         for (DevBuf* b : all) b->release();
+        for (void*& h : pinned) {
+            if (h) cudaFreeHost(h);
+            h = nullptr;
+        }
     };
 #define KM_TRY(expr)              \
     do {                          \
@@ -252,6 +259,59 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
             return cuda_fail(_e, __FILE__, __LINE__);     \
         }                                                 \
     } while (0)
+    const int64_t max_train = k * (int64_t)prm.max_points_per_centroid;
+    if (n_in > max_train) {
+        if (prm.verbose) printf("Sampling a subset of %ld / %ld for training\n", (long)max_train, (long)n_in);
+        rand_perm(perm, (size_t)n_in, prm.seed);
+        nx = max_train;
+    } else if (n_in < k * (int64_t)prm.min_points_per_centroid) {
+        fprintf(stderr, "WARNING clustering %ld points to %ld centroids: please provide at least %ld training points\n", (long)n_in, (long)k,
+                (long)(k * (int64_t)prm.min_points_per_centroid));
+    }
+    KM_TRY(d_x.ensure((size_t)nx * kDim * 4));
+    if (n_in > max_train) {
+        // The subsample (group_paras.py defaults: 10M of 21M rows, 5 GB) is gathered by host threads into two pinned buffers
+        // that alternate between being filled and being copied: the gather of chunk i+1 overlaps the H2D copy of chunk i.
+        const int64_t chunk = 1 << 17;  // 64 MB
+        cudaEvent_t copied[2] = {nullptr, nullptr};
+        for (int i = 0; i < 2; ++i) {
+            KM_CUDA(cudaMallocHost(&pinned[i], (size_t)chunk * kDim * 4));
+            KM_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        }
+        cudaError_t ge = cudaSuccess;
+        int which = 0;
+        for (int64_t a = 0; a < nx && ge == cudaSuccess; a += chunk, which ^= 1) {
+            const int64_t b = std::min(nx, a + chunk);
+            ge = cudaEventSynchronize(copied[which]);
+            if (ge != cudaSuccess) break;
+            gather_rows_parallel((float*)pinned[which], x_host, perm.data() + a, b - a);
+            ge = cudaMemcpyAsync((float*)d_x.p + (size_t)a * kDim, pinned[which], (size_t)(b - a) * kDim * 4, cudaMemcpyHostToDevice, st);
+            if (ge == cudaSuccess) ge = cudaEventRecord(copied[which], st);
+        }
+        if (ge == cudaSuccess) ge = cudaStreamSynchronize(st);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(copied[i]);
+        KM_CUDA(ge);
+        for (void*& h : pinned) {
+            cudaFreeHost(h);
+            h = nullptr;
+        }
+    } else {
+        KM_CUDA(cudaMemcpyAsync(d_x.p, x_host, (size_t)nx * kDim * 4, cudaMemcpyHostToDevice, st));
+    }
+    const float* dx = (const float*)d_x.p;
+
+    if (nx == k) {  // "Number of training points same as number of clusters, just copying"
+        KM_CUDA(cudaMemcpyAsync(centroids_out, dx, (size_t)k * kDim * 4, cudaMemcpyDeviceToHost, st));
+        KM_CUDA(cudaStreamSynchronize(st));
+        rc = index_reset_locked(ix);
+        if (!rc) rc = index_add_locked(ix, k, dx, true);
+        release();
+        if (n_obj) *n_obj = 0;
+        return rc;
+    }
+    if (prm.verbose)
+        printf("Clustering %d points in %dD to %ld clusters, redo %d times, %d iterations\n", (int)nx, kDim, (long)k, prm.nredo, prm.niter);
+
     KM_TRY(d_cent.ensure((size_t)k * kDim * 4));
     KM_TRY(d_D.ensure((size_t)nx * 4));
     KM_TRY(d_I.ensure((size_t)nx * 8));

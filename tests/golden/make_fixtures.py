@@ -57,17 +57,21 @@ def unambiguous(xb, xq):
     return bool((gap > MIN_GAP).all())
 
 
-def main():
+def find_inputs():
     seed = 20240
     while True:
         xb, xq = make_inputs(seed)
         if unambiguous(xb, xq):
-            break
+            return seed, xb, xq
         seed += 1
+
+
+def build_eval_tree(tmp, seed, xb, xq):
+    """The scratch tree retrieval/eval_retrieval.py expects (cwd = tmp/retrieval): paragraphs in sqlite, the idx->id JSON of
+    gen_index_id_map.py, the question file, both embedding files.  Deterministic in `seed`.  -> (db, qa, answers, texts)"""
     rng = np.random.default_rng(seed + 7)
-    tmp = tempfile.mkdtemp(prefix="proqa_golden_")
-    os.makedirs(os.path.join(tmp, "retrieval"))
-    os.makedirs(os.path.join(tmp, "pretrained_models"))
+    os.makedirs(os.path.join(tmp, "retrieval"), exist_ok=True)
+    os.makedirs(os.path.join(tmp, "pretrained_models"), exist_ok=True)
     # paragraphs: random word salads; the answer string of question i is planted in a few paragraphs
     answers = [[f"{WORDS[i % len(WORDS)]} {WORDS[(7 * i + 3) % len(WORDS)]} {i}"] for i in range(NQ)]
     texts = []
@@ -81,6 +85,8 @@ def main():
         texts[j] += f" The Answer Is {answers[i][0].upper()} , indeed ."
     ids = [f"doc_{j:05d}" for j in range(N)]
     db = os.path.join(tmp, "paras.db")
+    if os.path.exists(db):
+        os.remove(db)
     con = sqlite3.connect(db)
     con.execute("CREATE TABLE documents (id PRIMARY KEY, text)")
     con.executemany("INSERT INTO documents VALUES (?,?)", list(zip(ids, texts)))
@@ -94,6 +100,13 @@ def main():
             f.write(json.dumps({"question": f"which tree number {i} ?", "answer": answers[i]}) + "\n")
     np.save(os.path.join(tmp, "para_embed.npy"), xb)
     np.save(os.path.join(tmp, "query_embed.npy"), xq)
+    return db, qa, answers, texts
+
+
+def main():
+    seed, xb, xq = find_inputs()
+    tmp = tempfile.mkdtemp(prefix="proqa_golden_")
+    db, qa, answers, texts = build_eval_tree(tmp, seed, xb, xq)
 
     env = dict(os.environ)
     env["PYTHONPATH"] = os.path.join(HERE, "_oracle_faiss") + os.pathsep + env.get("PYTHONPATH", "")
