@@ -94,6 +94,16 @@ class ShardedClustering(ClusteringParameters):
         n, k = int(x.shape[0]), self.k
         if n < k:
             raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters ({k})")
+        # Clustering::train refuses non-finite input before anything else (as the single-GPU driver does); every rank holds the
+        # same x, so each checks its own stripe and the verdict is shared
+        flo, fhi = shard_bounds(n, self.world, self.rank)
+        bad = not bool(np.isfinite(np.asarray(x[flo:fhi], dtype=np.float32)).all())
+        if self.world > 1:
+            flags = [None] * self.world
+            self._dist.all_gather_object(flags, bad, group=self.group)
+            bad = any(flags)
+        if bad:
+            raise RuntimeError("input contains NaN's or Inf's")
         be = (self._backend_factory or _EngineBackend)(index, k)
         # ---- subsample + initial centroids: FAISS's own draws, identical on every rank -----------------------------------
         max_train = k * int(self.max_points_per_centroid)
@@ -110,7 +120,17 @@ class ShardedClustering(ClusteringParameters):
         be.set_points(x_local)
         first = be.rand_perm(nx, int(self.seed) + 1)[:k].astype(np.int64)
         cent0 = rows(sub[first]) if sub is not None else np.stack([np.asarray(x[i], dtype=np.float32) for i in first])
+        if nx == k:   # "Number of training points same as number of clusters, just copying" — no normalisation, no iterations
+            if self.verbose and self.rank == 0:
+                print(f"Number of training points ({nx}) same as number of clusters, just copying")
+            pts = rows(sub) if sub is not None else np.asarray(x, dtype=np.float32)
+            be.set_centroids(pts, False)
+            self.centroids = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1)
+            self.obj = np.zeros(0, dtype=np.float32)
+            return
         be.set_centroids(cent0, self.spherical)
+        if self.spherical:   # (niter = 0 must still hand back the normalised initial centroids, as Clustering::train does)
+            cent0 = cent0 / np.maximum(np.sqrt((cent0.astype(np.float32) ** 2).sum(1, keepdims=True, dtype=np.float32)), np.float32(1e-30))
         if self.verbose and self.rank == 0:
             print(f"Clustering {nx} points in {self.d}D to {k} clusters, redo 1 times, {self.niter} iterations ({self.world} ranks)")
         # ---- iterations ------------------------------------------------------------------------------------------------------

@@ -1,24 +1,17 @@
-"""-m gpu, OPT-IN (PROQA_B200_LARGEK=1): the tensor-core path for 1024 < k <= PQ_MAX_K (pq_mma_largek.inl) against the oracle.
-
-Skipped by default: that path was written after round 1's GPU budget was spent and has not run on hardware yet
-(DESIGN.md §5.6); without the variable the engine answers such k with the exact fp32 scan, which test_gpu_parity.py
-(test_large_k_trec_shape) covers.  To validate:  PROQA_B200_LARGEK=1 python -m pytest tests/test_gpu_largek.py -m gpu -x -q
-"""
-import os
-
+"""-m gpu: the tensor-core path for 1024 < k <= PQ_MAX_K (pq_mma_largek.inl; the default for such k since round 2) against the
+oracle — the retrieval/trec_process.py:76 (k = 10000) and qa/online_sampler.py:113 (k = 5000) call sites."""
 import numpy as np
 import pytest
 
 from oracle import oracle
 from tests import data
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PROQA_B200_LARGEK") != "1", reason="large-k tensor tier is opt-in until validated on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 def _search(metric, xb, xq, k):
     import proqa_b200 as pq
-    ix = pq.IndexFlatIP(128) if metric == 0 else pq.IndexFlatL2(128)   # the variable is read when the index is created
+    ix = pq.IndexFlatIP(128) if metric == 0 else pq.IndexFlatL2(128)
     ix.add(xb)
     D, I = ix.search(xq, k)
     return D, I, ix.last_stats

@@ -1,19 +1,12 @@
-"""-m gpu, OPT-IN (PROQA_B200_STAGED_KMEANS=1): k-means with the points sharded over GPUs (proqa_b200/sharded_clustering.py on
-pq_kmeans_set_centroids / _partial_device / _finish_device), one process, against the single-GPU Clustering.
-
-Skipped by default: the staged entry points were written after round 1's GPU budget was spent.  Their logic runs on the CPU
-under the SIMT emulator (tests/test_simt_kmeans.py, including the gloo multi-process case); this file is their first
-hardware check:  PROQA_B200_STAGED_KMEANS=1 python -m pytest tests/test_gpu_sharded_kmeans.py -m gpu -x -q
-(and under torchrun with 2 ranks through tools/gpu_runs/r02_sharded_kmeans.py)."""
-import os
-
+"""-m gpu: k-means with the points sharded over GPUs (proqa_b200/sharded_clustering.py on pq_kmeans_set_centroids /
+_partial_device / _finish_device), one process, against the single-GPU Clustering (validated on a B200 in round 2; the two-rank
+run under torchrun is tools/gpu_runs/r02_sharded_kmeans.py)."""
 import numpy as np
 import pytest
 
 from tests.test_kmeans_oracle import blobs
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PROQA_B200_STAGED_KMEANS") != "1", reason="staged k-means is opt-in until validated on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("metric,spherical,n,k,mpc", [(1, False, 6000, 20, 1000), (0, True, 6000, 20, 1000), (1, False, 40000, 16, 100)])
