@@ -470,7 +470,7 @@ def run_ours(args, wl):
                 ix.search_device(q.data_ptr(), nq, k, D_out.data_ptr(), I_out.data_ptr())
             else:
                 sh.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
-            return ix.last_stats[5] + (1 if (world > 1 and sh.R > 1) else 0)
+            return ix.last_stats[5] + ((5 if sh.R > 1 else 3) if (world > 1 and sh._xchg_on) else (1 if (world > 1 and sh.R > 1) else 0))
 
         def step_e2e_numpy():
             """The call the reference makes: index.search(pageable float32 array, k) -> new numpy (D, I)  (eval_retrieval.py:104)."""
@@ -556,25 +556,35 @@ def run_ours(args, wl):
                 evs[0].record(stream)
                 ix.search_device(q[qlo:qhi].data_ptr(), n_loc, k, D_loc.data_ptr(), I_loc.data_ptr())
                 evs[1].record(stream)
-                if sh.R > 1:
-                    Da = D_all.view(-1)[: sh.R * n_loc * k].view(sh.R * n_loc, k)
-                    Ia = I_all.view(-1)[: sh.R * n_loc * k].view(sh.R * n_loc, k)
-                    dist.all_gather_into_tensor(Da, D_loc[:n_loc], group=sh.row_group)
-                    dist.all_gather_into_tensor(Ia, I_loc[:n_loc], group=sh.row_group)
-                evs[2].record(stream)
-                if sh.R > 1:
-                    sh._merge_device(Da, Ia, n_loc, k, D_out[:n_loc], I_out[:n_loc])
-                evs[3].record(stream)
-                if sh.Q > 1:
-                    sh._gather_slices(D_loc[:n_loc], I_loc[:n_loc], nq, k)
+                if sh._xchg_on:
+                    sh._exchange(D_loc[:n_loc], I_loc[:n_loc], nq, k, D_out, I_out)
+                    evs[2].record(stream)
+                    evs[3].record(stream)
+                else:
+                    if sh.R > 1:
+                        Da = D_all.view(-1)[: sh.R * n_loc * k].view(sh.R * n_loc, k)
+                        Ia = I_all.view(-1)[: sh.R * n_loc * k].view(sh.R * n_loc, k)
+                        dist.all_gather_into_tensor(Da, D_loc[:n_loc], group=sh.row_group)
+                        dist.all_gather_into_tensor(Ia, I_loc[:n_loc], group=sh.row_group)
+                    evs[2].record(stream)
+                    if sh.R > 1:
+                        sh._merge_device(Da, Ia, n_loc, k, D_out[:n_loc], I_out[:n_loc])
+                    evs[3].record(stream)
+                    if sh.Q > 1:
+                        sh._gather_slices(D_loc[:n_loc], I_loc[:n_loc], nq, k)
                 evs[4].record(stream)
                 torch.cuda.synchronize()
                 for j in range(4):
                     acc[j] += evs[j].elapsed_time(evs[j + 1]) / reps
-            phases = {"local_search_ms": max_over_ranks(acc[0]), "row_group_all_gather_ms": max_over_ranks(acc[1]),
-                      "merge_kernel_ms": max_over_ranks(acc[2]), "query_group_all_gather_ms": max_over_ranks(acc[3]),
-                      "local_search_launches": int(ix.last_stats[5]), "threshold_exchanges_in_time_per_search": int(ix.last_stats[9]),
-                      "note": "max over ranks of CUDA-event times on the launching stream, one step taken apart"}
+            if sh._xchg_on:
+                phases = {"local_search_ms": max_over_ranks(acc[0]), "peer_memory_exchange_and_merge_ms": max_over_ranks(acc[1]),
+                          "exchange": "pq_xchg: scatter to the merging rank, merge of 1/R of the queries, result stored into every rank's HBM (NVLink P2P stores)"}
+            else:
+                phases = {"local_search_ms": max_over_ranks(acc[0]), "row_group_all_gather_ms": max_over_ranks(acc[1]),
+                          "merge_kernel_ms": max_over_ranks(acc[2]), "query_group_all_gather_ms": max_over_ranks(acc[3]),
+                          "exchange": "NCCL all-gather + merge kernel on every rank (PROQA_B200_XCHG=0)"}
+            phases.update({"local_search_launches": int(ix.last_stats[5]), "threshold_exchanges_in_time_per_search": int(ix.last_stats[9]),
+                           "note": "max over ranks of CUDA-event times on the launching stream, one step taken apart"})
 
         roofline = device_roofline(ix, step_device, 2.0 * (qhi - qlo) * (hi - lo) * 128, 512.0 * (hi - lo), t_dev,
                                    traffic_name=("c2" if (args.workload == "c2" and world == 1) else None))

@@ -206,6 +206,26 @@ int pq_multi_mode(const pq_multi* m);            /* 0 empty, 1 rows sharded, 2 r
 int pq_multi_last_stats(const pq_multi* m, int64_t* out, int n);   /* sums over the shards ([6], [7]: maxima) */
 pq_index* pq_multi_first_shard(pq_multi* m);     /* the shard on the first device (k-means training runs there) */
 
+/* ---- the exchange step of the row-sharded search, fused with its merge, over peer memory (proqa_b200/csrc/pq_xchg.cu) ------
+ * Replaces "NCCL all-gather of the per-shard lists, then pq_merge_shard_results on every GPU" (north_star (4)): every rank stores
+ * the slice of its list that rank p is to merge straight into p's HBM, merges its own slice of the queries, and stores the merged
+ * slice into every rank's result buffer.  One buffer per rank, mapped by all ranks (CUDA IPC across processes: pq_ipc_export /
+ * pq_ipc_open; plain pointers + pq_enable_peer_access within one process).  rank = query_group * row_shards + row_shard.
+ *   pq_xchg_bytes_needed  payload bytes for searches of up to nq queries at k results in that layout
+ *   pq_xchg_create        allocate this rank's buffer (returns its device address and size for the IPC export)
+ *   pq_xchg_connect       the world addresses, in rank order, as valid on THIS device
+ *   pq_xchg_run           enqueue one exchange on a stream: local list [n_loc, k] -> the full result [nq, k] on every rank;
+ *                         seq: the same strictly increasing number on every rank, one per search
+ *   pq_xchg_check         after a synchronisation: PQ_ERR_CUDA if a peer never delivered (10 s timeout inside the kernels) */
+typedef struct pq_xchg pq_xchg;
+int64_t pq_xchg_bytes_needed(int64_t nq, int64_t k, int row_shards, int query_groups);
+int pq_xchg_create(int device, int world, int rank, int64_t payload_bytes, pq_xchg** out, void** base_dev_out, int64_t* bytes_out);
+int pq_xchg_connect(pq_xchg* x, const void* const* peer_bases_dev);
+int pq_xchg_run(pq_xchg* x, int metric, int row_shards, int64_t nq, int64_t k, const float* D_local_dev, const int64_t* I_local_dev,
+                float* D_out_dev, int64_t* I_out_dev, uint64_t seq, void* cuda_stream);
+int pq_xchg_check(pq_xchg* x);
+void pq_xchg_free(pq_xchg* x);
+
 /* "proqa_b200 <version> sm_100a" */
 const char* pq_version(void);
 

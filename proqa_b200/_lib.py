@@ -68,6 +68,12 @@ SIGNATURES = {
     "pq_multi_mode": (ctypes.c_int, [_vp]),
     "pq_multi_last_stats": (ctypes.c_int, [_vp, _i64p, ctypes.c_int]),
     "pq_multi_first_shard": (_vp, [_vp]),
+    "pq_xchg_bytes_needed": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "pq_xchg_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64p]),
+    "pq_xchg_connect": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "pq_xchg_run": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp, _vp, _vp, ctypes.c_uint64, _vp]),
+    "pq_xchg_check": (ctypes.c_int, [_vp]),
+    "pq_xchg_free": (None, [_vp]),
     "pq_kmeans_default_params": (None, [ctypes.POINTER(KMeansParams)]),
     "pq_kmeans_train": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.POINTER(KMeansParams), ctypes.c_int64, _vp, _vp, _vp, ctypes.c_int64, _i64p]),
     "pq_rand_perm": (None, [ctypes.c_int64, ctypes.c_int64, _vp]),

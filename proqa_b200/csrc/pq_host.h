@@ -140,6 +140,8 @@ struct pq_index {
 
 namespace pq {
 // (the *_locked helpers expect the index's own lock, pq_index::mu, held by the C-ABI entry point)
+// requested < 0: PROQA_B200_DEVICE / LOCAL_RANK / the current device; validates that the device is an sm_100 part
+int pick_device(int requested, int* out);
 int index_init_device(pq_index* ix);
 int index_add_locked(pq_index* ix, int64_t n, const float* x, bool on_device);
 int index_reset_locked(pq_index* ix);

@@ -103,7 +103,7 @@ void DevBuf::release() {
     cap = 0;
 }
 
-static int pick_device(int requested, int* out) {
+int pick_device(int requested, int* out) {
     // cudaGetDeviceProperties costs milliseconds: validate each ordinal once per process
     static std::mutex mu;
     static int validated[64];
@@ -456,7 +456,9 @@ __global__ void pq_scatter_results_kernel(const float* __restrict__ Ds, const lo
 // sample to mean something; PROQA_B200_LARGEK=0 sends such requests to the fp32 scan instead.
 static bool tier_uses_largek(const pq_index* ix, int64_t nq, int64_t k) {
     if (!ix->largek || ix->has_nonfinite || ix->tier == PQ_TIER_FP32) return false;
-    return k > kMmaMaxK && k <= PQ_MAX_K && nq >= kMmaMinQueries && plan_large_k_applies(ix->ntotal, (int)k);
+    if (k > kMmaMaxK) return k <= PQ_MAX_K && nq >= kMmaMinQueries && plan_large_k_applies(ix->ntotal, (int)k);
+    // 512 <= k <= 1024 with a real batch (C5: 8192 queries, k = 1000): sample thresholds + one pass beat the epochs
+    return k >= kPlanMidK && nq >= 256 && ix->ntotal >= (1 << 20) && plan_large_k_applies(ix->ntotal, (int)k);
 }
 
 static bool tier_uses_mma(const pq_index* ix, int64_t nq, int64_t k) {
@@ -494,7 +496,7 @@ int search_device_impl(pq_index* ix, int64_t nq, const float* dq, int64_t k, flo
 
     if (tier_uses_mma(ix, nq, k)) {
         std::vector<int> rerun;
-        rc = k > kMmaMaxK ? search_mma_largek(ix, (int)nq, dq, (int)k, dD, dI, &rerun) : search_mma_filter(ix, (int)nq, dq, (int)k, dD, dI, &rerun);
+        rc = tier_uses_largek(ix, nq, k) ? search_mma_largek(ix, (int)nq, dq, (int)k, dD, dI, &rerun) : search_mma_filter(ix, (int)nq, dq, (int)k, dD, dI, &rerun);
         if (rc) return rc;
         ix->stats[0] = nq - (int64_t)rerun.size();
         ix->stats[1] = (int64_t)rerun.size();

@@ -1646,7 +1646,7 @@ extern "C" int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms
 //   query, queries per batch, slab bytes of a full batch, finalize shared-memory bytes, carry length of the sample search
 extern "C" int pq_plan_describe_large_k(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len) {
     using namespace pq;
-    if (ntotal < 1 || nq < 1 || k <= kMmaMaxK || k > PQ_MAX_K || n_sms < 1 || !out || out_len < 16)
+    if (ntotal < 1 || nq < 1 || k < kPlanMidK || k > PQ_MAX_K || n_sms < 1 || !out || out_len < 16)
         return set_error(PQ_ERR_INVALID, "plan_describe_large_k: bad arguments");
     const LargeKPlan lp = plan_large_k(ntotal, (int)k);
     const int nqb = (int)std::min<int64_t>(nq, kLargeKBatch);

@@ -83,7 +83,7 @@ inline void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n
 
 // Epochs of one search over rows [0, N): contiguous, in order, covering every row once.
 // share_n > 1: the corpus is row-sharded over share_n GPUs that exchange thresholds after every epoch (pq_mma.cu:
-// ShareParams), so a threshold reflects share_n times the rows this shard has seen: epochs grow faster, slabs stay small.
+// ShareParams), so a threshold reflects share_n times the rows this shard has seen: slabs stay small.
 inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const GridShape& gs, int n_sms, int share_n = 1) {
     std::vector<EpochPlan> plan;
     const int n_mtiles = nq_pad / kPlanQueryTile;
@@ -100,8 +100,12 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
     // Epoch growth: every epoch costs a fixed ~0.1-0.2 ms (launches, select) and about 1.5 k (growth - 1) survivors per
     // query; small batches are dominated by the fixed part, large ones by the survivors
     // (measured: nq=16 1.19 ms at 64x; nq=256 1.66 ms at 8x vs 1.81 at 64x).
+    // Row shards that exchange thresholds: a threshold reflects share_n times the rows this shard has seen, so slabs can be
+    // smaller — but a shard is share_n times shorter than the corpus, so the epochs must NOT grow faster: the loose-threshold
+    // epochs would cover a larger part of the shard (8 shards of C3 with growth 32: 37 % of a shard's rows ran with 40 % of the
+    // 32x32 chunks taking the append path — 51 ms against 36 ms for the same products with queries split instead).
     const int share_f = share_n >= 4 ? 4 : (share_n >= 2 ? 2 : 1);
-    const long long growth = std::min(64LL, (nq_pad <= 128 ? 64LL : (nq_pad <= 512 ? 16LL : 8LL)) * share_f);
+    const long long growth = nq_pad <= 128 ? 64LL : (nq_pad <= 512 ? 16LL : 8LL);
     const long long n0 = std::min<long long>(N, std::max(1024, plan_next_pow2(2 * kp)));
     long long begin = 0, end = n0;
     while (begin < N) {
@@ -144,14 +148,21 @@ struct LargeKPlan {
 constexpr int kLargeKPoolMax = 24576;   // keys (192 KB) the finalize kernel can hold next to its slab counters
 constexpr int kLargeKBatch = 8192;      // queries per pass: bounds the candidate slabs (about 0.7 MB per query at k = 10000)
 
+// k > 1024: the sample search runs at k_sample ~ 1024, its threshold aimed at full-corpus rank 1.35 k (rank noise ~ 1/sqrt(1024)
+// = 3 %, so rank < k — a failed certificate, the query then costs a whole fp32 scan — is an 8-sigma event).
+// kPlanMidK <= k <= 1024 (C5: k = 1000): the same scheme beats the epochs there too — K' = 4096 carry lists make every epoch's
+// select expensive and the frozen thresholds let ~7 x 1.5 k rows per query through — but a 1024-row sample search would
+// cost as much as it saves: k_sample ~ 160 on every ~10th row, aimed at rank 1.6 k (noise 8 %, 4.7 sigma above k).
+constexpr int kPlanMidK = 512;
 inline LargeKPlan plan_large_k(long long N, int k) {
     LargeKPlan lp;
-    const double rank_target = 1.35 * (double)k;
-    lp.step = std::max(2, (int)ceil(rank_target / 1024.0));
+    const bool mid = k <= 1024;
+    const double rank_target = (mid ? 1.6 : 1.35) * (double)k;
+    lp.step = std::max(2, (int)ceil(rank_target / (mid ? 160.0 : 1024.0)));
     lp.k_sample = (int)ceil(rank_target / (double)lp.step);
     lp.sample_rows = N / lp.step;
     lp.sort_n = plan_next_pow2(k);
-    lp.pool = std::max(lp.sort_n, std::min(kLargeKPoolMax, 2 * k));
+    lp.pool = std::max(lp.sort_n, std::min(kLargeKPoolMax, std::max(2 * k, 4096)));
     return lp;
 }
 // The single pass of phase B over rows [0, N): slices as for any epoch, slabs provisioned for 3 x 2.2 k survivors per query.
@@ -161,7 +172,7 @@ inline EpochPlan plan_large_k_pass(long long N, int k, int nq_pad, const GridSha
     ep.end = N;
     pick_slices(gs, nq_pad / kPlanQueryTile, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
     const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
-    const double expect = 2.2 * (double)k / slabs;
+    const double expect = (k <= 1024 ? 2.6 : 2.2) * (double)k / slabs;
     ep.cap = std::min(65536, std::max(128 / gs.subs_per_slice, plan_next_pow2((int)(3.0 * expect) + 128 / gs.subs_per_slice)));
     return ep;
 }

@@ -69,6 +69,15 @@ class ShardedIndexFlat:
         self._share_cap = 0
         self._share_peers = []
         self._seq = 0
+        # the exchange step itself: lists stored straight into the peers' HBM, merge spread over the ranks (pq_xchg.cu);
+        # PROQA_B200_XCHG=0 falls back to NCCL all-gather + merge kernel on every rank
+        self._xchg_on = (merge_fn is None and local_factory is None and os.environ.get("PROQA_B200_XCHG", "1") != "0")
+        self._xchg = None
+        self._xchg_bytes = 0
+        self._xchg_peers = []
+        self._xseq = 0
+        self._local_is_engine = local_factory is None
+        self._stream_set = False
         # process groups: every rank creates every group, in the same order (new_group is collective)
         self.row_group = group
         self.col_group = None
@@ -120,6 +129,7 @@ class ShardedIndexFlat:
         self.ntotal = 0
         self._first_add = True
         self._share_close()
+        self._xchg_close()
 
     # ---- threshold exchange between row shards ----------------------------------------------------
     def _share_close(self):
@@ -172,6 +182,59 @@ class ShardedIndexFlat:
         dist.barrier(group=self.row_group)   # nobody searches before every mailbox is mapped everywhere
         self._share_cap = cap
 
+    # ---- list exchange over peer memory ------------------------------------------------------------
+    def _xchg_close(self):
+        L = _lib.lib()
+        for ptr in self._xchg_peers:
+            L.pq_ipc_close(self._dev_index(), ctypes.c_void_p(ptr))
+        if self._xchg is not None:
+            L.pq_xchg_free(self._xchg)
+        self._xchg, self._xchg_bytes, self._xchg_peers = None, 0, []
+
+    def _xchg_setup(self, nq, k):
+        """Collective over all ranks: (re)allocate the exchange buffers for [nq, k] results and map every rank's buffer here."""
+        import torch
+        L = _lib.lib()
+        dist, dev = self._dist, torch.device("cuda", self._dev_index())
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)       # nobody is still inside an exchange that uses the old buffers
+        self._xchg_close()
+        need = int(L.pq_xchg_bytes_needed(nq, k, self.R, self.Q))
+        need = max(need, 1 << 20) * 5 // 4   # head-room: a slightly larger batch later does not re-map everything
+        h, base, nbytes = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(L.pq_xchg_create(self._dev_index(), self.world, self.rank, need, ctypes.byref(h), ctypes.byref(base), ctypes.byref(nbytes)),
+                   "xchg_create")
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(L.pq_ipc_export(base, handle), "ipc_export")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        every = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        every = every.cpu().numpy().reshape(self.world, 64)
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = base.value
+                continue
+            out = ctypes.c_void_p()
+            _lib.check(L.pq_ipc_open((ctypes.c_ubyte * 64)(*every[r].tolist()), self._dev_index(), ctypes.byref(out)), "ipc_open")
+            ptrs[r] = out.value
+            self._xchg_peers.append(out.value)
+        _lib.check(L.pq_xchg_connect(h, ptrs), "xchg_connect")
+        dist.barrier(group=self.group)
+        self._xchg, self._xchg_bytes = h, need
+
+    def _exchange(self, Dl, Il, nq, k, D_out, I_out):
+        """Local list of this rank's query slice -> the full [nq, k] result on every rank, on torch's current stream."""
+        import torch
+        L = _lib.lib()
+        if int(L.pq_xchg_bytes_needed(nq, k, self.R, self.Q)) > self._xchg_bytes:
+            self._xchg_setup(nq, k)
+        self._xseq += 1
+        rc = L.pq_xchg_run(self._xchg, self.metric_type, self.R, nq, k, ctypes.c_void_p(Dl.data_ptr() if Dl.numel() else 0),
+                           ctypes.c_void_p(Il.data_ptr() if Il.numel() else 0), ctypes.c_void_p(D_out.data_ptr()), ctypes.c_void_p(I_out.data_ptr()),
+                           self._xseq, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "xchg_run")
+
     def _share_begin(self, nq_local):
         """Before every search of this rank's query slice (same on all ranks of the row group)."""
         if not (self._share_on and self.R > 1 and self.world > 1):
@@ -193,10 +256,31 @@ class ShardedIndexFlat:
         k = int(k)
         nq = xq.shape[0]
         qlo, qhi = self.query_bounds(nq)
+        if self.world == 1:
+            return self._local.search(xq, k)
+        if self._merge_fn is None and self._local_is_engine:
+            # queries to the device once, local search + exchange on torch's current stream, one read-back of the result
+            dev = torch.device("cuda", self._dev_index())
+            if not self._stream_set:
+                self._local.set_stream(torch.cuda.current_stream().cuda_stream)
+                self._stream_set = True
+            q = torch.from_numpy(xq).to(dev, non_blocking=True)
+            n_loc = qhi - qlo
+            D_loc = torch.empty((max(n_loc, 1), k), dtype=torch.float32, device=dev)
+            I_loc = torch.empty((max(n_loc, 1), k), dtype=torch.int64, device=dev)
+            D_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            I_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            D_all = I_all = None
+            if not self._xchg_on:
+                D_all = torch.empty((self.world, nq, k), dtype=torch.float32, device=dev)
+                I_all = torch.empty((self.world, nq, k), dtype=torch.int64, device=dev)
+            self.search_device(q, k, D_loc, I_loc, D_all, I_all, D_out, I_out)
+            Dh, Ih = D_out.cpu().numpy(), I_out.cpu().numpy()
+            if self._xchg_on:
+                _lib.check(_lib.lib().pq_xchg_check(self._xchg), "list exchange")
+            return Dh, Ih
         self._share_begin(qhi - qlo)
         D, I = self._local.search(xq[qlo:qhi], k)
-        if self.world == 1:
-            return D, I
         on_gpu = self._merge_fn is None
         dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
         Dl, Il = torch.from_numpy(D).to(dev), torch.from_numpy(I).to(dev)
@@ -220,6 +304,9 @@ class ShardedIndexFlat:
         if self.world == 1:
             D_out.copy_(D_local)
             I_out.copy_(I_local)
+            return
+        if self._xchg_on:
+            self._exchange(Dl, Il, nq, k, D_out, I_out)
             return
         if self.R > 1 and n_loc:  # (every rank of a row group has the same slice, so an empty slice skips consistently)
             # rank-major concatenation along dim 0: [R*n_loc, k] is the layout every backend accepts for the output

@@ -161,7 +161,7 @@ def resid2(x):
     return (((x - bf16_round(x)).astype(np.float64) ** 2).sum(1) * 1.0001).astype(np.float32)
 
 
-def run_host_emu(lib, xb, xq, k, metric, n_sms=8, schedule=0, share=None, bound=None):
+def run_host_emu(lib, xb, xq, k, metric, n_sms=8, schedule=0, share=None, bound=None, force_largek=False):
     """-> D, I, sorted list of queries the driver wants re-run by the fp32 scan, the driver's statistics.
     schedule != 0: the emulator resumes the threads of a block in a different pseudo-random order at every pass."""
     lib.emu_set_schedule(schedule)
@@ -190,6 +190,7 @@ def run_host_emu(lib, xb, xq, k, metric, n_sms=8, schedule=0, share=None, bound=
         lib.emu_set_share(n_sh, rank, cap_q, wait_us, seq, id_base, arr)
     else:
         lib.emu_set_share(0, 0, 0, 0, 0, 0, None)
+    lib.emu_force_largek(1 if force_largek else 0)
     max_norm2, max_resid2 = bound if bound is not None else (float(norms.max()), float(resid2(xb).max()))
     msg = lib.emu_search_mma(xb.ctypes.data, xb_b.ctypes.data, norms.ctypes.data, len(xb), max_norm2, max_resid2,
                              xq.ctypes.data, xq_b.ctypes.data, q_norm.ctypes.data, q_resid.ctypes.data, q_bad.ctypes.data, nq, k, metric,

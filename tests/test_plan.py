@@ -131,5 +131,12 @@ def test_large_k_plan_of_the_trec_call():
 def test_large_k_plan_rejects_small_k():
     from proqa_b200 import _lib
     out = (ctypes.c_int64 * 16)()
-    assert _lib.lib().pq_plan_describe_large_k(1_000_000, 10, 1024, N_SMS, out, 16) != 0
+    assert _lib.lib().pq_plan_describe_large_k(1_000_000, 10, 511, N_SMS, out, 16) != 0       # below 512 the epochs stay
     assert _lib.lib().pq_plan_describe_large_k(1_000_000, 10, 15361, N_SMS, out, 16) != 0
+
+
+def test_mid_k_plan_of_the_scale_out_config():
+    """BASELINE C5: 8192-query batches, k = 1000, 12.5M rows per GPU — thresholds from every 10th row at k_sample = 160."""
+    p = plan_large_k(12_500_000, 8192, 1000)
+    assert p["applies"] == 1 and (p["step"], p["k_sample"], p["sort_n"]) == (10, 160, 1024) and p["pool"] >= 2 * 1000
+    assert p["step"] * p["k_sample"] >= 1.5 * 1000, "the threshold must aim well beyond rank k (rank noise ~ 1/sqrt(k_sample))"

@@ -229,6 +229,19 @@ def test_host_driver_phases_a_b_c_match_the_oracle(host_emu, metric, nb, nq, k, 
     assert stats[3] >= 3 and stats[4] >= 3   # sample epochs + the pass; their selects + the finalize
 
 
+@pytest.mark.parametrize("metric,nb,nq,k,n_sms", [(0, 90_000, 5, 1000, 8), (1, 70_000, 4, 600, 6), (0, 130_000, 3, 1024, 16)])
+def test_mid_k_takes_the_same_scheme(host_emu, metric, nb, nq, k, n_sms):
+    """512 <= k <= 1024 with a real batch (BASELINE C5: 8192 queries, k = 1000): thresholds from every ~10th row at k_sample ~ 160,
+    aimed at rank 1.6 k; one pass; finalize.  (pq_index.cu routes such searches here; the emulator is told to.)"""
+    xb, xq = data.corpus(nb), data.queries(nq)
+    D, I, rerun, stats = run_host_emu(host_emu, xb, xq, k, metric, n_sms, force_largek=True)
+    ok = [q for q in range(nq) if q not in rerun]
+    assert len(ok) >= nq - 1, f"queries sent to the fp32 scan: {rerun}"
+    Dr, Ir = oracle.engine_spec(xq, xb, k, metric)
+    np.testing.assert_array_equal(I[ok], Ir[ok])
+    np.testing.assert_array_equal(D[ok].view(np.uint32), Dr[ok].view(np.uint32))
+
+
 def test_host_driver_on_rows_in_document_order(host_emu):
     rng = np.random.default_rng(5)
     centres = rng.standard_normal((150, 128)).astype(np.float32)

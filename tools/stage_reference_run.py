@@ -22,7 +22,7 @@ def main():
     dst = os.path.join(ROOT, "baseline", "_ref")
     run = os.path.join(dst, "eval_run")
     os.makedirs(os.path.join(run, "retrieval"), exist_ok=True)
-    for name in ("eval_retrieval.py", "basic_tokenizer.py", "utils.py"):
+    for name in ("eval_retrieval.py", "basic_tokenizer.py", "utils.py"):  # (what the script imports)
         shutil.copyfile(os.path.join(REF, name), os.path.join(run, "retrieval", name))
     seed, xb, xq = mf.find_inputs()
     mf.build_eval_tree(run, seed, xb, xq)
