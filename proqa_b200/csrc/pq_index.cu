@@ -739,8 +739,12 @@ int pq_index_share_alloc(pq_index* ix, int n_ranks, int rank, int64_t cap_querie
     PQ_CUDA(cudaSetDevice(ix->device));
     pq_share_state& ss = ix->share;
     ss.connected = false;
-    const size_t bytes = ((size_t)n_ranks * (size_t)cap_queries * 2 + (size_t)n_ranks) * 8;
-    rc = ss.mailbox.ensure(bytes);
+    size_t bytes = ((size_t)n_ranks * (size_t)cap_queries * 2 + (size_t)n_ranks) * 8;
+    // whole 2 MB blocks: the mailbox is exported through CUDA IPC, and small cudaMalloc blocks share a driver allocation with
+    // whatever else is small (a peer cannot open two handles that resolve to the same allocation)
+    const size_t alloc_bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    ss.mailbox.release();
+    rc = ss.mailbox.ensure(alloc_bytes);
     if (rc) return rc;
     PQ_CUDA(cudaMemsetAsync(ss.mailbox.p, 0, bytes, ix->stream));   // tag 0 is never used by a search
     PQ_CUDA(cudaStreamSynchronize(ix->stream));

@@ -264,6 +264,21 @@ int pq_xchg_create(int device, int world, int rank, int64_t payload_bytes, pq_xc
     x->rank = rank;
     x->capacity = ((size_t)payload_bytes + 255) & ~size_t(255);
     PQ_CUDA(cudaSetDevice(dev));
+    {
+        // Load every kernel of the exchange NOW: with lazy module loading the first launch of a kernel can wait for the device
+        // to go idle — which never happens while another stage of the same exchange spins on a flag that launch would raise.
+        cudaFuncAttributes fa;
+        PQ_CUDA(cudaFuncGetAttributes(&fa, pq_xchg_scatter_kernel));
+        PQ_CUDA(cudaFuncGetAttributes(&fa, pq_xchg_signal_kernel));
+        PQ_CUDA(cudaFuncGetAttributes(&fa, pq_xchg_merge_sort_kernel));
+        PQ_CUDA(cudaFuncGetAttributes(&fa, pq_xchg_merge_rank_kernel));
+        PQ_CUDA(cudaFuncGetAttributes(&fa, pq_xchg_push_kernel));
+        PQ_CUDA(cudaFuncGetAttributes(&fa, pq_xchg_collect_kernel));
+        PQ_CUDA(cudaFuncSetAttribute(pq_xchg_merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    }
+    // (at least 2 MB, in 2 MB steps: small cudaMalloc blocks are carved out of shared driver allocations, and two IPC handles that
+    // resolve to the same allocation cannot both be opened by a peer — cudaErrorAlreadyMapped)
+    x->capacity = ((kXchgHeaderBytes + x->capacity + (2u << 20) - 1) / (2u << 20)) * (2u << 20) - kXchgHeaderBytes;
     rc = x->buf.ensure(kXchgHeaderBytes + x->capacity);
     if (rc) {
         delete x;
@@ -366,7 +381,6 @@ int pq_xchg_run(pq_xchg* x, int metric, int row_shards, int64_t nq, int64_t k, c
         while (work < R * (int)k) work <<= 1;
         if ((size_t)work * 8 <= 128 * 1024) {
             const size_t smem = (size_t)work * 8;
-            if (smem > 48 * 1024) PQ_CUDA(cudaFuncSetAttribute(pq_xchg_merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             pq_xchg_merge_sort_kernel<<<grid, 256, smem, st>>>(p, work);
         } else {
             pq_xchg_merge_rank_kernel<<<grid, 256, 0, st>>>(p);
