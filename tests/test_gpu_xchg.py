@@ -107,8 +107,8 @@ def test_buffers_too_small_are_refused():
     _lib.check(L.pq_xchg_create(0, 1, 0, L.pq_xchg_bytes_needed(10, 10, 1, 1), ctypes.byref(h), ctypes.byref(base), ctypes.byref(nbytes)), "create")
     arr = (ctypes.c_void_p * 1)(base.value)
     _lib.check(L.pq_xchg_connect(h, arr), "connect")
-    D, I = torch.zeros((100, 10), device="cuda"), torch.zeros((100, 10), dtype=torch.int64, device="cuda")
-    rc = L.pq_xchg_run(h, 0, 1, 100, 10, ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(D.data_ptr()),
+    D, I = torch.zeros((100_000, 10), device="cuda"), torch.zeros((100_000, 10), dtype=torch.int64, device="cuda")   # 24 MB of results; buffers are 2 MB
+    rc = L.pq_xchg_run(h, 0, 1, 100_000, 10, ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(D.data_ptr()),
                        ctypes.c_void_p(I.data_ptr()), 1, None)
     assert rc != 0 and "too small" in _lib.last_error()
     L.pq_xchg_free(h)
