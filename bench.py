@@ -285,13 +285,16 @@ def parity_gate(D, I, Dt, It, own, rtol=1e-4):
 def device_roofline(ix, run, flops_per_step, bytes_per_step, t_dev_hint, traffic_name=None):
     """Dominant-kernel time from CUDA events around it on its launching stream (pq_index_set_profile), against the measured peaks."""
     ix.set_profile(True)
-    kern_us = []
+    kern_us, other_us = [], []
     for _ in range(3):
         run()
         kern_us.append(ix.last_stats[7])
+        other_us.append(list(ix.last_stats[11:14]))
     ix.set_profile(False)
     st = ix.last_stats
     kernel_s = float(np.mean(kern_us)) * 1e-6
+    other = {"epoch_select_ms": float(np.mean([o[0] for o in other_us])) / 1e3, "threshold_fold_ms": float(np.mean([o[1] for o in other_us])) / 1e3,
+             "rescore_ms": float(np.mean([o[2] for o in other_us])) / 1e3}
     peaks = load_peaks()
     if st[3] > 0:
         long_run = t_dev_hint > 1.0
@@ -304,7 +307,7 @@ def device_roofline(ix, run, flops_per_step, bytes_per_step, t_dev_hint, traffic
                 "peak_source": f"{peaks['source']} cuBLAS bf16 ({'sustained' if long_run else 'burst'})",
                 "frac_of_burst": achieved / peaks["bf16_tflops"], "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
                 "algorithmic": "256 flop per (query,row) score",
-                "launches_per_step": int(st[3]), "kernel_ms_per_step": kernel_s * 1e3}
+                "launches_per_step": int(st[3]), "kernel_ms_per_step": kernel_s * 1e3, "other_kernels_ms_per_step": other}
     nbytes = bytes_per_step * max(1, st[2])
     achieved = nbytes / kernel_s / 1e9 if kernel_s > 0 else 0.0
     tr = load_traffic("pq_ffma_scan_kernel") if traffic_name else None
@@ -654,7 +657,8 @@ def run_ours(args, wl):
             "row_shards": r["R"], "query_groups": r["Q"], "ms_per_step": r["t_dev"] / args.steps * 1e3,
             "value": nq * args.steps / r["t_dev"] if r["parity_ok"] else None, "parity_ok": r["parity_ok"],
             "e2e_ms_per_step": r["e2e"]["numpy_pageable"] / args.steps * 1e3, "phases": r["phases"],
-            "kernel_frac": r["roofline"]["frac"], "gpu_launches": int(r["launches"]),
+            "kernel_frac": r["roofline"]["frac"], "filter_kernel_ms": r["roofline"]["kernel_ms_per_step"],
+            "other_kernels_ms": r["roofline"].get("other_kernels_ms_per_step"), "gpu_launches": int(r["launches"]),
             "threshold_exchanges_in_time": int(r["exchanges"])} for r in results.values()}
         out["layouts"]["headline"] = "rows" if best["R"] == world else f"R{best['R']}xQ{best['Q']}"
     if sweep is not None:

@@ -94,7 +94,9 @@ int pq_index_set_profile(pq_index* idx, int on);
  * [4]=select/merge/rescore launches, [5]=total kernel launches, [6]=device microseconds (CUDA events),
  * [7]=microseconds inside the dominant kernel (only with pq_index_set_profile), [8]=(query, epoch) pairs repaired after the
  * last epoch (candidate slabs overflowed: rows in document order can bring a whole cluster above the threshold at once),
- * [9]=threshold exchanges between row shards in which every shard's values had arrived in time. */
+ * [9]=threshold exchanges between row shards in which every shard's values had arrived in time; with pq_index_set_profile also
+ * [11]=microseconds inside the epoch-select kernels, [12]=inside the threshold-fold kernels, [13]=inside the rescoring kernel
+ * (n up to 16). */
 int pq_index_last_stats(const pq_index* idx, int64_t* out, int n);
 
 /* Merge G per-shard result lists (each [nq,k], best-first, global ids) into one — the kernel run

@@ -88,7 +88,7 @@ struct pq_index {
     pq::DevBuf ws_mma[12];
     pq::DevBuf ws_km[10];  // staged k-means (multi-GPU training): centroids, assignment, sort buffers
 
-    int64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t stats[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     pq_share_state share;
 
     // optional per-kernel timing of the dominant kernel (fp32 scan / tensor-core filter): event pairs on the stream
@@ -96,9 +96,12 @@ struct pq_index {
     bool stream_is_external = false;
     cudaStream_t own_stream = nullptr;
     std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_tags;   // what each event pair brackets: 0 dominant kernel, 1 epoch select, 2 threshold fold, 3 rescoring / finalize
     size_t prof_used = 0;
-    int prof_begin() {
+    int prof_begin(int tag = 0) {
         if (!profile) return 0;
+        prof_tags.resize(prof_used / 2 + 1);
+        prof_tags[prof_used / 2] = tag;
         if (prof_used + 2 > prof_events.size()) {
             for (int i = 0; i < 2; ++i) {
                 cudaEvent_t e;
@@ -113,15 +116,17 @@ struct pq_index {
         cudaEventRecord(prof_events[prof_used + 1], stream);
         prof_used += 2;
     }
-    // after the stream drained: total microseconds between the recorded pairs
+    // after the stream drained: total microseconds between the recorded pairs of the dominant kernel (returned; stats[7]);
+    // the other tags land in stats[10 + tag]
     int64_t prof_collect() {
-        double us = 0.0;
+        double us[4] = {0.0, 0.0, 0.0, 0.0};
         for (size_t i = 0; i + 1 < prof_used; i += 2) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, prof_events[i], prof_events[i + 1]) == cudaSuccess) us += ms * 1000.0;
+            if (cudaEventElapsedTime(&ms, prof_events[i], prof_events[i + 1]) == cudaSuccess) us[prof_tags[i / 2] & 3] += ms * 1000.0;
         }
         prof_used = 0;
-        return (int64_t)(us + 0.5);
+        for (int t = 1; t < 4; ++t) stats[10 + t] = (int64_t)(us[t] + 0.5);
+        return (int64_t)(us[0] + 0.5);
     }
 
     void release_all() {

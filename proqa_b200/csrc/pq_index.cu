@@ -696,7 +696,7 @@ int pq_index_set_profile(pq_index* ix, int on) {
 }
 int pq_index_last_stats(const pq_index* ix, int64_t* out, int n) {
     if (!ix || !out || n < 0) return set_error(PQ_ERR_INVALID, "last_stats: bad arguments");
-    for (int i = 0; i < n; ++i) out[i] = i < 10 ? ix->stats[i] : 0;
+    for (int i = 0; i < n; ++i) out[i] = i < 16 ? ix->stats[i] : 0;
     return PQ_OK;
 }
 

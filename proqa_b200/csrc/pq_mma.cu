@@ -1517,11 +1517,16 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.is_redo = 0;
             sp.allow_redo = ep.begin > 0 ? 1 : 0;  // the bootstrap epoch's slabs hold every row they can see
             sp.share = share;
-            PQ_CUDA(launch_epoch_select(sp, ix->device, ix->stream));
+            ix->prof_begin(1);
+            const cudaError_t se = launch_epoch_select(sp, ix->device, ix->stream);
+            ix->prof_end();
+            PQ_CUDA(se);
             ix->stats[4] += 1;
             ix->stats[5] += 1;
             if (share.n > 1 && e + 1 < (int)plan.size()) {  // what the row shards know together, before the next epoch admits on it
+                ix->prof_begin(2);
                 pq_share_fold_kernel<<<(nq + 255) / 256, 256, 0, ix->stream>>>(share, st, nq, e);
+                ix->prof_end();
                 PQ_CUDA(cudaGetLastError());
                 ix->stats[5] += 1;
             }
@@ -1557,7 +1562,10 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         rp.I = dI_all + (size_t)qb * k;
         rp.fail = (uint8_t*)w[7].p;
         rp.fail_count = st.counters + 2;
-        PQ_CUDA(launch_rescore(rp, ix->device, ix->stream));
+        ix->prof_begin(3);
+        const cudaError_t re = launch_rescore(rp, ix->device, ix->stream);
+        ix->prof_end();
+        PQ_CUDA(re);
         ix->stats[4] += 1;
         ix->stats[5] += 1;
 

@@ -135,9 +135,9 @@ class IndexFlat:
         _lib.check(_lib.lib().pq_index_set_profile(self._h, 1 if on else 0), "set_profile")
 
     def _pull_stats(self):
-        buf = (ctypes.c_int64 * 10)()
-        if _lib.lib().pq_index_last_stats(self._h, buf, 10) == 0:
-            _LAST_STATS[:] = list(buf)
+        buf = (ctypes.c_int64 * 16)()
+        if _lib.lib().pq_index_last_stats(self._h, buf, 16) == 0:
+            _LAST_STATS[:] = list(buf)[:10]
         self.last_stats = list(buf)
 
 
