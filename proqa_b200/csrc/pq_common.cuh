@@ -208,6 +208,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): no register staging, any number in flight per thread.
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));

@@ -924,8 +924,16 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(co
     const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
     const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
 
+    // Everything this warp reads from global memory is read with many loads in flight: a lone warp that waits out one L2 round
+    // trip per load (counts, then carry, then slab after slab) spent 70 us on ~300 keys.
     bool ovf = false;
-    for (int s = lane; s < n_sub; s += 32) ovf |= cnts[s] > (uint32_t)p.cap;
+    for (int s = lane; s < n_sub; s += 128) {
+        uint32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = s + 32 * u < n_sub ? cnts[s + 32 * u] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ovf |= c[u] > (uint32_t)p.cap;
+    }
     ovf = __any_sync(0xffffffffu, ovf);
 
     WarpSelState w;
@@ -937,13 +945,19 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(co
 
     // carry -> pool (a repair drops what the first attempt took from this epoch's rows: regenerated below)
     int fill = 0;
-    for (int i0 = 0; i0 < p.kp; i0 += 32) {
-        const uint64_t key = carry[i0 + lane];
-        const long long row = (long long)key_row(key);
-        const bool keep = key != 0ull && !(p.is_redo && row >= p.row_begin && row < p.row_end);
-        const unsigned km = __ballot_sync(0xffffffffu, keep);
-        if (keep) pool[fill + __popc(km & ((1u << lane) - 1u))] = key;
-        fill += __popc(km);
+    {
+        uint64_t ck[8];   // kp <= 256: at most eight keys per lane, all loads issued before the first is used
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ck[u] = 32 * u < p.kp ? carry[32 * u + lane] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint64_t key = ck[u];
+            const long long row = (long long)key_row(key);
+            const bool keep = key != 0ull && !(p.is_redo && row >= p.row_begin && row < p.row_end);
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (keep) pool[fill + __popc(km & ((1u << lane) - 1u))] = key;
+            fill += __popc(km);
+        }
     }
     __syncwarp();
 
@@ -958,31 +972,25 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(co
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) continue;
-        if (fill + total > kSelWarpPool && fill > p.kp) fill = warp_sel_reduce(p, pool, fill, w, hist, lane);
+        if (fill + total > kSelWarpPool && fill > p.kp) {
+            cp_async_wait_all();
+            __syncwarp();
+            fill = warp_sel_reduce(p, pool, fill, w, hist, lane);
+        }
         if (fill + total <= kSelWarpPool) {
-            // warp-wide copies, four slabs in flight (a lane copying its own slab serialises one global round trip per entry)
+            // slab by slab, warp-wide, as asynchronous 8-byte copies straight into the pool: nothing waits until the pool is reduced
             const int off = fill + incl - c;
-            for (int j0 = 0; j0 < 32 && s0 + j0 < n_sub; j0 += 4) {
-                int cj[4], oj[4];
-                uint64_t val[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    cj[u] = __shfl_sync(0xffffffffu, c, (j0 + u) & 31);
-                    oj[u] = __shfl_sync(0xffffffffu, off, (j0 + u) & 31);
-                }
-                const int longest = max(max(cj[0], cj[1]), max(cj[2], cj[3]));
-                for (int i = lane; i < longest; i += 32) {   // (warp-uniform bound: lanes beyond a slab's count just skip it)
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i < cj[u]) val[u] = keys[(size_t)(s0 + j0 + u) * p.cap + i];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i < cj[u]) pool[oj[u] + i] = val[u];
-                }
+            const int nj = min(32, n_sub - s0);
+            for (int j = 0; j < nj; ++j) {
+                const int cj = __shfl_sync(0xffffffffu, c, j);
+                const int oj = __shfl_sync(0xffffffffu, off, j);
+                const uint64_t* src = keys + (size_t)(s0 + j) * p.cap;
+                for (int i = lane; i < cj; i += 32) cp_async_8(pool + oj + i, src + i);
             }
             fill += total;
-            __syncwarp();
         } else {  // 32 slabs hold more than the pool has room for (rows in document order): slab by slab, warp-wide copies
+            cp_async_wait_all();
+            __syncwarp();
             for (int j = 0; j < 32; ++j) {
                 const int cj = __shfl_sync(0xffffffffu, c, j);
                 const uint64_t* src = keys + (size_t)(s0 + j) * p.cap;
@@ -997,6 +1005,8 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(co
             }
         }
     }
+    cp_async_wait_all();
+    __syncwarp();
     const int m = warp_sel_reduce(p, pool, fill, w, hist, lane);
     for (int i = lane; i < p.kp; i += 32) carry[i] = i < m ? pool[i] : 0ull;
     if (lane == 0) {
@@ -1118,8 +1128,14 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_rescore_warp_kernel(const R
     const uint64_t* carry = p.st.carry + (size_t)q * p.kp;
     const float bar = p.st.thr[q];
     const float4 qv = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
-    for (int i0 = 0; i0 < p.kp; i0 += 32) {
-        const uint64_t key = carry[i0 + lane];
+    uint64_t ck[8];   // kp <= 256: the carry in eight loads, all in flight together
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ck[u] = 32 * u < p.kp ? carry[32 * u + lane] : 0ull;
+#pragma unroll
+    for (int u8 = 0; u8 < 8; ++u8) {
+        const int i0 = 32 * u8;
+        if (i0 >= p.kp) break;
+        const uint64_t key = ck[u8];
         unsigned live = __ballot_sync(0xffffffffu, key != 0ull && key_score(key) >= bar);
         uint64_t mine = 0ull;
         while (live) {  // warp-uniform
@@ -1523,7 +1539,10 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             PQ_CUDA(se);
             ix->stats[4] += 1;
             ix->stats[5] += 1;
-            if (share.n > 1 && e + 1 < (int)plan.size()) {  // what the row shards know together, before the next epoch admits on it
+            // what the row shards know together, before the next epoch admits on it — and after the last epoch, before the rescoring:
+            // a shard's own k-th best score is far below the global one, so without the last exchange every shard would rescore
+            // (and ship) ~k rows per query instead of ~k/n
+            if (share.n > 1) {
                 ix->prof_begin(2);
                 pq_share_fold_kernel<<<(nq + 255) / 256, 256, 0, ix->stream>>>(share, st, nq, e);
                 ix->prof_end();
