@@ -188,10 +188,16 @@ static int index_grow(pq_index* ix, int64_t need_rows) {
         return rc;
     }
     if (ix->ntotal > 0) {
-        PQ_CUDA(cudaMemcpyAsync(nf.p, ix->rows_f32.p, (size_t)ix->ntotal * kDim * 4, cudaMemcpyDeviceToDevice, ix->stream));
-        PQ_CUDA(cudaMemcpyAsync(nb.p, ix->rows_bf16.p, (size_t)ix->ntotal * kDim * 2, cudaMemcpyDeviceToDevice, ix->stream));
-        PQ_CUDA(cudaMemcpyAsync(nn.p, ix->norms.p, (size_t)ix->ntotal * 4, cudaMemcpyDeviceToDevice, ix->stream));
-        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+        cudaError_t e = cudaMemcpyAsync(nf.p, ix->rows_f32.p, (size_t)ix->ntotal * kDim * 4, cudaMemcpyDeviceToDevice, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nb.p, ix->rows_bf16.p, (size_t)ix->ntotal * kDim * 2, cudaMemcpyDeviceToDevice, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nn.p, ix->norms.p, (size_t)ix->ntotal * 4, cudaMemcpyDeviceToDevice, ix->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        if (e != cudaSuccess) {  // the new buffers (1.5x the index) must not outlive a failed copy
+            nf.release();
+            nb.release();
+            nn.release();
+            return cuda_fail(e, __FILE__, __LINE__);
+        }
     }
     ix->rows_f32.release();
     ix->rows_bf16.release();

@@ -980,8 +980,10 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(co
         if (fill + total <= kSelWarpPool) {
             // slab by slab, warp-wide, as asynchronous 8-byte copies straight into the pool: nothing waits until the pool is reduced
             const int off = fill + incl - c;
-            const int nj = min(32, n_sub - s0);
-            for (int j = 0; j < nj; ++j) {
+            unsigned nonempty = __ballot_sync(0xffffffffu, c > 0);
+            while (nonempty) {  // (warp-uniform)
+                const int j = __ffs(nonempty) - 1;
+                nonempty &= nonempty - 1;
                 const int cj = __shfl_sync(0xffffffffu, c, j);
                 const int oj = __shfl_sync(0xffffffffu, off, j);
                 const uint64_t* src = keys + (size_t)(s0 + j) * p.cap;
