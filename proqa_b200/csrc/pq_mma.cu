@@ -44,19 +44,15 @@ namespace pq {
 
 constexpr int kBM = 128;            // queries per M tile (TMEM lanes)
 constexpr int kBN = 128;            // corpus rows per B tile (one TMA stage)
-constexpr int kEpiWarps = PQ_EPI_WARPS;        // 4 TMEM lane quarters x kEpiSets column sets
-constexpr int kEpiSets = kEpiWarps / 4;
-constexpr int kSubN = kBN / kEpiSets;          // accumulator columns (corpus rows) one epilogue warp set drains
-constexpr int kSubChunks = kSubN / 32;         // 32-column register chunks per warp and accumulator
+constexpr int kMaxEpiSets = 4;      // epilogue warp sets of the widest kernel variant (pq_plan.h: kPlanSetsLoose)
 constexpr int kStages = 6;          // B ring depth
 constexpr int kAccBufs = 2;         // TMEM accumulators of kBN = 128 columns (UMMA N = 128): one per (B tile, M tile), double-buffered
 constexpr int kTmemACol = kAccBufs * kBN;      // first TMEM column of the stationary query operand
 constexpr int kPanelBytes = 128 * 128;         // 128 rows x 128 B (64 bf16): one swizzle-128B K panel
 constexpr int kTileBytes = 2 * kPanelBytes;    // K = 128 -> two panels, 32 KB
 constexpr int kStageBytes = kTileBytes + 1024; // + the tile's 128 squared row norms (L2 only), padded to keep 1024-B alignment
-constexpr int kMmaThreads = (2 + kEpiWarps) * 32;
 constexpr int kMaxMTiles = 4;       // 4 x 64 TMEM columns of bf16 queries + 2 x 128 columns of accumulators = 512
-static_assert(kBM == kPlanQueryTile && kBN == kPlanTileRows && kMaxMTiles == kPlanMaxMTiles && kEpiSets == kPlanSubsPerSlice && (kEpiSets == 2 || kEpiSets == 4), "pq_plan.h must describe this kernel");
+static_assert(kBM == kPlanQueryTile && kBN == kPlanTileRows && kMaxMTiles == kPlanMaxMTiles && kMaxEpiSets == kPlanSetsLoose && kPlanSetsTight == 2, "pq_plan.h must describe this kernel");
 
 
 struct MmaCtrl {
@@ -83,7 +79,8 @@ struct MmaParams {
     // the tiles owned, so every CTA carries the same number of (query tile x row tile) products)
     int base, rem, s1, s0;
     int cap;
-    int n_sub;               // candidate slabs per query = max(s1, s0) * kEpiSets (one per epilogue warp set)
+    int n_sub;               // candidate slabs per query = max(s1, s0) * sets (one per epilogue warp set)
+    int sets;                // epilogue warp sets of the kernel variant launched (2 or 4)
     int k1_adapt;
     // second attempt at an epoch ("repair", launched after the last epoch and only when some slab overflowed): only the
     // queries whose slabs overflowed in that epoch (redo[q] & redo_bit) take part, with their final thresholds
@@ -208,9 +205,12 @@ __device__ __forceinline__ void mma_filter32_k1(float (&v)[32], float& thr, floa
 // so a consumer must never be able to run two uses ahead of a buffer (a round-robin over four buffers whose consumers
 // changed from use to use aliased and hung).  N = 128 per instruction measured ~5 % faster end to end than two N = 64
 // accumulators per tile (half the instructions, half the reads of the stationary operand from tensor memory).
-template <int M_TILES, bool kL2, bool kK1>
-__global__ void __launch_bounds__(kMmaThreads, 1)
+template <int M_TILES, bool kL2, bool kK1, int kEpiSets>
+__global__ void __launch_bounds__((2 + 4 * kEpiSets) * 32, 1)
 pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams p) {
+    constexpr int kEpiWarps = 4 * kEpiSets;        // 4 TMEM lane quarters x kEpiSets column sets
+    constexpr int kSubN = kBN / kEpiSets;          // accumulator columns (corpus rows) one epilogue warp set drains
+    constexpr int kSubChunks = kSubN / 32;         // 32-column register chunks per warp and accumulator
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_b = smem;                                        // kStages x (32 KB tile + norms)
     MmaCtrl* ctrl = reinterpret_cast<MmaCtrl*>(smem_b + (size_t)kStages * kStageBytes);
@@ -551,7 +551,7 @@ struct EpochSelParams {
     const uint32_t* cand_cnt;
     int n_sub, cap, kp, k, lmax;  // n_sub: slab stride per query; lmax: keys the CTA kernel's shared pool holds
     int nq;
-    int base, rem, s1, s0;        // the filter's grid shape: a query of a group with s row slices has 2 s slabs, the rest is unwritten
+    int base, rem, s1, s0, sets;  // the filter's grid shape: a query of a group with s row slices has sets x s slabs, the rest is unwritten
     int is_redo;                  // repair of this epoch: only queries with (st.redo & epoch_bit) take part
     int allow_redo;               // first attempt: a slab overflow asks for a repair instead of failing the query
     uint32_t epoch_bit;
@@ -562,7 +562,7 @@ struct EpochSelParams {
 // slabs the filter kernel wrote for query q
 __device__ __forceinline__ int sel_slabs_of_query(const EpochSelParams& p, int q) {
     const int mt = q / kPlanQueryTile;
-    return kPlanSubsPerSlice * (mt < p.rem * (p.base + 1) ? p.s1 : p.s0);
+    return p.sets * (mt < p.rem * (p.base + 1) ? p.s1 : p.s0);
 }
 
 // One CTA per query (any K'): carry  <-  top-K' of (carry U this epoch's slabs); threshold <- A_k - 2E.
@@ -1327,22 +1327,28 @@ static cudaError_t ensure_dyn_smem(K* kernel, size_t smem, int device) {
                                 [](const void* f, int v) { return cudaFuncSetAttribute((K*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, v); });
 }
 
-template <int M, bool L2, bool K1>
+template <int M, bool L2, bool K1, int SETS>
 static cudaError_t launch_filter(const CUtensorMap& tc, const MmaParams& p, int n_ctas, int device, cudaStream_t stream) {
-    const size_t smem = (size_t)kStages * kStageBytes + 256 + (size_t)kMaxMTiles * kEpiWarps * 32 * 12;  // ring + control + epilogue state
-    cudaError_t e = ensure_dyn_smem(pq_mma_filter_kernel<M, L2, K1>, smem, device);
+    const size_t smem = (size_t)kStages * kStageBytes + 256 + (size_t)kMaxMTiles * 4 * SETS * 32 * 12;  // ring + control + epilogue state
+    cudaError_t e = ensure_dyn_smem(pq_mma_filter_kernel<M, L2, K1, SETS>, smem, device);
     if (e != cudaSuccess) return e;
-    pq_mma_filter_kernel<M, L2, K1><<<n_ctas, kMmaThreads, smem, stream>>>(tc, p);
+    pq_mma_filter_kernel<M, L2, K1, SETS><<<n_ctas, (2 + 4 * SETS) * 32, smem, stream>>>(tc, p);
     return cudaGetLastError();
+}
+template <int M, bool L2, bool K1>
+static cudaError_t launch_filter_s(const CUtensorMap& tc, const MmaParams& p, int n_ctas, int device, cudaStream_t stream) {
+    if (p.sets == kPlanSetsTight) return launch_filter<M, L2, K1, kPlanSetsTight>(tc, p, n_ctas, device, stream);
+    return launch_filter<M, L2, K1, kPlanSetsLoose>(tc, p, n_ctas, device, stream);
 }
 template <bool L2, bool K1>
 static cudaError_t launch_filter_m(int m_max, const CUtensorMap& tc, const MmaParams& p, int n_ctas, int device, cudaStream_t stream) {
-    if (m_max == 1) return launch_filter<1, L2, K1>(tc, p, n_ctas, device, stream);
-    if (m_max == 2) return launch_filter<2, L2, K1>(tc, p, n_ctas, device, stream);
-    return launch_filter<4, L2, K1>(tc, p, n_ctas, device, stream);
+    if (m_max == 1) return launch_filter_s<1, L2, K1>(tc, p, n_ctas, device, stream);
+    if (m_max == 2) return launch_filter_s<2, L2, K1>(tc, p, n_ctas, device, stream);
+    return launch_filter_s<4, L2, K1>(tc, p, n_ctas, device, stream);
 }
 static cudaError_t launch_filter_any(int m_max, bool l2, bool k1, const CUtensorMap& tc, const MmaParams& p, int n_ctas, int device,
                                      cudaStream_t stream) {
+    if (p.sets != kPlanSetsTight && p.sets != kPlanSetsLoose) return cudaErrorInvalidValue;
     if (l2) return k1 ? launch_filter_m<true, true>(m_max, tc, p, n_ctas, device, stream) : launch_filter_m<true, false>(m_max, tc, p, n_ctas, device, stream);
     return k1 ? launch_filter_m<false, true>(m_max, tc, p, n_ctas, device, stream) : launch_filter_m<false, false>(m_max, tc, p, n_ctas, device, stream);
 }
@@ -1483,10 +1489,12 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.s0 = ep.s0;
             mp.cap = ep.cap;
             mp.n_sub = plan_n_sub(gs, ep);
+            mp.sets = ep.sets;
             sp.n_sub = mp.n_sub;
             sp.cap = ep.cap;
             sp.s1 = ep.s1;
             sp.s0 = ep.s0;
+            sp.sets = ep.sets;
             sp.epoch_bit = 1u << e;
             sp.row_begin = ep.begin;
             sp.row_end = ep.end;
@@ -1654,7 +1662,7 @@ extern "C" int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms
     out[4] = gs.m_max;
     out[5] = carry_size_for_k((int)k);
     out[6] = nq_pad;
-    out[7] = gs.subs_per_slice;
+    out[7] = kPlanSetsLoose;
     for (size_t e = 0; e < plan.size(); ++e) {
         int64_t* o = out + 8 + 8 * e;
         o[0] = plan[e].begin;
@@ -1664,7 +1672,7 @@ extern "C" int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms
         o[4] = plan[e].cap;
         o[5] = plan_n_ctas(gs, plan[e]);
         o[6] = plan_n_sub(gs, plan[e]);
-        o[7] = 0;
+        o[7] = plan[e].sets;
     }
     return PQ_OK;
 }

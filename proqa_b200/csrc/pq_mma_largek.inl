@@ -393,6 +393,7 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.s0 = ep.s0;
             mp.cap = ep.cap;
             mp.n_sub = plan_n_sub(gs, ep);
+            mp.sets = ep.sets;
             PQ_CUDA(launch_filter_any(gs.m_max, l2, false, ix->tmap_sample, mp, plan_n_ctas(gs, ep), ix->device, ix->stream));
             EpochSelParams sp;
             memset(&sp, 0, sizeof(sp));
@@ -409,6 +410,7 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.rem = gs.rem;
             sp.s1 = ep.s1;
             sp.s0 = ep.s0;
+            sp.sets = ep.sets;
             sp.is_redo = 0;
             sp.allow_redo = 0;   // a slab overflow only loosens the estimate (the k-th best of what fitted is still a real score)
             sp.epoch_bit = 0u;
@@ -428,6 +430,7 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         mp.s0 = pass.s0;
         mp.cap = pass.cap;
         mp.n_sub = plan_n_sub(gs, pass);
+        mp.sets = pass.sets;
         PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
         ix->prof_begin();
         const cudaError_t e = launch_filter_any(gs.m_max, l2, false, ix->tmap_bf16, mp, plan_n_ctas(gs, pass), ix->device, ix->stream);

@@ -13,18 +13,27 @@ namespace pq {
 constexpr int kPlanTileRows = 128;   // corpus rows per B tile (= kBN in pq_mma.cu)
 constexpr int kPlanQueryTile = 128;  // queries per M tile (= kBM)
 constexpr int kPlanMaxMTiles = 4;    // query tiles one CTA keeps in tensor memory (= kMaxMTiles)
-#ifndef PQ_EPI_WARPS
-#define PQ_EPI_WARPS 16              // epilogue warps of the filter kernel: 4 TMEM lane quarters x (PQ_EPI_WARPS / 4) column sets
-#endif
-constexpr int kPlanSubsPerSlice = PQ_EPI_WARPS / 4;  // every epilogue warp set (a column range of each row tile) keeps its own slab
+// Epilogue warp sets of the filter kernel (4 warps each, one per TMEM lane quarter; a set drains 128 / sets columns of every
+// accumulator and keeps its own candidate slab per (query, row slice)).  Two variants are compiled and chosen per epoch:
+//   4 sets (16 epilogue warps) while the threshold is loose — most 32x32 chunks have a survivor and the append path is
+//           issue-bound with two warps per scheduler (ncu: tensor pipe 25 %; 694 -> 556 us for rows 64k..512k of C2);
+//   2 sets ( 8 epilogue warps) once it is tight — the kernel is then power-limited, and the four-set kernel executes 40 % more
+//           instructions for the same products (ncu: 6.0e9 vs 4.3e9 in the last C2 epoch; sustained SM clock 1612 vs 1676 MHz).
+constexpr int kPlanSetsLoose = 4, kPlanSetsTight = 2;
+// expected share of 32x32 chunks with a survivor when rows [begin, ..) are filtered at the threshold known after `seen` rows
+inline int plan_sets_for(double k, double seen_rows) {
+    const double per_pair = 1.5 * k / std::max(1.0, seen_rows);
+    return 1024.0 * per_pair > 0.10 ? kPlanSetsLoose : kPlanSetsTight;
+}
 
 struct EpochPlan {
     long long begin, end;
     int s1, s0, cap;   // row slices per CTA group (groups owning base+1 / base query tiles), slab capacity
+    int sets;          // epilogue warp sets of the kernel variant this epoch runs (= slabs per row slice)
 };
 
 struct GridShape {
-    int n_groups, base, rem, m_max, subs_per_slice;
+    int n_groups, base, rem, m_max;
 };
 
 inline int plan_next_pow2(int v) {
@@ -43,7 +52,6 @@ inline GridShape make_grid_shape(int n_mtiles) {
     gs.base = n_mtiles / gs.n_groups;
     gs.rem = n_mtiles % gs.n_groups;
     gs.m_max = gs.base + (gs.rem ? 1 : 0);
-    gs.subs_per_slice = kPlanSubsPerSlice;  // the epilogue warp sets (column ranges of every row tile) keep separate slabs
     return gs;
 }
 
@@ -93,7 +101,8 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
         ep.begin = 0;
         ep.end = N;
         pick_slices(gs, n_mtiles, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
-        ep.cap = 128 / gs.subs_per_slice;  // a thread keeps only rows within 2E of its running maximum: a few dozen at most
+        ep.sets = kPlanSetsLoose;      // the running-maximum filter records often (C4 L2: 0.52 -> 0.58 of peak with four sets)
+        ep.cap = 128 / ep.sets;        // a thread keeps only rows within 2E of its running maximum: a few dozen at most
         plan.push_back(ep);
         return plan;
     }
@@ -115,15 +124,17 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
         const long long tiles = (ep.end - ep.begin + kPlanTileRows - 1) / kPlanTileRows;
         if (begin == 0) {  // bootstrap: every score is a candidate, one row tile per slice
             ep.s1 = ep.s0 = (int)tiles;
-            ep.cap = kPlanTileRows / gs.subs_per_slice;
+            ep.sets = kPlanSetsLoose;
+            ep.cap = kPlanTileRows / ep.sets;
         } else {
             pick_slices(gs, n_mtiles, tiles, n_sms, &ep.s1, &ep.s0);
             // survivors per query with the threshold frozen at the start of the epoch: about k * (end/begin - 1), times
             // ~1.5 for the 2E margin, on exchangeable rows; three times that is provisioned (rows in document order
             // bring whole clusters above the threshold at once — beyond the provision the epoch is run a second time)
-            const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
+            ep.sets = plan_sets_for((double)k, (double)ep.begin * share_n);
+            const double slabs = (double)std::min(ep.s1, ep.s0) * ep.sets;
             const double expect = 1.5 * (double)k * ((double)(ep.end - ep.begin) / (double)ep.begin) / slabs / share_f;
-            const int floor_cap = 128 / gs.subs_per_slice;  // (the same slab memory per slice whatever the number of warp sets)
+            const int floor_cap = 128 / ep.sets;  // (the same slab memory per slice whatever the number of warp sets)
             ep.cap = std::min(4096, std::max(floor_cap, plan_next_pow2((int)(3.0 * expect) + floor_cap)));
         }
         plan.push_back(ep);
@@ -171,15 +182,17 @@ inline EpochPlan plan_large_k_pass(long long N, int k, int nq_pad, const GridSha
     ep.begin = 0;
     ep.end = N;
     pick_slices(gs, nq_pad / kPlanQueryTile, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
-    const double slabs = (double)std::min(ep.s1, ep.s0) * gs.subs_per_slice;
+    // about 2.4 k survivors over N rows: with k in the thousands most chunks have one
+    ep.sets = 1024.0 * 2.4 * (double)k / (double)std::max(1LL, N) > 0.10 ? kPlanSetsLoose : kPlanSetsTight;
+    const double slabs = (double)std::min(ep.s1, ep.s0) * ep.sets;
     const double expect = (k <= 1024 ? 2.6 : 2.2) * (double)k / slabs;
-    ep.cap = std::min(65536, std::max(128 / gs.subs_per_slice, plan_next_pow2((int)(3.0 * expect) + 128 / gs.subs_per_slice)));
+    ep.cap = std::min(65536, std::max(128 / ep.sets, plan_next_pow2((int)(3.0 * expect) + 128 / ep.sets)));
     return ep;
 }
 // Large enough a corpus for the sample to mean something; otherwise the fp32 scan answers.
 inline bool plan_large_k_applies(long long N, int k) { return N >= 64LL * k; }
 
 inline int plan_n_ctas(const GridShape& gs, const EpochPlan& ep) { return gs.rem * ep.s1 + (gs.n_groups - gs.rem) * ep.s0; }
-inline int plan_n_sub(const GridShape& gs, const EpochPlan& ep) { return std::max(ep.s1, ep.s0) * gs.subs_per_slice; }
+inline int plan_n_sub(const GridShape& gs, const EpochPlan& ep) { return std::max(ep.s1, ep.s0) * ep.sets; }
 
 }  // namespace pq

@@ -78,6 +78,7 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
             extract(mma, "pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams p)")
             .replace("extern __shared__ __align__(1024) uint8_t smem[];", "uint8_t* smem = smem_raw;"),
             extract(mma, "static cudaError_t launch_filter(const CUtensorMap& tc"),
+            extract(mma, "static cudaError_t launch_filter_s(const CUtensorMap& tc"),
             extract(mma, "static cudaError_t launch_filter_m(int m_max"),
             extract(mma, "static cudaError_t launch_filter_any(int m_max"),
         ])

@@ -25,7 +25,7 @@ def plan(ntotal, nq, k, n_sms=N_SMS):
     rc = _lib.lib().pq_plan_describe(ntotal, nq, k, n_sms, out, len(out))
     assert rc == 0, _lib.last_error()
     head = dict(zip(["epochs", "groups", "base", "rem", "m_max", "kp", "nq_pad"], list(out[:7])))
-    eps = [dict(zip(["begin", "end", "s1", "s0", "cap", "ctas", "n_sub"], list(out[8 + 8 * e: 8 + 8 * e + 7]))) for e in range(head["epochs"])]
+    eps = [dict(zip(["begin", "end", "s1", "s0", "cap", "ctas", "n_sub", "sets"], list(out[8 + 8 * e: 8 + 8 * e + 8]))) for e in range(head["epochs"])]
     return head, eps
 
 
@@ -50,15 +50,15 @@ def test_plan_invariants(ntotal, nq, k):
         tiles = -(-(ep["end"] - ep["begin"]) // 128)
         assert 1 <= ep["s1"] <= tiles and 1 <= ep["s0"] <= tiles, "never more slices than row tiles"
         assert ep["ctas"] == head["rem"] * ep["s1"] + (head["groups"] - head["rem"]) * ep["s0"] >= 1
-        assert ep["n_sub"] == SETS * max(ep["s1"], ep["s0"])
-        assert 128 // SETS <= ep["cap"] <= 4096 and ep["cap"] & (ep["cap"] - 1) == 0
+        assert ep["sets"] in (2, 4) and ep["n_sub"] == ep["sets"] * max(ep["s1"], ep["s0"])
+        assert 128 // ep["sets"] <= ep["cap"] <= 4096 and ep["cap"] & (ep["cap"] - 1) == 0
         if ep["begin"] > 0:  # epoch boundaries are multiples of a tile, so a tile never straddles two epochs
             assert ep["begin"] % 128 == 0
         if k > 1 and i == 0:  # bootstrap: every score is a survivor, the slabs must hold a whole row half each
-            assert ep["s1"] == ep["s0"] == tiles and ep["cap"] == 128 // SETS
+            assert ep["s1"] == ep["s0"] == tiles and ep["sets"] == 4 and ep["cap"] == 32
         if k > 1 and i > 0:   # provision: at least twice the survivors expected on exchangeable rows (1.5 k (end/begin - 1))
             expect = 1.5 * k * (ep["end"] - ep["begin"]) / ep["begin"]
-            assert ep["cap"] * SETS * min(ep["s1"], ep["s0"]) >= min(2 * expect, 4096 * SETS * min(ep["s1"], ep["s0"]))
+            assert ep["cap"] * ep["sets"] * min(ep["s1"], ep["s0"]) >= min(2 * expect, 4096 * ep["sets"] * min(ep["s1"], ep["s0"]))
         # the candidate slabs of one pass stay far below a B200's 180 GB
         assert head["nq_pad"] * ep["n_sub"] * ep["cap"] * 8 <= 48e9
     if k == 1:
