@@ -595,9 +595,11 @@ def run_ours(args, wl):
                           roofline=roofline, parity_ok=parity_ok, parity_info=parity_info, nchk=nchk, clocks=clocks, t_build=t_build,
                           tensor_path=ix.last_stats[3] > 0)
         if R != layouts[-1]:
+            sh.close()
             del sh, ix, D_loc, I_loc, D_all, I_all, D_out, I_out
             torch.cuda.empty_cache()
 
+    sh.close()
     best = min(results.values(), key=lambda r: r["t_dev"] if r["parity_ok"] else float("inf"))
     sweep = None
     if world == 1 and args.workload == "c2" and not args.no_sweep and args.rows is None:

@@ -131,6 +131,24 @@ class ShardedIndexFlat:
         self._share_close()
         self._xchg_close()
 
+    def close(self):
+        """Collective: unmap the peers' buffers everywhere, then free the own ones (an exported buffer must outlive its mappings)."""
+        import torch
+        if self.world > 1 and self._merge_fn is None and self._local_is_engine:
+            torch.cuda.synchronize()
+            self._dist.barrier(group=self.group)
+        L = _lib.lib()
+        for ptr in self._share_peers:
+            L.pq_ipc_close(self._dev_index(), ctypes.c_void_p(ptr))
+        self._share_peers = []
+        for ptr in self._xchg_peers:
+            L.pq_ipc_close(self._dev_index(), ctypes.c_void_p(ptr))
+        self._xchg_peers = []
+        if self.world > 1 and self._merge_fn is None and self._local_is_engine:
+            self._dist.barrier(group=self.group)
+        self._share_close()
+        self._xchg_close()
+
     # ---- threshold exchange between row shards ----------------------------------------------------
     def _share_close(self):
         L = _lib.lib()
