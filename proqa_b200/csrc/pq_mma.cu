@@ -1228,21 +1228,47 @@ __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
     const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
     const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
     bool fail = p.q_bad[q] != 0;
+    // A lone warp per query: every global read below is issued together with its neighbours (counts: one per lane; slab
+    // entries: four slabs per round; rows: the four rows of a group) — one round trip per load made this kernel 30 % of a
+    // k-means assignment pass (21M points: 21 batches x 1.4 ms).
     // pass 1: best bf16 score over all candidates
     uint32_t best_hi = 0;
-    for (int s = 0; s < p.n_sub; ++s) {
-        const uint32_t c = cnts[s];
-        if (c > (uint32_t)p.cap) fail = true;
+    for (int s0 = 0; s0 < p.n_sub; s0 += 32) {
+        const int s = s0 + lane;
+        const uint32_t c = s < p.n_sub ? cnts[s] : 0u;
+        fail |= c > (uint32_t)p.cap;
         const int n = (int)min(c, (uint32_t)p.cap);
-        for (int i = lane; i < n; i += 32) best_hi = max(best_hi, (uint32_t)(keys[(size_t)s * p.cap + i] >> 32));
+        unsigned nonempty = __ballot_sync(0xffffffffu, n > 0);
+        while (nonempty) {  // (warp-uniform) four slabs per round
+            int sj[4], nj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sj[u] = -1;
+                nj[u] = 0;
+                if (nonempty) {
+                    sj[u] = __ffs(nonempty) - 1;
+                    nonempty &= nonempty - 1;
+                    nj[u] = __shfl_sync(0xffffffffu, n, sj[u]);
+                }
+            }
+            const int longest = max(max(nj[0], nj[1]), max(nj[2], nj[3]));
+            for (int i = lane; i < longest; i += 32) {
+                uint64_t kv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) kv[u] = i < nj[u] ? keys[(size_t)(s0 + sj[u]) * p.cap + i] : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) best_hi = max(best_hi, (uint32_t)(kv[u] >> 32));
+            }
+        }
     }
+    fail = __any_sync(0xffffffffu, fail);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best_hi = max(best_hi, __shfl_xor_sync(0xffffffffu, best_hi, o));
     uint64_t best = 0ull;
     if (best_hi != 0 && !fail) {
         const float bar = ordered_to_f32(best_hi) - p.two_e[q];
         const float4 qv = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
-        // pass 2: exact score of every candidate within 2E of the best
+        // pass 2: exact score of every candidate within 2E of the best (the slab entries come from L1 now)
         for (int s = 0; s < p.n_sub; ++s) {
             const int n = (int)min(cnts[s], (uint32_t)p.cap);
             for (int i0 = 0; i0 < n; i0 += 32) {
@@ -1253,14 +1279,20 @@ __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
                     const int src = __ffs(live) - 1;
                     live &= live - 1;
                     const uint32_t row0 = key_row(__shfl_sync(0xffffffffu, key, src));
+                    float4 rv[4];
+                    float rn[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // the four rows of the group, in flight together
+                        const bool in = (long long)(row0 + j) < p.n_rows;
+                        rv[j] = in ? __ldg(reinterpret_cast<const float4*>(p.rows + (size_t)(row0 + j) * kDim) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        rn[j] = (in && p.metric == kMetricL2) ? __ldg(p.row_norms + row0 + j) : 0.f;
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t row = row0 + j;
-                        if ((long long)row >= p.n_rows) break;
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(p.rows + (size_t)row * kDim) + lane);
-                        float sc = warp_engine_dot(rv, qv, lane);
-                        if (p.metric == kMetricL2) sc = fmaf(2.f, sc, -__ldg(p.row_norms + row));
-                        if (sc >= PQ_THR_FLOOR) best = max(best, make_key(sc, row));
+                        if ((long long)(row0 + j) >= p.n_rows) break;
+                        float sc = warp_engine_dot(rv[j], qv, lane);
+                        if (p.metric == kMetricL2) sc = fmaf(2.f, sc, -rn[j]);
+                        if (sc >= PQ_THR_FLOOR) best = max(best, make_key(sc, row0 + j));
                     }
                 }
             }

@@ -390,6 +390,7 @@ inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 struct float4 {
     float x, y, z, w;
 };
+inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 struct uint2 {
     unsigned x, y;
 };

@@ -24,11 +24,19 @@ def host_emu(request, tmp_path_factory):
     import os
     old = os.environ.get("PROQA_B200_SELECT_WARP_MIN")
     os.environ["PROQA_B200_SELECT_WARP_MIN"] = "1" if request.param == "warp_per_query" else "1000000000"
-    yield harness.build_host_emu(tmp_path_factory.mktemp("simt_host_" + request.param))
+    lib = harness.build_host_emu(tmp_path_factory.mktemp("simt_host_" + request.param))
+    lib.family = request.param
+    yield lib
     if old is None:
         os.environ.pop("PROQA_B200_SELECT_WARP_MIN", None)
     else:
         os.environ["PROQA_B200_SELECT_WARP_MIN"] = old
+
+
+def _warp_family_only(lib):
+    """K' > 256, k = 1 and the schedule fuzzing do not depend on the family (or always take the CTA kernels): run them once."""
+    if lib.family != "warp_per_query":
+        pytest.skip("covered by the warp-per-query run (this case does not depend on the selection-kernel family)")
 
 
 def _exact(D, I, xq, xb, k, metric, rows=None):
@@ -51,6 +59,7 @@ def test_epoch_search_matches_the_oracle(host_emu, metric, nb, nq, k, kind, n_sm
 @pytest.mark.parametrize("metric,nb,nq", [(1, 2_000, 300), (0, 1_500, 200), (1, 130, 140)])
 def test_k1_assignment_path_matches_the_oracle(host_emu, metric, nb, nq):
     """group_paras.py:45,51 — few centroids (the rows), many points (the queries), k = 1."""
+    _warp_family_only(host_emu)
     xb, xq = data.corpus(nb), data.queries(nq)
     D, I, rerun, st = harness.run_host_emu(host_emu, xb, xq, 1, metric)
     assert rerun == []
@@ -59,6 +68,7 @@ def test_k1_assignment_path_matches_the_oracle(host_emu, metric, nb, nq):
 
 
 def test_k_larger_than_ntotal_pads(host_emu):
+    _warp_family_only(host_emu)
     xb, xq = data.corpus(50), data.queries(4)
     D, I, rerun, _ = harness.run_host_emu(host_emu, xb, xq, 80, 0)
     assert rerun == []
@@ -87,6 +97,8 @@ def test_results_do_not_depend_on_the_thread_schedule(host_emu, schedule):
     """The emulator resumes a block's threads in a different pseudo-random order after every barrier / warp collective, so
     that another thread runs ahead each time; shared state read after a barrier that a thread running ahead may already have
     changed shows up as wrong results or as a divergent barrier (tests/test_simt_select.py has the worked example)."""
+    if host_emu.family != "warp_per_query" and schedule == 2:
+        pytest.skip("one fuzzed schedule per family")
     try:
         for metric, nb, nq, k in ((0, 30_000, 10, 80), (1, 1_500, 150, 1), (0, 80_000, 5, 1100)):
             xb, xq = data.corpus(nb), data.queries(nq)
@@ -122,6 +134,8 @@ def test_row_shards_exchanging_thresholds_merge_to_the_exact_result(host_emu, me
     the bounded wait runs out); in the second round (same sequence number) it sees every other shard's final values next to
     its own early ones — the k-th-best rule bites when the shards differ (rows in document order), the ceil(k/R) rule needs
     the shards in step, which only real GPUs give (tests/test_gpu_sharded.py)."""
+    if host_emu.family != "warp_per_query" and (R != 2 or ordered):
+        pytest.skip("the CTA-per-query family publishes through the same code: two of the cases")
     if ordered:
         rng = np.random.default_rng(21)
         cent = rng.standard_normal((3, 128)).astype(np.float32)
