@@ -1227,10 +1227,11 @@ __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
     if (q >= p.nq) return;
     const uint64_t* keys = p.cand_keys + (size_t)q * p.n_sub * p.cap;
     const uint32_t* cnts = p.cand_cnt + (size_t)q * p.n_sub;
+    // A lone warp per query: every global read below is issued together with its neighbours (query, bound and counts up front;
+    // slab entries four slabs per round; the four rows of a group together) — the dependent chain is counts -> entries -> rows.
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
+    const float two_e = p.two_e[q];
     bool fail = p.q_bad[q] != 0;
-    // A lone warp per query: every global read below is issued together with its neighbours (counts: one per lane; slab
-    // entries: four slabs per round; rows: the four rows of a group) — one round trip per load made this kernel 30 % of a
-    // k-means assignment pass (21M points: 21 batches x 1.4 ms).
     // pass 1: best bf16 score over all candidates
     uint32_t best_hi = 0;
     for (int s0 = 0; s0 < p.n_sub; s0 += 32) {
@@ -1265,63 +1266,37 @@ __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best_hi = max(best_hi, __shfl_xor_sync(0xffffffffu, best_hi, o));
     uint64_t best = 0ull;
-    __align__(16) __shared__ float s_q[8][kDim];
     if (best_hi != 0 && !fail) {
-        const float bar = ordered_to_f32(best_hi) - p.two_e[q];
-        const int w = threadIdx.x >> 5;
-        reinterpret_cast<float4*>(s_q[w])[lane] = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
-        __syncwarp();
-        // pass 2: exact score of every row of the groups within 2E of the best — ONE LANE PER ROW: the rows of up to eight
-        // groups are dealt to the lanes and each lane runs the engine's defined score (eight fmaf chains of sixteen, tree) over
-        // its row against the query in shared memory.  (The warp-wide dot of round 1 cost ~40 instructions per row, ~500 per
-        // query: instruction-bound at 1.27 ms per million queries, 30 % of an assignment pass.)
-        int fill = 0;
-        long long myrow = -1;
-        auto flush = [&]() {
-            if (myrow >= 0) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.rows + (size_t)myrow * kDim);
-                const float4* q4 = reinterpret_cast<const float4*>(s_q[w]);
-                float pj[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 v = __ldg(r4 + 4 * j + i);
-                        const float4 qq = q4[4 * j + i];
-                        a = fmaf(v.x, qq.x, a);
-                        a = fmaf(v.y, qq.y, a);
-                        a = fmaf(v.z, qq.z, a);
-                        a = fmaf(v.w, qq.w, a);
-                    }
-                    pj[j] = a;
-                }
-                float sc = ((pj[0] + pj[1]) + (pj[2] + pj[3])) + ((pj[4] + pj[5]) + (pj[6] + pj[7]));
-                if (p.metric == kMetricL2) sc = fmaf(2.f, sc, -__ldg(p.row_norms + myrow));
-                if (sc >= PQ_THR_FLOOR) best = max(best, make_key(sc, (uint32_t)myrow));
-            }
-            myrow = -1;
-            fill = 0;
-        };
+        const float bar = ordered_to_f32(best_hi) - two_e;
+        // pass 2: exact score of every candidate within 2E of the best (the slab entries come from L1 now)
         for (int s = 0; s < p.n_sub; ++s) {
             const int n = (int)min(cnts[s], (uint32_t)p.cap);
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
                 const uint64_t key = i < n ? keys[(size_t)s * p.cap + i] : 0ull;
                 unsigned live = __ballot_sync(0xffffffffu, key != 0ull && key_score(key) >= bar);
-                while (live) {  // (warp-uniform)
+                while (live) {
                     const int src = __ffs(live) - 1;
                     live &= live - 1;
-                    const long long row0 = (long long)key_row(__shfl_sync(0xffffffffu, key, src));
-                    if (lane >= fill && lane < fill + 4 && row0 + (lane - fill) < p.n_rows) myrow = row0 + (lane - fill);
-                    fill += 4;
-                    if (fill == 32) flush();
+                    const uint32_t row0 = key_row(__shfl_sync(0xffffffffu, key, src));
+                    float4 rv[4];
+                    float rn[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // the four rows of the group, in flight together
+                        const bool in = (long long)(row0 + j) < p.n_rows;
+                        rv[j] = in ? __ldg(reinterpret_cast<const float4*>(p.rows + (size_t)(row0 + j) * kDim) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        rn[j] = (in && p.metric == kMetricL2) ? __ldg(p.row_norms + row0 + j) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if ((long long)(row0 + j) >= p.n_rows) break;
+                        float sc = warp_engine_dot(rv[j], qv, lane);
+                        if (p.metric == kMetricL2) sc = fmaf(2.f, sc, -rn[j]);
+                        if (sc >= PQ_THR_FLOOR) best = max(best, make_key(sc, row0 + j));
+                    }
                 }
             }
         }
-        flush();
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     }
     if (lane == 0) {
         float d;
