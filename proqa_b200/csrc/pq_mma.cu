@@ -1584,10 +1584,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             // what the row shards know together, before the next epoch admits on it — and after the last epoch, before the rescoring:
             // a shard's own k-th best score is far below the global one, so without the last exchange every shard would rescore
             // (and ship) ~k rows per query instead of ~k/n
-            // (not before the two or three tiny epochs at the start: a fold costs a launch plus the wait for the slowest shard, more
-            // than a tighter threshold saves on a few thousand rows)
-            const bool last = e + 1 == (int)plan.size();
-            if (share.n > 1 && (last || plan[e + 1].end - plan[e + 1].begin >= 32768)) {
+            if (share.n > 1) {
                 ix->prof_begin(2);
                 pq_share_fold_kernel<<<(nq + 255) / 256, 256, 0, ix->stream>>>(share, st, nq, e);
                 ix->prof_end();

@@ -114,15 +114,8 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
     // epochs would cover a larger part of the shard (8 shards of C3 with growth 32: 37 % of a shard's rows ran with 40 % of the
     // 32x32 chunks taking the append path — 51 ms against 36 ms for the same products with queries split instead).
     const int share_f = share_n >= 4 ? 4 : (share_n >= 2 ? 2 : 1);
-    long long growth = nq_pad <= 128 ? 64LL : (nq_pad <= 512 ? 16LL : 8LL);
-    long long n0 = std::min<long long>(N, std::max(1024, plan_next_pow2(2 * kp)));
-    // ... except that a few thousand queries on a shard are dominated by the per-epoch fixed cost (select, fold, launch, the
-    // wait for the slowest shard): one epoch fewer — twice the bootstrap, twice the growth (2k, 32k, 512k, N for 8 shards of 21M
-    // rows instead of 1k, 8k, 64k, 512k, N; the thresholds still reflect share_n times the rows).  Measured on 8 GPUs, C2.
-    if (share_n >= 2 && nq_pad > 512 && nq_pad <= 8192) {
-        growth *= 2;
-        n0 = std::min<long long>(N, 2 * n0);
-    }
+    const long long growth = nq_pad <= 128 ? 64LL : (nq_pad <= 512 ? 16LL : 8LL);
+    const long long n0 = std::min<long long>(N, std::max(1024, plan_next_pow2(2 * kp)));
     long long begin = 0, end = n0;
     while (begin < N) {
         EpochPlan ep;
