@@ -105,6 +105,8 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
         extract(mma, "int warp_sum(int v)"),
         extract(mma, "uint64_t warp_radix_select(const uint64_t* pool, int n, int want, int* hist, int lane)"),
         extract(mma, "struct WarpSelState {"),
+        extract(mma, "int warp_hist_rank(const int* hist, int want, int lane)"),
+        extract(mma, "bool warp_binned_bounds(const EpochSelParams& p"),
         extract(mma, "int warp_sel_reduce(const EpochSelParams& p"),
         extract(mma, "pq_epoch_select_warp_kernel(const EpochSelParams p)"),
         extract(mma, "struct RescoreParams {"),
