@@ -976,7 +976,7 @@ __device__ __forceinline__ int warp_sel_reduce(const EpochSelParams& p, uint64_t
 __global__ void __launch_bounds__(kSelWarps * 32) pq_epoch_select_warp_kernel(const EpochSelParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * kSelWarps + warp;
+    const int q = blockIdx.x + warp * gridDim.x;  // queries dealt round-robin to the CTAs (warp_query_grid): every SM gets the same number
     if (q >= p.nq) return;  // (whole warp; this kernel has no block-wide barrier)
     uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * kSelWarpPool;
     int* hist = reinterpret_cast<int*>(reinterpret_cast<uint64_t*>(smem_raw) + (size_t)kSelWarps * kSelWarpPool) + warp * 256;
@@ -1188,7 +1188,7 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const RescoreParams p) 
 __global__ void __launch_bounds__(kSelWarps * 32) pq_rescore_warp_kernel(const RescoreParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * kSelWarps + warp;
+    const int q = blockIdx.x + warp * gridDim.x;
     if (q >= p.nq) return;
     uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * p.kp;
     const uint64_t* carry = p.st.carry + (size_t)q * p.kp;
@@ -1456,12 +1456,19 @@ static int sel_warp_min_queries() {
     const char* s = getenv("PROQA_B200_SELECT_WARP_MIN");
     return (s && *s) ? atoi(s) : 1024;
 }
-static cudaError_t launch_epoch_select(const EpochSelParams& sp, int device, cudaStream_t stream) {
+// Grid of the warp-per-query kernels: a whole number of CTAs per SM, the queries dealt to them round-robin (q = block + warp x grid).
+// ceil(nq / 8) CTAs put 3.05 CTAs on an SM for C2's 3610 queries — eight SMs with a fourth CTA set the kernel's time (ncu: SMs busy
+// 112k of 170k cycles).
+static int warp_query_grid(int nq, int n_sms) {
+    const int per_wave = std::max(1, n_sms) * kSelWarps;
+    return std::max(1, n_sms) * ((nq + per_wave - 1) / per_wave);
+}
+static cudaError_t launch_epoch_select(const EpochSelParams& sp, int n_sms, int device, cudaStream_t stream) {
     if (sp.kp <= 256 && sp.nq >= sel_warp_min_queries()) {
         const size_t smem = (size_t)kSelWarps * (kSelWarpPool * 8 + 256 * 4);
         cudaError_t e = ensure_dyn_smem(pq_epoch_select_warp_kernel, smem, device);
         if (e != cudaSuccess) return e;
-        pq_epoch_select_warp_kernel<<<(sp.nq + kSelWarps - 1) / kSelWarps, kSelWarps * 32, smem, stream>>>(sp);
+        pq_epoch_select_warp_kernel<<<warp_query_grid(sp.nq, n_sms), kSelWarps * 32, smem, stream>>>(sp);
     } else {
         const size_t smem = ((size_t)sp.lmax + sp.kp) * 8 + (size_t)sp.n_sub * 8;
         cudaError_t e = ensure_dyn_smem(pq_epoch_select_kernel, smem, device);
@@ -1470,10 +1477,10 @@ static cudaError_t launch_epoch_select(const EpochSelParams& sp, int device, cud
     }
     return cudaGetLastError();
 }
-static cudaError_t launch_rescore(const RescoreParams& rp, int device, cudaStream_t stream) {
+static cudaError_t launch_rescore(const RescoreParams& rp, int n_sms, int device, cudaStream_t stream) {
     if (rp.kp <= 256 && rp.nq >= sel_warp_min_queries()) {
         const size_t smem = (size_t)kSelWarps * rp.kp * 8;
-        pq_rescore_warp_kernel<<<(rp.nq + kSelWarps - 1) / kSelWarps, kSelWarps * 32, smem, stream>>>(rp);
+        pq_rescore_warp_kernel<<<warp_query_grid(rp.nq, n_sms), kSelWarps * 32, smem, stream>>>(rp);
     } else {
         const size_t smem = (size_t)rp.work * 8;
         cudaError_t e = ensure_dyn_smem(pq_rescore_kernel, smem, device);
@@ -1640,7 +1647,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.allow_redo = ep.begin > 0 ? 1 : 0;  // the bootstrap epoch's slabs hold every row they can see
             sp.share = share;
             ix->prof_begin(1);
-            const cudaError_t se = launch_epoch_select(sp, ix->device, ix->stream);
+            const cudaError_t se = launch_epoch_select(sp, ix->n_sms, ix->device, ix->stream);
             ix->prof_end();
             PQ_CUDA(se);
             ix->stats[4] += 1;
@@ -1688,7 +1695,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         rp.fail = (uint8_t*)w[7].p;
         rp.fail_count = st.counters + 2;
         ix->prof_begin(3);
-        const cudaError_t re = launch_rescore(rp, ix->device, ix->stream);
+        const cudaError_t re = launch_rescore(rp, ix->n_sms, ix->device, ix->stream);
         ix->prof_end();
         PQ_CUDA(re);
         ix->stats[4] += 1;
@@ -1711,13 +1718,13 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
                 sp.is_redo = 1;
                 sp.allow_redo = 0;
                 sp.share.n = 0;
-                PQ_CUDA(launch_epoch_select(sp, ix->device, ix->stream));
+                PQ_CUDA(launch_epoch_select(sp, ix->n_sms, ix->device, ix->stream));
                 ix->stats[3] += 1;
                 ix->stats[4] += 1;
                 ix->stats[5] += 2;
             }
             PQ_CUDA(cudaMemsetAsync(st.counters + 2, 0, 4, ix->stream));
-            PQ_CUDA(launch_rescore(rp, ix->device, ix->stream));
+            PQ_CUDA(launch_rescore(rp, ix->n_sms, ix->device, ix->stream));
             ix->stats[4] += 1;
             ix->stats[5] += 1;
             uint32_t again[4] = {0, 0, 0, 0};

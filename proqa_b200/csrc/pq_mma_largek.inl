@@ -416,7 +416,7 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             sp.epoch_bit = 0u;
             sp.row_begin = ep.begin;
             sp.row_end = ep.end;
-            PQ_CUDA(launch_epoch_select(sp, ix->device, ix->stream));
+            PQ_CUDA(launch_epoch_select(sp, ix->n_sms, ix->device, ix->stream));
             ix->stats[3] += 1;
             ix->stats[4] += 1;
             ix->stats[5] += 2;

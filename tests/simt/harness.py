@@ -120,6 +120,7 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
     host = (extract(mma, "static int next_pow2i(int v)") + extract(mma, "static cudaError_t ensure_dyn_smem_impl(const void* fn")
             + extract(mma, "static cudaError_t ensure_dyn_smem(K* kernel, size_t smem, int device)")
             + extract(mma, "static int sel_warp_min_queries()")
+            + extract(mma, "static int warp_query_grid(int nq, int n_sms)")
             + extract(mma, "static cudaError_t launch_epoch_select(const EpochSelParams& sp")
             + extract(mma, "static cudaError_t launch_rescore(const RescoreParams& rp")
             + extract(mma, "static ShareParams make_share_params(const pq_index* ix")
