@@ -149,12 +149,14 @@ int pq_kmeans_finish_device(pq_index* index, int64_t k, int64_t n_total, int sph
 
 /* Introspection (no device needed; used by the CPU tests of the host logic): the launch plan of one tensor-tier search of nq
  * queries, top-k, over ntotal local rows on a device with n_sms SMs.  out[0..7] = {epochs, CTA groups, query tiles per group
- * (base), groups owning base+1, max tiles per group, carry length K', padded queries, 0}; then per epoch 8 values
- * {first row, end row, slices of the base+1 groups, slices of the base groups, slab capacity, CTAs, slabs per query, 0}. */
+ * (base), groups owning base+1, max tiles per group, carry length K', padded queries, epilogue warp sets of the widest kernel
+ * variant}; then per epoch 8 values {first row, end row, slices of the base+1 groups, slices of the base groups, slab capacity,
+ * CTAs, slabs per query, epilogue warp sets of the variant the epoch runs (4 while the threshold is loose, 2 once it is tight)}. */
 int pq_plan_describe(int64_t ntotal, int64_t nq, int64_t k, int n_sms, int64_t* out, int out_len);
-/* The same for 1024 < k <= PQ_MAX_K (retrieval/trec_process.py:76 asks for k = 10000).  That tensor-tier path — thresholds from a
- * row sample, one filter pass, a finalize kernel — is opt-in through the environment (PROQA_B200_LARGEK=1 at pq_index_create)
- * until validated on hardware; by default such k are answered by the exact fp32 scan.  out[0..15] = {applies, sample step,
+/* The same for 512 <= k <= PQ_MAX_K (retrieval/trec_process.py:76 asks for k = 10000; BASELINE C5 for k = 1000).  That tensor-tier
+ * path — thresholds from a row sample, one filter pass, a finalize kernel — is the default for such k on corpora of at least 64 k
+ * rows (512 <= k <= 1024: with at least 256 queries and 2^20 rows); PROQA_B200_LARGEK=0 at pq_index_create switches it off.
+ * out[0..15] = {applies, sample step,
  * k of the sample search, sample rows, finalize pool keys, sort length, sample epochs, pass slices (base+1 groups), pass slices
  * (base groups), slab capacity, pass CTAs, slabs per query, queries per batch, slab bytes of a batch, finalize shared-memory
  * bytes, carry length of the sample search}. */

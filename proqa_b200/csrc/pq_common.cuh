@@ -243,6 +243,34 @@ __device__ __forceinline__ float warp_engine_dot(const float4 a, const float4 b,
     return acc;
 }
 
+// engine_dot of FOUR rows by one warp: lane = 8 r + j computes chain p_j (dims 16j .. 16j+15, ascending, from 0) of row r from its
+// own 64 bytes of the row and the query in shared memory; three butterfly steps inside each group of eight lanes add the chains
+// in the tree of engine_dot (xor 1: p0+p1 ..., xor 2, xor 4; fp addition commutes, so every lane of the group ends with the same
+// bits).  35 instructions for four rows, against 4 x 35 with warp_engine_dot.  `row` may be null (lane group without a row).
+__device__ __forceinline__ float quad_engine_dot(const float* __restrict__ row, const float* q_smem, int lane) {
+    const int j = lane & 7;
+    float a = 0.f;
+    if (row != nullptr) {
+        const float4* r4 = reinterpret_cast<const float4*>(row + 16 * j);
+        const float4* q4 = reinterpret_cast<const float4*>(q_smem + 16 * j);
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __ldg(r4 + i);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 qq = q4[i];
+            a = fmaf(v[i].x, qq.x, a);
+            a = fmaf(v[i].y, qq.y, a);
+            a = fmaf(v[i].z, qq.z, a);
+            a = fmaf(v[i].w, qq.w, a);
+        }
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    return a;
+}
+
 // Bitonic sort of n (power of two) keys in shared memory by the whole CTA; ascending or descending.
 template <int kThreads>
 __device__ __forceinline__ void block_sort(uint64_t* a, int n, bool ascending) {

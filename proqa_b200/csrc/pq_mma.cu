@@ -1193,10 +1193,13 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_rescore_warp_kernel(const R
     uint64_t* work = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * p.kp;
     const uint64_t* carry = p.st.carry + (size_t)q * p.kp;
     const float bar = p.st.thr[q];
-    const float4 qv = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
+    __align__(16) __shared__ float s_q[kSelWarps][kDim];
+    reinterpret_cast<float4*>(s_q[warp])[lane] = __ldg(reinterpret_cast<const float4*>(p.queries + (size_t)q * kDim) + lane);
     uint64_t ck[8];   // kp <= 256: the carry in eight loads, all in flight together
 #pragma unroll
     for (int u = 0; u < 8; ++u) ck[u] = 32 * u < p.kp ? carry[32 * u + lane] : 0ull;
+    __syncwarp();
+    const int g = lane >> 3;  // lane group: scores the g-th of the (up to) four rows of a pass (quad_engine_dot)
 #pragma unroll
     for (int u8 = 0; u8 < 8; ++u8) {
         const int i0 = 32 * u8;
@@ -1204,34 +1207,25 @@ __global__ void __launch_bounds__(kSelWarps * 32) pq_rescore_warp_kernel(const R
         const uint64_t key = ck[u8];
         unsigned live = __ballot_sync(0xffffffffu, key != 0ull && key_score(key) >= bar);
         uint64_t mine = 0ull;
-        while (live) {  // warp-uniform
+        while (live) {  // warp-uniform: four candidates per pass
             int src[4];
-            uint32_t row[4];
-            float4 rv[4];
-            int n = 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 src[u] = -1;
                 if (live) {
                     src[u] = __ffs(live) - 1;
                     live &= live - 1;
-                    ++n;
                 }
             }
+            const int my_src = g == 0 ? src[0] : (g == 1 ? src[1] : (g == 2 ? src[2] : src[3]));
+            const uint32_t row = key_row(__shfl_sync(0xffffffffu, key, my_src < 0 ? 0 : my_src));
+            float sc = quad_engine_dot(my_src >= 0 ? p.rows + (size_t)row * kDim : nullptr, s_q[warp], lane);
+            if (my_src >= 0 && p.metric == kMetricL2) sc = fmaf(2.f, sc, -__ldg(p.row_norms + row));
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (u < n) {
-                    row[u] = key_row(__shfl_sync(0xffffffffu, key, src[u]));
-                    rv[u] = __ldg(reinterpret_cast<const float4*>(p.rows + (size_t)row[u] * kDim) + lane);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (u < n) {
-                    float acc = warp_engine_dot(rv[u], qv, lane);
-                    if (p.metric == kMetricL2) acc = fmaf(2.f, acc, -__ldg(p.row_norms + row[u]));
-                    if (lane == src[u] && acc >= PQ_THR_FLOOR) mine = make_key(acc, row[u]);
-                }
+                const float su = __shfl_sync(0xffffffffu, sc, 8 * u);
+                const uint32_t ru = __shfl_sync(0xffffffffu, row, 8 * u);
+                if (lane == src[u] && su >= PQ_THR_FLOOR) mine = make_key(su, ru);
             }
         }
         work[i0 + lane] = mine;
@@ -1330,9 +1324,15 @@ __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best_hi = max(best_hi, __shfl_xor_sync(0xffffffffu, best_hi, o));
     uint64_t best = 0ull;
+    __align__(16) __shared__ float s_q[8][kDim];
     if (best_hi != 0 && !fail) {
         const float bar = ordered_to_f32(best_hi) - two_e;
-        // pass 2: exact score of every candidate within 2E of the best (the slab entries come from L1 now)
+        const int w = threadIdx.x >> 5;
+        reinterpret_cast<float4*>(s_q[w])[lane] = qv;
+        __syncwarp();
+        // pass 2: exact score of every candidate within 2E of the best (the slab entries come from L1 now).  A record is a group of
+        // four consecutive rows: one quad_engine_dot scores all four (ncu: this kernel was issue-bound at 870 instructions per
+        // query, most of them the row-by-row warp-wide dots).
         for (int s = 0; s < p.n_sub; ++s) {
             const int n = (int)min(cnts[s], (uint32_t)p.cap);
             for (int i0 = 0; i0 < n; i0 += 32) {
@@ -1342,25 +1342,18 @@ __global__ void __launch_bounds__(256) pq_k1_finalize_kernel(const K1Params p) {
                 while (live) {
                     const int src = __ffs(live) - 1;
                     live &= live - 1;
-                    const uint32_t row0 = key_row(__shfl_sync(0xffffffffu, key, src));
-                    float4 rv[4];
-                    float rn[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // the four rows of the group, in flight together
-                        const bool in = (long long)(row0 + j) < p.n_rows;
-                        rv[j] = in ? __ldg(reinterpret_cast<const float4*>(p.rows + (size_t)(row0 + j) * kDim) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        rn[j] = (in && p.metric == kMetricL2) ? __ldg(p.row_norms + row0 + j) : 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if ((long long)(row0 + j) >= p.n_rows) break;
-                        float sc = warp_engine_dot(rv[j], qv, lane);
-                        if (p.metric == kMetricL2) sc = fmaf(2.f, sc, -rn[j]);
-                        if (sc >= PQ_THR_FLOOR) best = max(best, make_key(sc, row0 + j));
+                    const long long row = (long long)key_row(__shfl_sync(0xffffffffu, key, src)) + (lane >> 3);
+                    const bool in = row < p.n_rows;
+                    float sc = quad_engine_dot(in ? p.rows + (size_t)row * kDim : nullptr, s_q[w], lane);
+                    if (in) {
+                        if (p.metric == kMetricL2) sc = fmaf(2.f, sc, -__ldg(p.row_norms + row));
+                        if (sc >= PQ_THR_FLOOR) best = max(best, make_key(sc, (uint32_t)row));
                     }
                 }
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     }
     if (lane == 0) {
         float d;

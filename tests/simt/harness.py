@@ -46,6 +46,7 @@ def sources():
 def key_and_sort_helpers(common):
     return [extract(common, "uint32_t f32_to_ordered(float f)", upto="uint32_t key_row(uint64_t key)"),
             extract(common, "float warp_engine_dot(const float4 a, const float4 b, int lane)"),
+            extract(common, "float quad_engine_dot(const float* __restrict__ row, const float* q_smem, int lane)"),
             extract(common, "void block_sort(uint64_t* a, int n, bool ascending)"),
             extract(common, "void block_sort_desc(uint64_t* a, int n)")]
 
