@@ -1488,7 +1488,8 @@ static ShareParams make_share_params(const pq_index* ix, int nq, int k, int batc
     ShareParams sh;
     memset(&sh, 0, sizeof(sh));
     const pq_share_state& ss = ix->share;
-    if (!ss.connected || ss.n < 2 || ss.n > kShareMaxPeers || nq > ss.cap_q || k == 1) return sh;
+    // (the tag has four bits for the query batch: a search of more than 16 batches of 2^18 queries exchanges nothing after the 16th)
+    if (!ss.connected || ss.n < 2 || ss.n > kShareMaxPeers || nq > ss.cap_q || k == 1 || batch >= 16) return sh;
     sh.n = ss.n;
     sh.rank = ss.rank;
     sh.kr = (k + ss.n - 1) / ss.n;
