@@ -574,6 +574,8 @@ int pq_index_create(int d, int metric, int device, pq_index** out) {
         if (!strcmp(t, "fp32")) ix->tier = PQ_TIER_FP32;
         else if (!strcmp(t, "bf16")) ix->tier = PQ_TIER_BF16;
     }
+    const char* ks = getenv("PROQA_B200_K1_SETS");
+    if (ks && (atoi(ks) == 2 || atoi(ks) == 4)) plan_k1_sets() = atoi(ks);
     const char* lk = getenv("PROQA_B200_LARGEK");
     ix->largek = !(lk && !strcmp(lk, "0"));  // tensor tier for 1024 < k unless switched off
     *out = ix;  // CUDA is touched lazily (first add/search): the reference forks after importing faiss

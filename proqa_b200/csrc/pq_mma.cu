@@ -1520,7 +1520,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         const ShareParams share = make_share_params(ix, nq, k, batch);
 
         // ---- epoch plan (pq_plan.h) -----------------------------------------------------------
-        const std::vector<EpochPlan> plan = plan_epochs(N, k, nq_pad, gs, ix->n_sms, share.n > 1 ? share.n : 1);
+        const std::vector<EpochPlan> plan = plan_epochs(N, k, nq_pad, gs, ix->n_sms, share.n > 1 ? share.n : 1, l2);
         if (plan.size() > 31) return set_error(PQ_ERR_UNSUPPORTED, "search: %zu epochs", plan.size());
         size_t max_slab = 0, max_cnt = 0;
         for (const EpochPlan& ep : plan) {

@@ -26,6 +26,12 @@ inline int plan_sets_for(double k, double seen_rows) {
     return 1024.0 * per_pair > 0.10 ? kPlanSetsLoose : kPlanSetsTight;
 }
 
+// (tuning hook, PROQA_B200_K1_SETS: epilogue warp sets of the k = 1 pass; 0 = the default)
+inline int& plan_k1_sets() {
+    static int v = 0;
+    return v;
+}
+
 struct EpochPlan {
     long long begin, end;
     int s1, s0, cap;   // row slices per CTA group (groups owning base+1 / base query tiles), slab capacity
@@ -92,7 +98,7 @@ inline void pick_slices(const GridShape& g, int n_mtiles, long long tiles, int n
 // Epochs of one search over rows [0, N): contiguous, in order, covering every row once.
 // share_n > 1: the corpus is row-sharded over share_n GPUs that exchange thresholds after every epoch (pq_mma.cu:
 // ShareParams), so a threshold reflects share_n times the rows this shard has seen: slabs stay small.
-inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const GridShape& gs, int n_sms, int share_n = 1) {
+inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const GridShape& gs, int n_sms, int share_n = 1, bool l2 = true) {
     std::vector<EpochPlan> plan;
     const int n_mtiles = nq_pad / kPlanQueryTile;
     const int kp = carry_size_for_k(k);
@@ -101,7 +107,10 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
         ep.begin = 0;
         ep.end = N;
         pick_slices(gs, n_mtiles, (N + kPlanTileRows - 1) / kPlanTileRows, n_sms, &ep.s1, &ep.s0);
-        ep.sets = kPlanSetsLoose;      // the running-maximum filter records often (C4 L2: 0.52 -> 0.58 of peak with four sets)
+        // the running-maximum filter records often.  L2 (bias epilogue: the most instructions per column) gains from four warp sets
+        // (filter 61.8 -> 55.2 ms on C4, pass 87.5 -> 83.5 ms); IP does not (46.6 vs 45.8 ms) and pays for the two extra slabs per query
+        // in the finalize (pass 71.3 vs 73.2 ms) — measured A/B, tools/gpu_runs/r02_r_k1sets.sh
+        ep.sets = plan_k1_sets() ? plan_k1_sets() : (l2 ? kPlanSetsLoose : kPlanSetsTight);
         ep.cap = 128 / ep.sets;        // a thread keeps only rows within 2E of its running maximum: a few dozen at most
         plan.push_back(ep);
         return plan;
