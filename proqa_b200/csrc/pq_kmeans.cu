@@ -25,7 +25,6 @@
 #include <random>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
 
 namespace pq {
 
@@ -57,6 +56,112 @@ __global__ void km_keys_kernel(const long long* __restrict__ assign, int n, int*
     vals[i] = i;
     atomicAdd(hist + (int)a, 1);
 }
+
+// ---- stable sort of (centroid, point index) pairs by centroid: the engine's own LSD radix sort ---------------------------------
+// The centroid sums must add each centroid's points in ascending point index (that is what makes them bit-identical to
+// Clustering::train's sequential sums), so the sort has to be stable.  8-bit digits, ceil(key_bits / 8) passes, each:
+//   km_sort_hist_kernel     block b counts the digits of its contiguous chunk of kSortChunk elements      -> H[digit][block]
+//   km_sort_scan_kernel     exclusive prefix sum over H in (digit, block) order, one CTA                      -> base offsets
+//   km_sort_scatter_kernel  block b walks its chunk in order, 256 elements at a time; an element's place is the base of
+//                           (its digit, this block) + the elements of that digit seen earlier in the chunk (a shared-memory
+//                           running count + the earlier warps of this tile + the earlier lanes of its warp: __match_any_sync)
+// (Round 1 called cub::DeviceRadixSort here — the one library kernel on the f1 path.)
+constexpr int kSortChunk = 4096;
+
+__global__ void __launch_bounds__(256) km_sort_hist_kernel(const int* __restrict__ keys, int n, int shift, int n_blocks, int* __restrict__ H) {
+    __shared__ int s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long a = (long long)blockIdx.x * kSortChunk;
+    const int end = (int)min((long long)n, a + kSortChunk);
+    for (int i = (int)a + threadIdx.x; i < end; i += 256) atomicAdd(&s_h[(keys[i] >> shift) & 255], 1);
+    __syncthreads();
+    H[(size_t)threadIdx.x * n_blocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) km_sort_scan_kernel(int* __restrict__ H, int total) {
+    __shared__ int s_sum[1024];
+    const int t = threadIdx.x;
+    const int per = (total + 1023) / 1024;
+    const int a = min(total, t * per), b = min(total, a + per);
+    int run = 0;
+    for (int i = a; i < b; ++i) run += H[i];
+    s_sum[t] = run;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan of the per-thread sums
+        const int v = t >= o ? s_sum[t - o] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    int base = s_sum[t] - run;
+    for (int i = a; i < b; ++i) {
+        const int c = H[i];
+        H[i] = base;
+        base += c;
+    }
+}
+
+__global__ void __launch_bounds__(256) km_sort_scatter_kernel(const int* __restrict__ keys_in, const int* __restrict__ vals_in, int n, int shift,
+                                                              int n_blocks, const int* __restrict__ H, int* __restrict__ keys_out,
+                                                              int* __restrict__ vals_out) {
+    __shared__ int s_run[256];       // elements of each digit placed so far by this block
+    __shared__ int s_warp[8][256];   // per tile: digit counts of each warp
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    s_run[t] = H[(size_t)t * n_blocks + blockIdx.x];
+    const long long a = (long long)blockIdx.x * kSortChunk;
+    const int end = (int)min((long long)n, a + kSortChunk);
+    for (int i0 = (int)a; i0 < end; i0 += 256) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s_warp[w][t] = 0;
+        __syncthreads();
+        const int i = i0 + t;
+        const bool in = i < end;
+        const int key = in ? keys_in[i] : 0, val = in ? vals_in[i] : 0;
+        const int digit = (key >> shift) & 255;
+        const unsigned act = __ballot_sync(0xffffffffu, in);
+        int rank_in_warp = 0;
+        if (in) {
+            const unsigned peers = __match_any_sync(act, digit);
+            rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (rank_in_warp == 0) s_warp[warp][digit] = __popc(peers);   // (the first lane of each digit group records the group's size)
+        }
+        __syncthreads();
+        if (in) {
+            int before = s_run[digit];
+            for (int w = 0; w < warp; ++w) before += s_warp[w][digit];
+            const int dst = before + rank_in_warp;
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+        }
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += s_warp[w][t];
+        s_run[t] += tot;
+        __syncthreads();
+    }
+}
+
+// Sorts n pairs by the low key_bits bits of the key, stably.  a and b are two (keys, vals) buffer pairs: the input is in a, the
+// passes alternate between them, *vals_sorted tells where the sorted values ended up.  H: (256 * ceil(n / kSortChunk)) ints.
+static cudaError_t km_sort_pairs(int* keys_a, int* vals_a, int* keys_b, int* vals_b, int n, int key_bits, int* H, cudaStream_t st,
+                                 const int** vals_sorted) {
+    const int n_blocks = (n + kSortChunk - 1) / kSortChunk;
+    int *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        km_sort_hist_kernel<<<n_blocks, 256, 0, st>>>(ki, n, shift, n_blocks, H);
+        km_sort_scan_kernel<<<1, 1024, 0, st>>>(H, 256 * n_blocks);
+        km_sort_scatter_kernel<<<n_blocks, 256, 0, st>>>(ki, vi, n, shift, n_blocks, H, ko, vo);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        std::swap(ki, ko);
+        std::swap(vi, vo);
+    }
+    *vals_sorted = vi;
+    return cudaSuccess;
+}
+static size_t km_sort_workspace_bytes(long long n) { return (size_t)256 * (size_t)((n + kSortChunk - 1) / kSortChunk) * 4; }
 
 // One warp per centroid: lane l owns dims 4l..4l+3; points are added in ascending point index (stable sort order).
 // kMean = false leaves the plain sums (multi-GPU training: the shards' sums are all-reduced before the division).
@@ -325,10 +430,7 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
     KM_TRY(d_perm.ensure((size_t)k * 4));
     int key_bits = 1;
     while ((1LL << key_bits) < k) ++key_bits;
-    size_t tmp_bytes = 0;
-    KM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int*)d_keys.p, (int*)d_keys2.p, (const int*)d_vals.p, (int*)d_vals2.p, (int)nx, 0,
-                                            key_bits, st));
-    KM_TRY(d_tmp.ensure(tmp_bytes));
+    KM_TRY(d_tmp.ensure(km_sort_workspace_bytes(nx)));
 
     std::vector<float> cent((size_t)k * kDim), best_cent;
     std::vector<int> hassign((size_t)k), offsets((size_t)k);
@@ -362,8 +464,8 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
             KM_CUDA(cudaMemsetAsync(d_hist.p, 0, (size_t)k * 4, st));
             km_keys_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>((const long long*)d_I.p, (int)nx, (int*)d_keys.p, (int*)d_vals.p, (int*)d_hist.p,
                                                                         (int)k);
-            KM_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, (const int*)d_keys.p, (int*)d_keys2.p, (const int*)d_vals.p, (int*)d_vals2.p, (int)nx,
-                                                    0, key_bits, st));
+            const int* sorted_idx = nullptr;
+            KM_CUDA(km_sort_pairs((int*)d_keys.p, (int*)d_vals.p, (int*)d_keys2.p, (int*)d_vals2.p, (int)nx, key_bits, (int*)d_tmp.p, st, &sorted_idx));
             KM_CUDA(cudaMemcpyAsync(hassign.data(), d_hist.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
             KM_CUDA(cudaStreamSynchronize(st));
             double e64 = 0.0;
@@ -380,7 +482,7 @@ static int kmeans_train_locked(pq_index* ix, int64_t k, const pq_kmeans_params& 
             }
             const double imbalance = uf * (double)k / ((double)run * (double)run);
             KM_CUDA(cudaMemcpyAsync(d_off.p, offsets.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
-            km_centroid_kernel<true><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, (const int*)d_vals2.p, (const int*)d_off.p, (const int*)d_hist.p, (int)k,
+            km_centroid_kernel<true><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, sorted_idx, (const int*)d_off.p, (const int*)d_hist.p, (int)k,
                                                                        (float*)d_cent.p);
             KM_CUDA(cudaGetLastError());
             int nsplit = 0;
@@ -470,9 +572,7 @@ static int kmeans_partial_locked(pq_index* ix, int64_t k, int64_t n, const float
     if (rc) return rc;
     int key_bits = 1;
     while ((1LL << key_bits) < k) ++key_bits;
-    size_t tmp_bytes = 0;
-    PQ_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int*)w[3].p, (int*)w[4].p, (const int*)w[5].p, (int*)w[6].p, (int)n, 0, key_bits, st));
-    rc = w[8].ensure(tmp_bytes);
+    rc = w[8].ensure(km_sort_workspace_bytes(n));
     if (rc) return rc;
     rc = search_device_impl(ix, n, dx, 1, (float*)w[1].p, (long long*)w[2].p);  // leaves the stream drained
     if (rc) return rc;
@@ -480,7 +580,8 @@ static int kmeans_partial_locked(pq_index* ix, int64_t k, int64_t n, const float
     km_objective_kernel<<<1024, 256, 0, st>>>((const float*)w[1].p, (int)n, (double*)w[9].p);
     PQ_CUDA(cudaMemcpyAsync(partial.data(), w[9].p, 1024 * 8, cudaMemcpyDeviceToHost, st));
     km_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const long long*)w[2].p, (int)n, (int*)w[3].p, (int*)w[5].p, counts_dev, (int)k);
-    PQ_CUDA(cub::DeviceRadixSort::SortPairs(w[8].p, tmp_bytes, (const int*)w[3].p, (int*)w[4].p, (const int*)w[5].p, (int*)w[6].p, (int)n, 0, key_bits, st));
+    const int* sorted_idx = nullptr;
+    PQ_CUDA(km_sort_pairs((int*)w[3].p, (int*)w[5].p, (int*)w[4].p, (int*)w[6].p, (int)n, key_bits, (int*)w[8].p, st, &sorted_idx));
     std::vector<int> hassign((size_t)k), offsets((size_t)k);
     PQ_CUDA(cudaMemcpyAsync(hassign.data(), counts_dev, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
     PQ_CUDA(cudaStreamSynchronize(st));
@@ -490,7 +591,7 @@ static int kmeans_partial_locked(pq_index* ix, int64_t k, int64_t n, const float
         run += hassign[c];
     }
     PQ_CUDA(cudaMemcpyAsync(w[7].p, offsets.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
-    km_centroid_kernel<false><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, (const int*)w[6].p, (const int*)w[7].p, counts_dev, (int)k, sums_dev);
+    km_centroid_kernel<false><<<(unsigned)((k + 7) / 8), 256, 0, st>>>(dx, sorted_idx, (const int*)w[7].p, counts_dev, (int)k, sums_dev);
     PQ_CUDA(cudaGetLastError());
     PQ_CUDA(cudaStreamSynchronize(st));  // `offsets` (host vector) must outlive its copy; the caller all-reduces next
     double e64 = 0.0;

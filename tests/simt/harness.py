@@ -263,8 +263,8 @@ def merge_di(lib, D_all, I_all, k, metric):
 
 
 def build_kmeans_emu(workdir):
-    """pq_kmeans.cu: the single-GPU driver and the staged (multi-GPU) steps with their kernels; CUB sort and the index
-    replaced by stand-ins (kmeans_emu.cpp.in)."""
+    """pq_kmeans.cu: the single-GPU driver and the staged (multi-GPU) steps with their kernels (incl. the engine's own stable
+    radix sort); the index replaced by a stand-in (kmeans_emu.cpp.in)."""
     common = open(os.path.join(CSRC, "pq_common.cuh")).read()
     km = open(os.path.join(CSRC, "pq_kmeans.cu")).read()
     helpers = "\n".join(key_and_sort_helpers(common)[:2] + [extract(common, "float engine_dot(const float* __restrict__ a")])
@@ -290,6 +290,8 @@ def load_kmeans_emu(path):
         getattr(lib, name).argtypes = args
     lib.emu_km_assign.restype = ll
     lib.emu_km_assign.argtypes = [vp, ll, vp, vp]
+    lib.emu_km_sort.restype = ctypes.c_char_p
+    lib.emu_km_sort.argtypes = [vp, vp, i32, i32, vp]
     return lib
 
 

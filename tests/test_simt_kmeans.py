@@ -244,3 +244,21 @@ def test_group_paras_flow_on_the_emulated_driver_matches_the_fixture(km):
     np.testing.assert_allclose(D, fx["D"], rtol=1e-3, atol=3e-3)
     assert [len(s) for s in samples] == fx["split_sizes"].tolist()
     assert np.concatenate([np.array(s, np.int32) for s in samples]).tolist() == fx["split_lines"].tolist()
+
+
+# ---- the engine's own stable radix sort (replaces cub::DeviceRadixSort on the k-means path) ------------------------------------
+@pytest.mark.parametrize("n,k", [(1, 2), (300, 7), (4096, 256), (4097, 300), (20_000, 10_000), (13_000, 70_000)])
+def test_stable_sort_by_centroid_matches_numpy(km, n, k):
+    """Pairs (centroid of point i, i) sorted by centroid, stably: every centroid's points come out in ascending point index — the
+    order Clustering::train adds them in.  One, two and three 8-bit passes; chunks of 4096 elements per block, ragged last chunk."""
+    rng = np.random.default_rng(n + k)
+    keys = rng.integers(0, k, n).astype(np.int32)
+    keys[: min(n, 50)] = keys[0]                      # a run of equal keys across warp and tile boundaries
+    vals = np.arange(n, dtype=np.int32)
+    out = np.full(n, -9, np.int32)
+    key_bits = 1
+    while (1 << key_bits) < k:
+        key_bits += 1
+    msg = km.emu_km_sort(keys.ctypes.data, vals.ctypes.data, n, key_bits, out.ctypes.data)
+    assert msg is None, msg
+    np.testing.assert_array_equal(out, np.argsort(keys, kind="stable").astype(np.int32))
