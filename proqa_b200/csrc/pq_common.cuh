@@ -208,6 +208,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// 16-byte read-only load the compiler must issue where it stands (a plain __ldg may be sunk next to its use, which serialises
+// the round trips of a latency-bound gather).
+__device__ __forceinline__ float4 ldg_f4_now(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // 8-byte asynchronous copy global -> shared (LDGSTS): no register staging, any number in flight per thread.
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");

@@ -88,10 +88,19 @@ __device__ __forceinline__ uint32_t slab_radix_select_score(const uint64_t* keys
     uint32_t a = ~0u, o = 0u;
     for (int s = warp; s < n_sub; s += 8) {
         const uint64_t* src = keys + (size_t)s * cap;
-        for (int pos = lane; pos < s_cnt[s]; pos += 32) {
-            const uint32_t u = (uint32_t)(src[pos] >> 32);
-            a &= u;
-            o |= u;
+        const int n = s_cnt[s];
+        for (int p0 = 0; p0 < n; p0 += 128) {  // four loads in flight per lane (the slabs are read from L2: one round trip each)
+            uint64_t kv[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) kv[u4] = p0 + 32 * u4 + lane < n ? src[p0 + 32 * u4 + lane] : 0ull;
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                if (p0 + 32 * u4 + lane < n) {
+                    const uint32_t u = (uint32_t)(kv[u4] >> 32);
+                    a &= u;
+                    o |= u;
+                }
+            }
         }
     }
 #pragma unroll
@@ -122,19 +131,27 @@ __device__ __forceinline__ uint32_t slab_radix_select_score(const uint64_t* keys
         for (int s = warp; s < n_sub; s += 8) {
             const uint64_t* src = keys + (size_t)s * cap;
             const int n = s_cnt[s];
-            for (int p0 = 0; p0 < n; p0 += 32) {  // warp-uniform trip count
-                const int pos = p0 + lane;
-                uint32_t u = 0;
-                bool in = false;
-                if (pos < n) {
-                    u = (uint32_t)(src[pos] >> 32);
-                    in = ((u ^ prefix) & mask) == 0;
-                }
-                const unsigned act = __ballot_sync(0xffffffffu, in);
-                if (in) {
-                    const int digit = (int)((u >> shift) & dmask);
-                    const unsigned peers = __match_any_sync(act, digit);
-                    if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+            for (int q0 = 0; q0 < n; q0 += 128) {  // warp-uniform trip counts; four loads in flight per lane
+                uint64_t kv[4];
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) kv[u4] = q0 + 32 * u4 + lane < n ? src[q0 + 32 * u4 + lane] : 0ull;
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int p0 = q0 + 32 * u4;
+                    if (p0 >= n) break;
+                    const int pos = p0 + lane;
+                    uint32_t u = 0;
+                    bool in = false;
+                    if (pos < n) {
+                        u = (uint32_t)(kv[u4] >> 32);
+                        in = ((u ^ prefix) & mask) == 0;
+                    }
+                    const unsigned act = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int digit = (int)((u >> shift) & dmask);
+                        const unsigned peers = __match_any_sync(act, digit);
+                        if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+                    }
                 }
             }
         }
@@ -221,16 +238,24 @@ __global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKPar
         for (int s = warp; s < p.n_sub; s += 8) {
             const uint64_t* src = keys + (size_t)s * p.cap;
             const int n = s_cnt[s];
-            for (int p0 = 0; p0 < n; p0 += 32) {
-                const int pos = p0 + lane;
-                const uint64_t key = pos < n ? src[pos] : 0ull;
-                const bool hit = pos < n && key_score(key) >= bar;
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                int base = 0;
-                if (lane == 0 && m) base = atomicAdd(&s_slot, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int dst = base + __popc(m & ((1u << lane) - 1u));
-                if (hit && dst < p.pool) pool[dst] = key;
+            for (int q0 = 0; q0 < n; q0 += 128) {
+                uint64_t kv[4];
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) kv[u4] = q0 + 32 * u4 + lane < n ? src[q0 + 32 * u4 + lane] : 0ull;
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int p0 = q0 + 32 * u4;
+                    if (p0 >= n) break;
+                    const int pos = p0 + lane;
+                    const uint64_t key = kv[u4];
+                    const bool hit = pos < n && key_score(key) >= bar;
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    int base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&s_slot, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const int dst = base + __popc(m & ((1u << lane) - 1u));
+                    if (hit && dst < p.pool) pool[dst] = key;
+                }
             }
         }
         __syncthreads();
@@ -245,13 +270,16 @@ __global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKPar
             const uint32_t row = key_row(pool[i]);
             // the engine's defined score (pq_common.cuh: engine_dot): 8 chains of 16 dims, tree-combined
             const float4* r4 = reinterpret_cast<const float4*>(p.rows + (size_t)row * kDim);
+            float4 rv[32];   // the whole row in flight (one CTA per SM: registers are plentiful, loads in flight are what is short)
+#pragma unroll
+            for (int l = 0; l < 32; ++l) rv[l] = ldg_f4_now(r4 + l);
             float pj[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float a = 0.f;
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 v = __ldg(r4 + 4 * j + i4);
+                    const float4 v = rv[4 * j + i4];
                     a = fmaf(v.x, s_q[16 * j + 4 * i4 + 0], a);
                     a = fmaf(v.y, s_q[16 * j + 4 * i4 + 1], a);
                     a = fmaf(v.z, s_q[16 * j + 4 * i4 + 2], a);

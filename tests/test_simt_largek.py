@@ -39,6 +39,7 @@ constexpr int kDim = 128;
 constexpr int kMetricL2 = 1;
 #define PQ_THR_FLOOR (-3.4028232635611926e38f)
 alignas(16) uint8_t smem_raw[232448];
+static float4 ldg_f4_now(const float4* p) { return *p; }   // (inline-PTX load of the engine: a plain read here)
 %s
 }  // namespace pq
 
