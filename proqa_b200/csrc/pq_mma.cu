@@ -152,16 +152,17 @@ __device__ __forceinline__ void mma_append_if(bool hit, uint64_t* slab, uint32_t
 }
 // rows past the end of the epoch (TMA zero fill in the last tile, stale norms) must not look like scores
 __device__ __forceinline__ void mma_mask_tail(float (&v)[32], uint32_t base_row, uint32_t row_end32) {
-    if (base_row + 32 > row_end32) {  // warp-uniform, last tile only
+    const int left = (int)(row_end32 - base_row);  // rows of this chunk inside the epoch (negative: none); one uniform value,
+    if (left < 32) {                               // compared with immediates — warp-uniform, last tile only
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-            if (base_row + c >= row_end32) v[c] = -INFINITY;
+            if (c >= left) v[c] = -INFINITY;
     }
 }
 
 __device__ __forceinline__ void mma_filter32(float (&v)[32], float th, uint32_t base_row, uint32_t row_end32, uint64_t* slab, uint32_t& cnt,
                                              uint32_t cap) {
-    mma_mask_tail(v, base_row, row_end32);
+    // (the caller has masked the rows past the end of the epoch: mma_mask_tail)
     float g4[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) g4[g] = fmaxf(fmaxf(v[4 * g], v[4 * g + 1]), fmaxf(v[4 * g + 2], v[4 * g + 3]));
@@ -175,6 +176,46 @@ __device__ __forceinline__ void mma_filter32(float (&v)[32], float th, uint32_t 
             }
         }
     }
+}
+
+// Maximum of all the accumulator values a thread holds for one accumulator (kChunks x 32 columns), as a tree of 3-input
+// maxima (FMNMX3): 16 instructions per 32 values.  The steady state of a search — threshold tight, a survivor in one
+// accumulator out of ten — is then ONE compare and ONE vote per accumulator and warp; only a warp that has a survivor
+// goes on to locate it (mma_filter32).  The epilogue's instruction count is what this kernel's power budget is spent on
+// besides the MMAs themselves (the kernel runs at the power cap: every instruction saved is clock gained).
+__device__ __forceinline__ float mma_max3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    float d;  // one FMNMX3; as opaque asm the compiler cannot re-associate the tree into the two-input maxima of the slow path
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+template <int N>
+__device__ __forceinline__ float mma_max_reduce(float (&a)[N]) {
+    if constexpr (N == 1) {
+        return a[0];
+    } else if constexpr (N == 2) {
+        return fmaxf(a[0], a[1]);
+    } else {
+        constexpr int T = N / 3, R = N % 3;
+        float b[T + R];
+#pragma unroll
+        for (int i = 0; i < T; ++i) b[i] = mma_max3(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) b[T + r] = a[3 * T + r];
+        return mma_max_reduce<T + R>(b);
+    }
+}
+template <int kChunks>
+__device__ __forceinline__ float mma_max_all(float (&v)[kChunks][32]) {
+    float a[kChunks * 32];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[c * 32 + i] = v[c][i];
+    return mma_max_reduce<kChunks * 32>(a);
 }
 
 // k = 1 variant (k-means assignment: few rows per thread, so survivors are common).  The thread keeps a running maximum;
@@ -363,23 +404,23 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         }
         const uint32_t row_end32 = (uint32_t)p.row_end;
         const uint32_t cap = (uint32_t)p.cap;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * kSubN);
+        uint32_t base_row = (uint32_t)(row0 + set * kSubN);  // first row of this warp set's columns in tile t
+        uint32_t j = 0;                                      // accumulator sequence number t * m + mi
 #pragma unroll 1
-        for (int t = 0; t < ntiles; ++t) {
-            const uint32_t base_row = (uint32_t)(row0 + (long long)t * tile_stride + set * kSubN);
+        for (int t = 0; t < ntiles; ++t, base_row += (uint32_t)tile_stride) {
             const int s = t % kStages;
             const float4* norms = reinterpret_cast<const float4*>(smem_b + (size_t)s * kStageBytes + kTileBytes) + set * (kSubN / 4);
             if (kL2) mbar_wait(&ctrl->full[s], (uint32_t)(t / kStages) & 1u);  // already complete (the MMAs needed it): acquire only
+            const bool tail = base_row + kSubN > row_end32;  // warp-uniform: rows past the end of the epoch (last tile only)
 #pragma unroll 1
-            for (int mi = 0; mi < m; ++mi) {
-                const int j = t * m + mi;
-                const int b = j & 1;
-                const uint32_t aph = (uint32_t)(j >> 1) & 1u;
-                mbar_wait(&ctrl->tmem_full[b], aph);
+            for (int mi = 0; mi < m; ++mi, ++j) {
+                const uint32_t b = j & 1u;
+                mbar_wait(&ctrl->tmem_full[b], (j >> 1) & 1u);
                 tc_fence_after_sync();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kBN + set * kSubN);
                 float v[kSubChunks][32];
 #pragma unroll
-                for (int c = 0; c < kSubChunks; ++c) tmem_ld_32x32(taddr + 32 * c, v[c]);
+                for (int c = 0; c < kSubChunks; ++c) tmem_ld_32x32(taddr0 + b * kBN + 32 * c, v[c]);
                 tmem_ld_wait();
                 // The accumulator is in registers now: hand the TMEM buffer back before filtering.
                 tc_fence_before_sync();
@@ -394,20 +435,37 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
                     }
                 }
                 const int slot = mi * kEpiThreads + tid_e;
-                uint64_t* slab = p.cand_keys + (((size_t)(mt0 + mi) * kBM + lane_q) * p.n_sub + sub) * (size_t)cap;
-                uint32_t cnt = s_cnt[slot];
-                const uint32_t cnt_in = cnt;
-                float th = s_thr[slot];
                 if (kK1) {
+                    uint64_t* slab = p.cand_keys + (((size_t)(mt0 + mi) * kBM + lane_q) * p.n_sub + sub) * (size_t)cap;
+                    uint32_t cnt = s_cnt[slot];
+                    const uint32_t cnt_in = cnt;
+                    float th = s_thr[slot];
                     const float two_e = s_2e[slot];
 #pragma unroll
                     for (int c = 0; c < kSubChunks; ++c) mma_filter32_k1(v[c], th, two_e, base_row + 32 * c, row_end32, slab, cnt, cap);
                     s_thr[slot] = th;
+                    if (cnt != cnt_in) s_cnt[slot] = cnt;
                 } else {
+                    const float th = s_thr[slot];
+                    if (tail) {
 #pragma unroll
-                    for (int c = 0; c < kSubChunks; ++c) mma_filter32(v[c], th, base_row + 32 * c, row_end32, slab, cnt, cap);
+                        for (int c = 0; c < kSubChunks; ++c) mma_mask_tail(v[c], base_row + 32 * c, row_end32);
+                    }
+                    // fast path (tight-threshold variant): no thread of the warp has a survivor anywhere in this accumulator.
+                    // The loose-threshold variant nearly always has one, so it goes straight to the per-chunk votes.
+                    if (kEpiSets == kMaxEpiSets || __any_sync(0xffffffffu, mma_max_all<kSubChunks>(v) >= th)) {
+                        uint64_t* slab = p.cand_keys + (((size_t)(mt0 + mi) * kBM + lane_q) * p.n_sub + sub) * (size_t)cap;
+                        uint32_t cnt = s_cnt[slot];
+                        const uint32_t cnt_in = cnt;
+                        uint32_t row = base_row;
+#if defined(__CUDA_ARCH__)
+                        asm volatile("" : "+r"(row));  // keeps the 64 row numbers of the keys from being precomputed once per tile
+#endif
+#pragma unroll
+                        for (int c = 0; c < kSubChunks; ++c) mma_filter32(v[c], th, row + 32 * c, row_end32, slab, cnt, cap);
+                        if (cnt != cnt_in) s_cnt[slot] = cnt;
+                    }
                 }
-                if (cnt != cnt_in) s_cnt[slot] = cnt;
             }
         }
         for (int mi = 0; mi < m; ++mi) {

@@ -75,6 +75,9 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
             extract(mma, "void mma_apply_l2_bias(float (&v)[32], const float4* norms)"),
             extract(mma, "void mma_mask_tail(float (&v)[32], uint32_t base_row, uint32_t row_end32)"),
             extract(mma, "void mma_filter32(float (&v)[32], float th, uint32_t base_row"),
+            extract(mma, "float mma_max3(float a, float b, float c)"),
+            extract(mma, "float mma_max_reduce(float (&a)[N])"),
+            extract(mma, "float mma_max_all(float (&v)[kChunks][32])"),
             extract(mma, "void mma_filter32_k1(float (&v)[32], float& thr, float two_e"),
             extract(mma, "pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams p)")
             .replace("extern __shared__ __align__(1024) uint8_t smem[];", "uint8_t* smem = smem_raw;"),

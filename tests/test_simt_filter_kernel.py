@@ -69,8 +69,8 @@ def test_second_attempt_path_with_the_real_kernel(real):
 @pytest.mark.parametrize("old,new,expect", [
     ("mbar_init(&ctrl->tmem_empty[b], kEpiWarps);", "mbar_init(&ctrl->tmem_empty[b], kEpiWarps + 1);", b"deadlock"),
     ("if (lane == 0) mbar_arrive(&ctrl->tmem_empty[b]);", "", b"deadlock"),
-    ("const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kBN + set * kSubN);",
-     "const uint32_t taddr = tmem_base + ((uint32_t)(set * 32) << 16) + (uint32_t)(b * kBN + set * kSubN);", b"lane quarter"),
+    ("const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * kSubN);",
+     "const uint32_t taddr0 = tmem_base + ((uint32_t)(set * 32) << 16) + (uint32_t)(set * kSubN);", b"lane quarter"),
 ])
 def test_protocol_slips_are_caught_on_the_cpu(tmp_path, old, new, expect):
     """The same kernel with one line changed: a barrier initialised for one arrival too many, a missing arrival, a warp
