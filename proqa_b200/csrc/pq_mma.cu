@@ -628,11 +628,13 @@ __device__ __forceinline__ int sel_slabs_of_query(const EpochSelParams& p, int q
 // pool next to the old carry; when the pool exceeds K' an MSB-first radix select over the 64-bit keys (8-bit digits, bytes
 // common to all keys skipped) finds the K'-th largest key and the survivors are compacted — no sort of the pool.  Only the
 // K' survivors are sorted at the end (the threshold is read off the k-th entry).
+template <int kT = 256>
 __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* pool, int n, int want, int* hist, uint64_t* s_u64, int* s_int) {
+    constexpr int kW = kT / 32;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     // bytes on which all keys agree need no pass
     uint64_t a = ~0ull, o = 0ull;
-    for (int i = t; i < n; i += 256) {
+    for (int i = t; i < n; i += kT) {
         const uint64_t k = pool[i];
         a &= k;
         o |= k;
@@ -644,15 +646,15 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* pool, int
     }
     if (lane == 0) {
         s_u64[warp] = a;
-        s_u64[8 + warp] = o;
+        s_u64[kW + warp] = o;
     }
     __syncthreads();
     a = s_u64[0];
-    o = s_u64[8];
+    o = s_u64[kW];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < kW; ++w) {
         a &= s_u64[w];
-        o |= s_u64[8 + w];
+        o |= s_u64[kW + w];
     }
     const uint64_t differ = a ^ o;  // bit set = keys disagree there
     uint64_t prefix = a & ~differ, mask = ~differ;  // agreed bits are part of the prefix already
@@ -660,9 +662,9 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* pool, int
     for (int shift = 56; shift >= 0; shift -= 8) {
         if (((differ >> shift) & 0xffull) == 0) continue;  // block-uniform
         const uint64_t dmask = (differ >> shift) & 0xffull;  // only the disagreeing bits of this byte vary
-        hist[t] = 0;
+        if (t < 256) hist[t] = 0;
         __syncthreads();
-        for (int i = t; i < n; i += 256) {
+        for (int i = t; i < n; i += kT) {
             const uint64_t k = pool[i];
             if (((k ^ prefix) & mask) == 0) atomicAdd(&hist[(int)((k >> shift) & dmask)], 1);
         }

@@ -82,11 +82,13 @@ struct LargeKParams {
 // k-th largest 32-bit ordered score among the slab entries of one query, MSB-first radix select straight over the slabs
 // (one warp per slab, coalesced).  Bytes on which every score agrees are skipped; inside a warp, lanes with the same
 // digit are combined before the shared-memory atomic (the scores above a threshold share their leading bits).
+template <int kT>
 __device__ __forceinline__ uint32_t slab_radix_select_score(const uint64_t* keys, const int* s_cnt, int n_sub, int cap, int want, int* hist,
                                                             uint32_t* s_u32, int* s_int) {
+    constexpr int kW = kT / 32;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     uint32_t a = ~0u, o = 0u;
-    for (int s = warp; s < n_sub; s += 8) {
+    for (int s = warp; s < n_sub; s += kW) {
         const uint64_t* src = keys + (size_t)s * cap;
         const int n = s_cnt[s];
         for (int p0 = 0; p0 < n; p0 += 128) {  // four loads in flight per lane (the slabs are read from L2: one round trip each)
@@ -110,15 +112,15 @@ __device__ __forceinline__ uint32_t slab_radix_select_score(const uint64_t* keys
     }
     if (lane == 0) {
         s_u32[warp] = a;
-        s_u32[8 + warp] = o;
+        s_u32[kW + warp] = o;
     }
     __syncthreads();
     a = s_u32[0];
-    o = s_u32[8];
+    o = s_u32[kW];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < kW; ++w) {
         a &= s_u32[w];
-        o |= s_u32[8 + w];
+        o |= s_u32[kW + w];
     }
     const uint32_t differ = a ^ o;
     uint32_t prefix = a & ~differ, mask = ~differ;
@@ -126,9 +128,9 @@ __device__ __forceinline__ uint32_t slab_radix_select_score(const uint64_t* keys
     for (int shift = 24; shift >= 0; shift -= 8) {
         const uint32_t dmask = (differ >> shift) & 0xffu;
         if (dmask == 0) continue;  // block-uniform
-        hist[t] = 0;
+        if (t < 256) hist[t] = 0;
         __syncthreads();
-        for (int s = warp; s < n_sub; s += 8) {
+        for (int s = warp; s < n_sub; s += kW) {
             const uint64_t* src = keys + (size_t)s * cap;
             const int n = s_cnt[s];
             for (int q0 = 0; q0 < n; q0 += 128) {  // warp-uniform trip counts; four loads in flight per lane
@@ -188,15 +190,21 @@ __device__ __forceinline__ uint32_t slab_radix_select_score(const uint64_t* keys
     return prefix;
 }
 
-__global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKParams p) {
+// kLargeKFinT threads: the kernel is a chain of dependent global reads (slab passes, then the row gather of the rescoring) with
+// one CTA per SM because of its shared-memory pool — 8 warps left the SM waiting on memory 90 % of the time (ncu: issue slots
+// 10 % busy, 65 % of the stall samples long_scoreboard), 32 warps keep four times the loads in flight.
+constexpr int kLargeKFinT = 1024;
+template <int kT>
+__global__ void __launch_bounds__(kT) pq_largek_finalize_kernel(const LargeKParams p) {
+    constexpr int kW = kT / 32;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw);                       // max(pool, sort_n) keys
     int* s_cnt = reinterpret_cast<int*>(pool + max(p.pool, p.sort_n));            // n_sub
     __shared__ float s_q[kDim];
     __shared__ int hist[256];
-    __shared__ uint64_t s_u64[16];
+    __shared__ uint64_t s_u64[2 * kW];
     __shared__ int s_int[2];
-    __shared__ int s_wbase[8];
+    __shared__ int s_wbase[kW];
     __shared__ int s_total, s_ovf, s_slot, s_valid;
     const int q = blockIdx.x;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKPar
     __syncthreads();
     {
         int mine = 0;
-        for (int s = t; s < p.n_sub; s += 256) {
+        for (int s = t; s < p.n_sub; s += kT) {
             const uint32_t c = cnts[s];
             if (c > (uint32_t)p.cap) s_ovf = 1;
             s_cnt[s] = (int)min(c, (uint32_t)p.cap);
@@ -229,13 +237,13 @@ __global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKPar
     float bar = 0.f;
     if (!fail) {
         // ---- A_k and the certificate ----
-        const uint32_t kth = slab_radix_select_score(keys, s_cnt, p.n_sub, p.cap, p.k, hist, reinterpret_cast<uint32_t*>(s_u64), s_int);
+        const uint32_t kth = slab_radix_select_score<kT>(keys, s_cnt, p.n_sub, p.cap, p.k, hist, reinterpret_cast<uint32_t*>(s_u64), s_int);
         bar = ordered_to_f32(kth) - two_e;
         fail = !(p.thr[q] <= bar);
     }
     if (!fail) {
         // ---- survivors within 2E of A_k -> shared memory ----
-        for (int s = warp; s < p.n_sub; s += 8) {
+        for (int s = warp; s < p.n_sub; s += kW) {
             const uint64_t* src = keys + (size_t)s * p.cap;
             const int n = s_cnt[s];
             for (int q0 = 0; q0 < n; q0 += 128) {
@@ -264,34 +272,65 @@ __global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKPar
     int n_r = 0;
     if (!fail) {
         // ---- exact scores, in place ----
+        // The engine's defined score (pq_common.cuh: engine_dot / quad_engine_dot): lane = 8 r + j computes chain p_j (dims
+        // 16 j .. 16 j + 15 ascending) of row r of its group of four from its own 64 bytes of the row; three butterfly steps add
+        // the chains in engine_dot's tree.  A warp takes EIGHT rows per pass (two groups): eight independent 16-byte loads per
+        // lane, 4 KB per warp, in flight together; the lane's 16 query values stay in registers.
         n_r = s_slot;
         int valid = 0;
-        for (int i = t; i < n_r; i += 256) {
-            const uint32_t row = key_row(pool[i]);
-            // the engine's defined score (pq_common.cuh: engine_dot): 8 chains of 16 dims, tree-combined
-            const float4* r4 = reinterpret_cast<const float4*>(p.rows + (size_t)row * kDim);
-            float4 rv[32];   // the whole row in flight (one CTA per SM: registers are plentiful, loads in flight are what is short)
+        const int j = lane & 7, r = lane >> 3;
+        float4 qv[4];
 #pragma unroll
-            for (int l = 0; l < 32; ++l) rv[l] = ldg_f4_now(r4 + l);
-            float pj[8];
+        for (int i4 = 0; i4 < 4; ++i4) qv[i4] = reinterpret_cast<const float4*>(s_q + 16 * j)[i4];
+        for (int i0 = warp * 8; i0 < n_r; i0 += kW * 8) {
+            const int ia = i0 + r, ib = i0 + 4 + r;
+            const bool has_a = ia < n_r, has_b = ib < n_r;
+            const uint32_t row_a = has_a ? key_row(pool[ia]) : 0u, row_b = has_b ? key_row(pool[ib]) : 0u;
+            const float4* ra = reinterpret_cast<const float4*>(p.rows + (size_t)row_a * kDim + 16 * j);
+            const float4* rb = reinterpret_cast<const float4*>(p.rows + (size_t)row_b * kDim + 16 * j);
+            float4 va[4], vb[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float a = 0.f;
+            for (int i4 = 0; i4 < 4; ++i4) va[i4] = ldg_f4_now(ra + i4);   // (row 0 stands in for a missing row: read, not used)
 #pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 v = rv[4 * j + i4];
-                    a = fmaf(v.x, s_q[16 * j + 4 * i4 + 0], a);
-                    a = fmaf(v.y, s_q[16 * j + 4 * i4 + 1], a);
-                    a = fmaf(v.z, s_q[16 * j + 4 * i4 + 2], a);
-                    a = fmaf(v.w, s_q[16 * j + 4 * i4 + 3], a);
-                }
-                pj[j] = a;
+            for (int i4 = 0; i4 < 4; ++i4) vb[i4] = ldg_f4_now(rb + i4);
+            float na = 0.f, nb = 0.f;
+            if (p.metric == kMetricL2 && j == 0) {
+                na = __ldg(p.row_norms + row_a);
+                nb = __ldg(p.row_norms + row_b);
             }
-            float acc = ((pj[0] + pj[1]) + (pj[2] + pj[3])) + ((pj[4] + pj[5]) + (pj[6] + pj[7]));
-            if (p.metric == kMetricL2) acc = fmaf(2.f, acc, -__ldg(p.row_norms + row));
-            const bool ok = acc >= PQ_THR_FLOOR;
-            pool[i] = ok ? make_key(acc, row) : 0ull;
-            valid += ok ? 1 : 0;
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                a = fmaf(va[i4].x, qv[i4].x, a);
+                a = fmaf(va[i4].y, qv[i4].y, a);
+                a = fmaf(va[i4].z, qv[i4].z, a);
+                a = fmaf(va[i4].w, qv[i4].w, a);
+                b = fmaf(vb[i4].x, qv[i4].x, b);
+                b = fmaf(vb[i4].y, qv[i4].y, b);
+                b = fmaf(vb[i4].z, qv[i4].z, b);
+                b = fmaf(vb[i4].w, qv[i4].w, b);
+            }
+#pragma unroll
+            for (int sft = 1; sft <= 4; sft <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, sft);
+                b += __shfl_xor_sync(0xffffffffu, b, sft);
+            }
+            if (j == 0) {
+                if (p.metric == kMetricL2) {
+                    a = fmaf(2.f, a, -na);
+                    b = fmaf(2.f, b, -nb);
+                }
+                if (has_a) {
+                    const bool ok = a >= PQ_THR_FLOOR;
+                    pool[ia] = ok ? make_key(a, row_a) : 0ull;
+                    valid += ok ? 1 : 0;
+                }
+                if (has_b) {
+                    const bool ok = b >= PQ_THR_FLOOR;
+                    pool[ib] = ok ? make_key(b, row_b) : 0ull;
+                    valid += ok ? 1 : 0;
+                }
+            }
         }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, s);
@@ -308,10 +347,10 @@ __global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKPar
     }
     // ---- the k best exact keys to the front, in place ----
     if (n_r > p.k) {
-        const uint64_t pivot = block_radix_select(pool, n_r, p.k, hist, s_u64, s_int);  // k-th largest; the keys >= it are unique
+        const uint64_t pivot = block_radix_select<kT>(pool, n_r, p.k, hist, s_u64, s_int);  // k-th largest; the keys >= it are unique
         if (t == 0) s_slot = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < n_r; i0 += 256) {   // ordered compaction: a chunk is read by everyone before anyone writes at or below it
+        for (int i0 = 0; i0 < n_r; i0 += kT) {   // ordered compaction: a chunk is read by everyone before anyone writes at or below it
             const int i = i0 + t;
             const uint64_t key = i < n_r ? pool[i] : 0ull;
             const bool keep = i < n_r && key >= pivot;
@@ -324,16 +363,16 @@ __global__ void __launch_bounds__(256) pq_largek_finalize_kernel(const LargeKPar
             __syncthreads();
             if (t == 0) {
                 int tot = 0;
-                for (int w = 0; w < 8; ++w) tot += s_wbase[w];
+                for (int w = 0; w < kW; ++w) tot += s_wbase[w];
                 s_slot += tot;
             }
             __syncthreads();
         }
     }
-    for (int i = p.k + t; i < p.sort_n; i += 256) pool[i] = 0ull;
+    for (int i = p.k + t; i < p.sort_n; i += kT) pool[i] = 0ull;
     __syncthreads();
-    block_sort_desc<256>(pool, p.sort_n);
-    for (int i = t; i < p.k; i += 256) {
+    block_sort_desc<kT>(pool, p.sort_n);
+    for (int i = t; i < p.k; i += kT) {
         const uint64_t key = pool[i];
         const float s = key_score(key);
         p.D[(size_t)q * p.k + i] = (p.metric == kMetricL2) ? fmaxf(0.f, p.q_norms[q] - s) : s;
@@ -490,8 +529,8 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         fp.fail = (uint8_t*)w[7].p;
         fp.fail_count = st.counters + 2;
         const size_t fsmem = (size_t)std::max(lp.pool, lp.sort_n) * 8 + (size_t)fp.n_sub * 4;
-        PQ_CUDA(ensure_dyn_smem(pq_largek_finalize_kernel, fsmem, ix->device));
-        pq_largek_finalize_kernel<<<nq, 256, fsmem, ix->stream>>>(fp);
+        PQ_CUDA(ensure_dyn_smem(pq_largek_finalize_kernel<kLargeKFinT>, fsmem, ix->device));
+        pq_largek_finalize_kernel<kLargeKFinT><<<nq, kLargeKFinT, fsmem, ix->stream>>>(fp);
         PQ_CUDA(cudaGetLastError());
         ix->stats[4] += 1;
         ix->stats[5] += 1;

@@ -28,6 +28,7 @@ def _device_source():
         harness.extract(mma, "uint64_t block_radix_select(const uint64_t* pool"),
         harness.extract(inl, "struct LargeKParams {"),
         harness.extract(inl, "uint32_t slab_radix_select_score(const uint64_t* keys"),
+        harness.extract(inl, "constexpr int kLargeKFinT = ", upto="constexpr int kLargeKFinT = "),
         harness.extract(inl, "pq_largek_finalize_kernel(const LargeKParams p)"),
     ]))
 
@@ -52,7 +53,7 @@ extern "C" const char* emu_largek_finalize(const uint64_t* cand_keys, const uint
     p.row_norms = row_norms; p.q_norms = q_norms; p.q_bad = q_bad; p.n_sub = n_sub; p.cap = cap; p.k = k; p.pool = pool;
     p.sort_n = sort_n; p.metric = metric; p.id_base = id_base; p.D = D; p.I = I; p.fail = fail; p.fail_count = fail_count;
     if ((size_t)std::max(pool, sort_n) * 8 + (size_t)n_sub * 4 > sizeof(pq::smem_raw)) return "shared memory request exceeds an SM";
-    return simt::launch((unsigned)nq, 256, [&] { pq::pq_largek_finalize_kernel(p); });
+    return simt::launch((unsigned)nq, pq::kLargeKFinT, [&] { pq::pq_largek_finalize_kernel<pq::kLargeKFinT>(p); });
 }
 '''
 
