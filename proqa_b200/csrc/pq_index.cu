@@ -576,6 +576,10 @@ int pq_index_create(int d, int metric, int device, pq_index** out) {
     }
     const char* ks = getenv("PROQA_B200_K1_SETS");
     if (ks && (atoi(ks) == 2 || atoi(ks) == 4)) plan_k1_sets() = atoi(ks);
+    const char* gr = getenv("PROQA_B200_GROWTH");
+    if (gr && atoll(gr) > 1) plan_growth_override() = atoll(gr);
+    const char* br = getenv("PROQA_B200_BOOT_ROWS");
+    if (br && atoll(br) >= 1024) plan_boot_rows_override() = atoll(br) / 128 * 128;
     const char* lk = getenv("PROQA_B200_LARGEK");
     ix->largek = !(lk && !strcmp(lk, "0"));  // tensor tier for 1024 < k unless switched off
     *out = ix;  // CUDA is touched lazily (first add/search): the reference forks after importing faiss

@@ -86,6 +86,10 @@ struct MmaParams {
     // queries whose slabs overflowed in that epoch (redo[q] & redo_bit) take part, with their final thresholds
     const uint32_t* redo;      // [nq_pad] or null
     uint32_t redo_bit;
+    // pacing of the TMA producers (pace_* below): null, or one zeroed arrival counter per block of 2^pace_shift row tiles
+    uint32_t* pace;
+    int pace_shift;
+    int pace_blocks;
 };
 
 // D[tmem] (+)= A[tmem] * B[smem desc]^T: the stationary operand (queries) is read from tensor memory, so shared
@@ -239,6 +243,27 @@ __device__ __forceinline__ void mma_filter32_k1(float (&v)[32], float& thr, floa
     }
 }
 
+// Pacing of the TMA producers.  Every CTA group streams the whole epoch's rows (each group owns other queries); the groups
+// advance at the same rate by construction, and as long as all of them are within an L2's worth of rows of each other a tile
+// comes from DRAM once and from L2 for the other groups.  Left alone the CTAs drift apart (a 0.5 % difference in speed over
+// an 11 ms launch is 25 MB of rows): ncu showed 14.1 GB of DRAM reads for the 4.3 GB of rows of the last C2 epoch.  So the row
+// tiles of the epoch are cut into blocks of 2^pace_shift tiles; a producer counts itself out of every block it has left, and
+// does not start block b before every CTA of the grid has left block b - kPaceWindow.  Rate control only — no data depends on
+// it — and bounded: a producer that waits longer than ~1 ms (some CTA is not running: the grid is not co-resident) stops pacing
+// for the rest of the launch.  The host enables it only for grids of at most one CTA per SM.
+constexpr int kPaceWindow = 3;
+constexpr int kPaceMaxPolls = 4096;
+__device__ __forceinline__ void pace_leave(uint32_t* pace, int from, int to) {
+    for (int b = from; b < to; ++b) atomicAdd(pace + b, 1u);
+}
+__device__ __forceinline__ bool pace_wait(const uint32_t* cnt, uint32_t n_ctas) {
+    for (int i = 0; i < kPaceMaxPolls; ++i) {
+        if (*reinterpret_cast<const volatile uint32_t*>(cnt) >= n_ctas) return true;
+        __nanosleep(256);
+    }
+    return false;
+}
+
 // Accumulator schedule shared by the MMA issuer and the epilogue.  For row tile t and query tile mi (< m) one accumulator
 // of 128 columns is produced, sequence number j = t*m + mi, in TMEM buffer j & 1 (use number j >> 1).  The epilogue
 // warps form kEpiSets sets of four (one warp per TMEM lane quarter); set h drains columns h*kSubN .. (h+1)*kSubN-1 (those rows
@@ -339,9 +364,22 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        int pace_blk = 0;              // block of row tiles this producer is in (pacing, see pace_leave / pace_wait)
+        bool pacing = p.pace != nullptr;
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % kStages;
             const uint32_t ph = (uint32_t)(t / kStages) & 1u;
+            if (p.pace != nullptr) {
+                const int blk = (int)(((long long)slice + (long long)t * n_slices) >> p.pace_shift);
+                if (blk != pace_blk) {  // warp-uniform
+                    if (lane == 0) {
+                        pace_leave(p.pace, pace_blk, blk);
+                        if (pacing && blk >= kPaceWindow) pacing = pace_wait(p.pace + (blk - kPaceWindow), gridDim.x);
+                    }
+                    pace_blk = blk;
+                    __syncwarp();
+                }
+            }
             mbar_wait(&ctrl->empty[s], ph ^ 1u);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&ctrl->full[s], kTileBytes + (kL2 ? kBN * 4 : 0));
@@ -353,6 +391,7 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
             }
             __syncwarp();
         }
+        if (p.pace != nullptr && lane == 0) pace_leave(p.pace, pace_blk, p.pace_blocks);  // (a CTA without tiles leaves them all)
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
         constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN);
@@ -1560,6 +1599,46 @@ static ShareParams make_share_params(const pq_index* ix, int nq, int k, int batc
     return sh;
 }
 
+// Producer pacing of a filter launch (pq_mma_filter_kernel: pace_leave / pace_wait): on when several CTA groups stream rows
+// that do not fit L2 together and the whole grid is resident at once (one CTA per SM) — the only case in which waiting for the
+// other CTAs is safe and pays.  Returns the number of arrival counters the launch needs (0: unpaced).
+// PROQA_B200_PACE=0 switches pacing off; PROQA_B200_PACE_MIN_TILES / _SHIFT are test hooks.
+static int pace_shift() {
+    static const int shift = [] { const char* e = getenv("PROQA_B200_PACE_SHIFT"); return e ? atoi(e) : 8; }();
+    return shift;
+}
+static long long pace_blocks_for(const pq_index* ix, const GridShape& gs, int n_ctas, long long row_begin, long long row_end) {
+    static const int enabled = [] { const char* e = getenv("PROQA_B200_PACE"); return e ? atoi(e) : 1; }();
+    static const long long min_tiles = [] { const char* e = getenv("PROQA_B200_PACE_MIN_TILES"); return e ? atoll(e) : 2048LL; }();
+    const long long tiles = (row_end - row_begin + kBN - 1) / kBN;
+    if (!enabled || gs.n_groups < 2 || n_ctas > ix->n_sms || tiles < min_tiles) return 0;
+    return ((tiles - 1) >> pace_shift()) + 1;
+}
+// One zeroed counter area for all paced launches of a search (a single memset node), handed out launch by launch.
+struct PaceArea {
+    uint32_t* base = nullptr;
+    long long used = 0, total = 0;
+    int reserve(pq_index* ix, long long counters) {
+        used = 0;
+        total = counters;
+        base = nullptr;
+        if (counters == 0) return PQ_OK;
+        if (const int rc = ix->ws_mma[9].ensure((size_t)counters * 4)) return rc;
+        base = (uint32_t*)ix->ws_mma[9].p;
+        PQ_CUDA(cudaMemsetAsync(base, 0, (size_t)counters * 4, ix->stream));
+        return PQ_OK;
+    }
+    void assign(MmaParams& mp, long long blocks) {
+        mp.pace = nullptr;
+        mp.pace_shift = pace_shift();
+        mp.pace_blocks = 0;
+        if (blocks == 0 || base == nullptr || used + blocks > total) return;
+        mp.pace = base + used;
+        mp.pace_blocks = (int)blocks;
+        used += blocks;
+    }
+};
+
 int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, float* dD_all, long long* dI_all,
                       std::vector<int>* rerun) {
     const long long N = ix->ntotal;
@@ -1612,6 +1691,13 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
 
         if (!k1) PQ_CUDA(cudaMemsetAsync(st.carry, 0, (size_t)nq_pad * kp * 8, ix->stream));
         PQ_CUDA(cudaMemsetAsync(st.counters, 0, 16, ix->stream));
+        PaceArea pace;
+        {
+            long long counters = 0;
+            if (!k1)
+                for (const EpochPlan& ep : plan) counters += pace_blocks_for(ix, gs, plan_n_ctas(gs, ep), ep.begin, ep.end);
+            if (const int prc = pace.reserve(ix, counters)) return prc;
+        }
         pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, (const float*)ix->ws_qresid.p + qb, dq_bad, nq, nq_pad, kp,
                                                                              ix->max_norm2, ix->max_resid2, ix->metric);
         PQ_CUDA(cudaGetLastError());
@@ -1647,6 +1733,9 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.cap = ep.cap;
             mp.n_sub = plan_n_sub(gs, ep);
             mp.sets = ep.sets;
+            mp.pace = nullptr;   // (set per launch by pace_setup; the repair launches run unpaced)
+            mp.pace_shift = 0;
+            mp.pace_blocks = 0;
             sp.n_sub = mp.n_sub;
             sp.cap = ep.cap;
             sp.s1 = ep.s1;
@@ -1665,6 +1754,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.redo_bit = 0u;
             const int n_ctas = plan_n_ctas(gs, ep);
             if (k1) PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));  // (its finalize reads every slab)
+            pace.assign(mp, pace_blocks_for(ix, gs, n_ctas, ep.begin, ep.end));
             ix->prof_begin();
             const cudaError_t fe = launch_filter_any(gs.m_max, l2, k1, ix->tmap_bf16, mp, n_ctas, ix->device, ix->stream);
             ix->prof_end();

@@ -32,6 +32,16 @@ inline int& plan_k1_sets() {
     return v;
 }
 
+// (tuning hooks, PROQA_B200_GROWTH / PROQA_B200_BOOT_ROWS: epoch growth factor and rows of the bootstrap epoch; 0 = the defaults)
+inline long long& plan_growth_override() {
+    static long long v = 0;
+    return v;
+}
+inline long long& plan_boot_rows_override() {
+    static long long v = 0;
+    return v;
+}
+
 struct EpochPlan {
     long long begin, end;
     int s1, s0, cap;   // row slices per CTA group (groups owning base+1 / base query tiles), slab capacity
@@ -123,8 +133,8 @@ inline std::vector<EpochPlan> plan_epochs(long long N, int k, int nq_pad, const 
     // epochs would cover a larger part of the shard (8 shards of C3 with growth 32: 37 % of a shard's rows ran with 40 % of the
     // 32x32 chunks taking the append path — 51 ms against 36 ms for the same products with queries split instead).
     const int share_f = share_n >= 4 ? 4 : (share_n >= 2 ? 2 : 1);
-    const long long growth = nq_pad <= 128 ? 64LL : (nq_pad <= 512 ? 16LL : 8LL);
-    const long long n0 = std::min<long long>(N, std::max(1024, plan_next_pow2(2 * kp)));
+    const long long growth = plan_growth_override() > 1 ? plan_growth_override() : (nq_pad <= 128 ? 64LL : (nq_pad <= 512 ? 16LL : 8LL));
+    const long long n0 = std::min<long long>(N, std::max<long long>(std::max(1024, plan_next_pow2(2 * kp)), plan_boot_rows_override()));
     long long begin = 0, end = n0;
     while (begin < N) {
         EpochPlan ep;

@@ -79,6 +79,8 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
             extract(mma, "float mma_max_reduce(float (&a)[N])"),
             extract(mma, "float mma_max_all(float (&v)[kChunks][32])"),
             extract(mma, "void mma_filter32_k1(float (&v)[32], float& thr, float two_e"),
+            extract(mma, "constexpr int kPaceWindow = 3;", upto="constexpr int kPaceMaxPolls = 4096;"),
+            extract(mma, "void pace_leave(uint32_t* pace, int from, int to)"),
             extract(mma, "pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams p)")
             .replace("extern __shared__ __align__(1024) uint8_t smem[];", "uint8_t* smem = smem_raw;"),
             extract(mma, "static cudaError_t launch_filter(const CUtensorMap& tc"),
@@ -128,6 +130,9 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
             + extract(mma, "static cudaError_t launch_epoch_select(const EpochSelParams& sp")
             + extract(mma, "static cudaError_t launch_rescore(const RescoreParams& rp")
             + extract(mma, "static ShareParams make_share_params(const pq_index* ix")
+            + extract(mma, "static int pace_shift() {")
+            + extract(mma, "static long long pace_blocks_for(const pq_index* ix")
+            + extract(mma, "struct PaceArea {")
             + extract(mma, "int search_mma_filter(pq_index* ix"))
     tmpl = open(os.path.join(SIMT, "mma_host_emu.cpp.in")).read()
     text = (tmpl.replace("@EXTRACTED_DEVICE@", to_host(device)).replace("@FILTER_IMPL@", filter_impl)

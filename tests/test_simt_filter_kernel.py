@@ -86,3 +86,27 @@ def test_protocol_slips_are_caught_on_the_cpu(tmp_path, old, new, expect):
     Dr, Ir = oracle.engine_spec(xq, xb, 10, 0)
     ok = [q for q in range(7) if q not in rerun]
     assert len(ok) < 7 or not np.array_equal(I, Ir), "a protocol slip went unnoticed"
+
+
+def test_producer_pacing_counts_every_cta_out_of_every_block(tmp_path, monkeypatch):
+    """Pacing of the TMA producers (pq_mma.cu: pace_setup / pace_leave / pace_wait), forced on for a small epoch: blocks of two
+    row tiles.  Results are unchanged (pacing is rate control only), and after the last paced launch every CTA of its grid has
+    counted itself out of every block exactly once — a producer that missed one would leave the others waiting on the
+    hardware."""
+    monkeypatch.setenv("PROQA_B200_PACE_MIN_TILES", "1")
+    monkeypatch.setenv("PROQA_B200_PACE_SHIFT", "1")
+    lib = harness.build_host_emu(tmp_path, real_filter=True)
+    n_sms, nb, nq, k = 5, 3_000, 700, 3            # 6 query tiles -> two CTA groups; 24 row tiles
+    xb, xq = data.corpus(nb), data.queries(nq)
+    D, I, rerun, st = harness.run_host_emu(lib, xb, xq, k, 1, n_sms)
+    assert rerun == []
+    _exact(D, I, xq, xb, k, 1, rows=list(range(8)) + [nq - 1])
+    import ctypes
+    buf = (ctypes.c_uint32 * 64)()
+    n = lib.emu_last_pace(buf, 64)
+    assert n >= 1, "no paced launch"
+    counts = list(buf)[:min(n, 64)]
+    # one counter per block of two row tiles of every paced epoch (the bootstrap epoch runs one CTA per row tile and group —
+    # more CTAs than SMs here — and stays unpaced; the second epoch has 16 row tiles: 8 blocks), each left exactly once by every
+    # CTA of the epoch's grid
+    assert n == 8 and len(set(counts)) == 1 and 2 <= counts[0] <= n_sms, counts
