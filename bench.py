@@ -357,6 +357,19 @@ def sweep_lines(args, ix, dev, stream, N, local_rank):
                              "step_frac_of_hbm": hbm_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                              "step_frac_of_hbm_note": "bytes the tier must stream once (fp32 rows: scan; bf16 copy: tensor tier) / whole-step time / measured copy bandwidth",
                              "parity_ok": ok}
+        if nq <= 4:
+            # AUTO answers these from the bf16 copy on a corpus this large; the exact fp32 scan (north_star (2): the HBM-bound FFMA tier,
+            # what smaller corpora and certificate failures get) is timed beside it
+            ix.set_tier("fp32")
+            ms = timed(stream, run, 10, 3)
+            Dt, It, own = truth_topk_fp64(q, 0, N, N, k, dev, ids=I)
+            ok, _ = parity_gate(D, I, Dt, It, own)
+            rf = device_roofline(ix, run, 2.0 * nq * N * 128, 512.0 * N, 0.0)
+            ix.set_tier("auto")
+            out[f"s0_nq{nq}_fp32_scan"] = {"nq": nq, "rows": N, "k": k, "ms": ms, "queries_per_s": nq / ms * 1e3,
+                                           "corpus_gbs_fp32_equiv": N * 512 / ms / 1e6, "tier": rf["bound"],
+                                           "kernel_frac_of_its_roofline": rf["frac"],
+                                           "step_frac_of_hbm": N * 512.0 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "parity_ok": ok}
     # C1: eval_retrieval.py shape, its own 1M-row index
     wl = WORKLOADS["c1"]
     c1 = pq.IndexFlatIP(128, local_rank)

@@ -37,7 +37,7 @@ enum pq_status {
 };
 
 /* Search tiers (pq_index_set_tier / env PROQA_B200_TIER):
- *   AUTO : fp32 scan for small batches / small corpora, tensor-core filter otherwise.
+ *   AUTO : fp32 scan for small corpora (and for fewer than 5 queries below 2^23 rows), tensor-core filter otherwise.
  *   FP32 : always the exact fp32 streaming scan (coalesced FFMA path).
  *   BF16 : always the tcgen05 bf16 filter + exact fp32 rescoring with an exactness certificate;
  *          queries whose certificate fails are re-run through the fp32 scan.

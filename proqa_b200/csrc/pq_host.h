@@ -1,5 +1,6 @@
 // proqa_b200 — host-side state shared by pq_index.cu (C ABI, fp32 tier) and pq_mma.cu (tensor-core tier).
 #pragma once
+#include <stdlib.h>
 
 #include <stdint.h>
 
@@ -31,7 +32,19 @@ int make_row_tensor_map(CUtensorMap* out, const void* base, long long rows, int 
 
 // Tensor-core tier limits
 constexpr int kMmaMaxK = 1024;          // carry list K' <= 4096 entries
-constexpr int kMmaMinQueries = 5;       // nq <= 4: the fp32 scan streams the corpus at the HBM roofline (measured 1.0 of peak)
+constexpr int kMmaMinQueries = 5;       // nq <= 4 on a small corpus: the fp32 scan streams it at the HBM roofline (measured 1.0 of peak) with no fixed cost ...
+// ... but the tensor tier streams the bf16 copy, half the bytes, for ~0.3 ms of fixed epoch costs: from about 7M rows on it wins even
+// for one query (measured at 21M rows, k = 80 / 1000 / 5000: nq = 1 1.66 / 3.45 / 4.26 ms on the scan, 1.10 / 2.15 / 2.01 ms on the
+// tensor tier; nq = 4, k = 5000: 17.0 vs 2.05 ms — tools/gpu_runs/r02_zc_smallnq.sh)
+constexpr long long kMmaSmallBatchMinRows = 1LL << 23;
+// (the value in force: PROQA_B200_MMA_MIN_QUERIES overrides it, read once)
+inline int mma_min_queries() {
+    static const int v = [] {
+        const char* e = getenv("PROQA_B200_MMA_MIN_QUERIES");
+        return (e && atoi(e) >= 1) ? atoi(e) : kMmaMinQueries;
+    }();
+    return v;
+}
 constexpr int kMmaMinRows = 16384;      // below this the epoch machinery is pure overhead ...
 constexpr long long kMmaMinPairs = 1LL << 24;  // ... unless the query side is large (k-means assignment: 10k centroids x millions of points)
 

@@ -462,7 +462,7 @@ __global__ void pq_scatter_results_kernel(const float* __restrict__ Ds, const lo
 // sample to mean something; PROQA_B200_LARGEK=0 sends such requests to the fp32 scan instead.
 static bool tier_uses_largek(const pq_index* ix, int64_t nq, int64_t k) {
     if (!ix->largek || ix->has_nonfinite || ix->tier == PQ_TIER_FP32) return false;
-    if (k > kMmaMaxK) return k <= PQ_MAX_K && nq >= kMmaMinQueries && plan_large_k_applies(ix->ntotal, (int)k);
+    if (k > kMmaMaxK) return k <= PQ_MAX_K && (nq >= mma_min_queries() || ix->ntotal >= kMmaSmallBatchMinRows) && plan_large_k_applies(ix->ntotal, (int)k);
     // 512 <= k <= 1024 with a real batch (C5: 8192 queries, k = 1000): sample thresholds + one pass beat the epochs
     return k >= kPlanMidK && nq >= 256 && ix->ntotal >= (1 << 20) && plan_large_k_applies(ix->ntotal, (int)k);
 }
@@ -473,7 +473,8 @@ static bool tier_uses_mma(const pq_index* ix, int64_t nq, int64_t k) {
     if (ix->tier == PQ_TIER_FP32) return false;
     if (ix->tier == PQ_TIER_BF16) return ix->ntotal >= 1;
     // enough (query,row) pairs to pay for the epoch machinery: a big corpus, or the k-means shape (few centroids, millions of points)
-    return nq >= kMmaMinQueries && (ix->ntotal >= kMmaMinRows || nq * ix->ntotal >= kMmaMinPairs);
+    if (nq < mma_min_queries()) return ix->ntotal >= kMmaSmallBatchMinRows;
+    return ix->ntotal >= kMmaMinRows || nq * ix->ntotal >= kMmaMinPairs;
 }
 
 // Device-resident search: dq [nq,128] fp32 -> dD [nq,k], dI [nq,k]; all on ix->stream; leaves the stream drained.

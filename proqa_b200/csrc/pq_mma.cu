@@ -825,13 +825,30 @@ __global__ void __launch_bounds__(256) pq_epoch_select_kernel(const EpochSelPara
     int nc = s_nc;
     for (int c0 = 0; c0 < total;) {  // almost always a single chunk
         const int chunk = min(total - c0, p.lmax - nc);
-        for (int s = warp; s < n_sub; s += 8) {
-            const int base = s_off[s] - c0, n = s_cnt[s];
-            if (base + n <= 0 || base >= chunk) continue;
-            const uint64_t* src = keys + (size_t)s * p.cap;
-            for (int pos = lane; pos < n; pos += 32) {
-                const int f = base + pos;
-                if (f >= 0 && f < chunk) pool[nc + f] = src[pos];
+        // Gather by flat candidate index: thread -> (slab, position) through a binary search over the offsets in shared memory, so
+        // every global load is independent of the others and four are in flight per thread.  (A warp per slab walked its 74 slabs
+        // of ~13 keys one L2 round trip after the other: 80-95 us per select at nq = 16, a fifth of the whole search.)
+        for (int f0 = t; f0 < chunk; f0 += 4 * 256) {
+            uint64_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int f = f0 + u * 256;
+                v[u] = 0ull;
+                if (f < chunk) {
+                    const int g = c0 + f;
+                    int lo = 0, hi = n_sub - 1;  // last slab whose offset is <= g: it holds candidate g (empty slabs share an offset
+                    while (lo < hi) {            // with their successor and are never the last)
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (s_off[mid] <= g) lo = mid;
+                        else hi = mid - 1;
+                    }
+                    v[u] = keys[(size_t)lo * p.cap + (size_t)(g - s_off[lo])];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int f = f0 + u * 256;
+                if (f < chunk) pool[nc + f] = v[u];
             }
         }
         __syncthreads();

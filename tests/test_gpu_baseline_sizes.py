@@ -60,3 +60,16 @@ def test_c2_nq_scale_shape_device_generated():
     ok, info = bench.parity_gate(torch.from_numpy(D[:nchk]).to(dev), torch.from_numpy(I[:nchk]).to(dev), Dt, It, own)
     assert ok, info
     assert info["ids_equal_frac"] > 0.999 and info["max_near_tie_gap_rel"] < 1e-4
+    # Small batches on the same 21M-row index (S0; online_sampler.py:113 asks one question at a time, k = 5000): from 2^23 rows on
+    # AUTO sends them to the tensor tier too (half the bytes of the fp32 scan), and the two tiers return the same bits.
+    for nq_s, k_s in ((1, 80), (4, 80), (1, 5000), (3, 1000)):
+        ix.set_tier("auto")
+        Da, Ia = ix.search(xq[:nq_s], k_s)
+        st = ix.last_stats
+        assert st[3] > 0 and st[1] == 0, f"nq={nq_s} k={k_s}: expected the tensor tier without re-runs, stats {st}"
+        ix.set_tier("fp32")
+        Df, If = ix.search(xq[:nq_s], k_s)
+        assert ix.last_stats[3] == 0
+        np.testing.assert_array_equal(Ia, If)
+        np.testing.assert_array_equal(Da.view(np.uint32), Df.view(np.uint32))
+    np.testing.assert_array_equal(Ia[:, :100], I[:3])               # (and a prefix of the big batch's answer)
