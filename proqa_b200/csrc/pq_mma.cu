@@ -87,9 +87,10 @@ struct MmaParams {
     const uint32_t* redo;      // [nq_pad] or null
     uint32_t redo_bit;
     // pacing of the TMA producers (pace_* below): null, or one zeroed arrival counter per block of 2^pace_shift row tiles
-    uint32_t* pace;
+    uint32_t* pace;          // [cohorts][pace_blocks]
     int pace_shift;
     int pace_blocks;
+    int pace_cohort;         // CTAs per cohort: blockIdx / pace_cohort = the wave a CTA runs in (a single-wave grid is one cohort)
 };
 
 // D[tmem] (+)= A[tmem] * B[smem desc]^T: the stationary operand (queries) is read from tensor memory, so shared
@@ -366,6 +367,13 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
         // ===================== TMA producer =====================
         int pace_blk = 0;              // block of row tiles this producer is in (pacing, see pace_leave / pace_wait)
         bool pacing = p.pace != nullptr;
+        uint32_t* pace = nullptr;      // this CTA's cohort: the CTAs of its wave, which start together and advance together
+        uint32_t pace_n = 0;
+        if (p.pace != nullptr) {
+            const int cohort = (int)blockIdx.x / p.pace_cohort;
+            pace = p.pace + (size_t)cohort * p.pace_blocks;
+            pace_n = (uint32_t)min(p.pace_cohort, (int)gridDim.x - cohort * p.pace_cohort);
+        }
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % kStages;
             const uint32_t ph = (uint32_t)(t / kStages) & 1u;
@@ -373,8 +381,8 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
                 const int blk = (int)(((long long)slice + (long long)t * n_slices) >> p.pace_shift);
                 if (blk != pace_blk) {  // warp-uniform
                     if (lane == 0) {
-                        pace_leave(p.pace, pace_blk, blk);
-                        if (pacing && blk >= kPaceWindow) pacing = pace_wait(p.pace + (blk - kPaceWindow), gridDim.x);
+                        pace_leave(pace, pace_blk, blk);
+                        if (pacing && blk >= kPaceWindow) pacing = pace_wait(pace + (blk - kPaceWindow), pace_n);
                     }
                     pace_blk = blk;
                     __syncwarp();
@@ -391,7 +399,7 @@ pq_mma_filter_kernel(const __grid_constant__ CUtensorMap tmap_c, const MmaParams
             }
             __syncwarp();
         }
-        if (p.pace != nullptr && lane == 0) pace_leave(p.pace, pace_blk, p.pace_blocks);  // (a CTA without tiles leaves them all)
+        if (p.pace != nullptr && lane == 0) pace_leave(pace, pace_blk, p.pace_blocks);  // (a CTA without tiles leaves them all)
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
         constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN);
@@ -1617,18 +1625,22 @@ static ShareParams make_share_params(const pq_index* ix, int nq, int k, int batc
 }
 
 // Producer pacing of a filter launch (pq_mma_filter_kernel: pace_leave / pace_wait): on when several CTA groups stream rows
-// that do not fit L2 together and the whole grid is resident at once (one CTA per SM) — the only case in which waiting for the
-// other CTAs is safe and pays.  Returns the number of arrival counters the launch needs (0: unpaced).
-// PROQA_B200_PACE=0 switches pacing off; PROQA_B200_PACE_MIN_TILES / _SHIFT are test hooks.
+// that do not fit L2 together.  A grid of at most one CTA per SM is resident at once and paces as one cohort.  A larger grid
+// (65,536 queries: 1024 CTAs, seven waves) paces wave by wave — cohort c = CTAs [c n_sms, (c+1) n_sms): they start together as
+// the previous, paced, wave ends together; a CTA whose cohort is not all there within the bounded wait simply runs unpaced.
+// Returns the arrival counters one cohort needs (0: unpaced).  PROQA_B200_PACE = 0 off, 1 single-wave grids only, 2 (default)
+// every grid; PROQA_B200_PACE_MIN_TILES / _SHIFT are test hooks.
 static int pace_shift() {
     static const int shift = [] { const char* e = getenv("PROQA_B200_PACE_SHIFT"); return e ? atoi(e) : 8; }();
     return shift;
 }
+static int pace_cohorts(const pq_index* ix, int n_ctas) { return (n_ctas + ix->n_sms - 1) / ix->n_sms; }
 static long long pace_blocks_for(const pq_index* ix, const GridShape& gs, int n_ctas, long long row_begin, long long row_end) {
-    static const int enabled = [] { const char* e = getenv("PROQA_B200_PACE"); return e ? atoi(e) : 1; }();
+    static const int mode = [] { const char* e = getenv("PROQA_B200_PACE"); return e ? atoi(e) : 2; }();
     static const long long min_tiles = [] { const char* e = getenv("PROQA_B200_PACE_MIN_TILES"); return e ? atoll(e) : 2048LL; }();
     const long long tiles = (row_end - row_begin + kBN - 1) / kBN;
-    if (!enabled || gs.n_groups < 2 || n_ctas > ix->n_sms || tiles < min_tiles) return 0;
+    if (mode <= 0 || gs.n_groups < 2 || tiles < min_tiles) return 0;
+    if (n_ctas > ix->n_sms && (mode < 2 || pace_cohorts(ix, n_ctas) > 64)) return 0;
     return ((tiles - 1) >> pace_shift()) + 1;
 }
 // One zeroed counter area for all paced launches of a search (a single memset node), handed out launch by launch.
@@ -1645,14 +1657,17 @@ struct PaceArea {
         PQ_CUDA(cudaMemsetAsync(base, 0, (size_t)counters * 4, ix->stream));
         return PQ_OK;
     }
-    void assign(MmaParams& mp, long long blocks) {
+    void assign(const pq_index* ix, MmaParams& mp, long long blocks, int n_ctas) {
+        const long long need = blocks * pace_cohorts(ix, n_ctas);
         mp.pace = nullptr;
         mp.pace_shift = pace_shift();
         mp.pace_blocks = 0;
-        if (blocks == 0 || base == nullptr || used + blocks > total) return;
+        mp.pace_cohort = 1;
+        if (blocks == 0 || base == nullptr || used + need > total) return;
         mp.pace = base + used;
         mp.pace_blocks = (int)blocks;
-        used += blocks;
+        mp.pace_cohort = n_ctas <= ix->n_sms ? n_ctas : ix->n_sms;
+        used += need;
     }
 };
 
@@ -1712,7 +1727,8 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         {
             long long counters = 0;
             if (!k1)
-                for (const EpochPlan& ep : plan) counters += pace_blocks_for(ix, gs, plan_n_ctas(gs, ep), ep.begin, ep.end);
+                for (const EpochPlan& ep : plan)
+                    counters += pace_blocks_for(ix, gs, plan_n_ctas(gs, ep), ep.begin, ep.end) * pace_cohorts(ix, plan_n_ctas(gs, ep));
             if (const int prc = pace.reserve(ix, counters)) return prc;
         }
         pq_mma_init_state_kernel<<<(nq_pad + 255) / 256, 256, 0, ix->stream>>>(st, dq_norm, (const float*)ix->ws_qresid.p + qb, dq_bad, nq, nq_pad, kp,
@@ -1753,6 +1769,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.pace = nullptr;   // (set per launch by pace_setup; the repair launches run unpaced)
             mp.pace_shift = 0;
             mp.pace_blocks = 0;
+            mp.pace_cohort = 1;
             sp.n_sub = mp.n_sub;
             sp.cap = ep.cap;
             sp.s1 = ep.s1;
@@ -1771,7 +1788,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.redo_bit = 0u;
             const int n_ctas = plan_n_ctas(gs, ep);
             if (k1) PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));  // (its finalize reads every slab)
-            pace.assign(mp, pace_blocks_for(ix, gs, n_ctas, ep.begin, ep.end));
+            pace.assign(ix, mp, pace_blocks_for(ix, gs, n_ctas, ep.begin, ep.end), n_ctas);
             ix->prof_begin();
             const cudaError_t fe = launch_filter_any(gs.m_max, l2, k1, ix->tmap_bf16, mp, n_ctas, ix->device, ix->stream);
             ix->prof_end();

@@ -453,6 +453,7 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         mp.pace = nullptr;   // (the sample epochs are small; the full pass below sets it up)
         mp.pace_shift = 0;
         mp.pace_blocks = 0;
+        mp.pace_cohort = 1;
 
         // ---- A. thresholds from the sample ----------------------------------------------------
         for (const EpochPlan& ep : plan_s) {
@@ -503,8 +504,9 @@ int search_mma_largek(pq_index* ix, int nq_total, const float* dq_all, int k, fl
         mp.sets = pass.sets;
         PQ_CUDA(cudaMemsetAsync(mp.cand_cnt, 0, (size_t)nq_pad * mp.n_sub * 4, ix->stream));
         PaceArea pace;
-        if (const int prc = pace.reserve(ix, pace_blocks_for(ix, gs, plan_n_ctas(gs, pass), 0, N))) return prc;
-        pace.assign(mp, pace.total);
+        const long long pace_blocks = pace_blocks_for(ix, gs, plan_n_ctas(gs, pass), 0, N);
+        if (const int prc = pace.reserve(ix, pace_blocks * pace_cohorts(ix, plan_n_ctas(gs, pass)))) return prc;
+        pace.assign(ix, mp, pace_blocks, plan_n_ctas(gs, pass));
         ix->prof_begin();
         const cudaError_t e = launch_filter_any(gs.m_max, l2, false, ix->tmap_bf16, mp, plan_n_ctas(gs, pass), ix->device, ix->stream);
         ix->prof_end();

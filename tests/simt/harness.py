@@ -131,6 +131,7 @@ def build_host_emu(workdir, real_filter=False, mutate=None):
             + extract(mma, "static cudaError_t launch_rescore(const RescoreParams& rp")
             + extract(mma, "static ShareParams make_share_params(const pq_index* ix")
             + extract(mma, "static int pace_shift() {")
+            + extract(mma, "static int pace_cohorts(const pq_index* ix, int n_ctas)", upto="static int pace_cohorts(const pq_index* ix, int n_ctas)")
             + extract(mma, "static long long pace_blocks_for(const pq_index* ix")
             + extract(mma, "struct PaceArea {")
             + extract(mma, "int search_mma_filter(pq_index* ix"))

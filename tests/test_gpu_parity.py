@@ -320,3 +320,17 @@ def test_add_npy_streams_float32_and_float16_files(tmp_path):
         ix = _index(0, np.zeros((0, 128), np.float32), "auto")
         assert ix.add_npy(str(tmp_path / name), chunk_rows=1500) == 5000 and ix.ntotal == 5000
         _assert_bit_exact(*ix.search(xq, 10), *ref)
+
+
+def test_many_waves_of_ctas_paced_wave_by_wave():
+    """20,000 queries = 40 CTA groups; the last epoch (rows 64k..400k, 2613 row tiles) runs 585 CTAs — four waves on 148 SMs — with
+    the TMA producers paced cohort by cohort (pq_mma.cu: pace_blocks_for; BASELINE C3's 65,536 queries run seven such waves).
+    Pacing is rate control only: results stay bit-exact."""
+    xb, xq = data.corpus(400_000), data.queries(20_000)
+    ix = _index(0, xb, "auto")
+    D, I = ix.search(xq, 10)
+    st = ix.last_stats
+    assert st[3] >= 4 and st[1] == 0, st
+    sample = np.arange(0, 20_000, 487)                             # 42 queries spread over the groups
+    Dr, Ir = oracle.engine_spec(xq[sample], xb, 10, 0)
+    _assert_bit_exact(D[sample], I[sample], Dr, Ir)

@@ -88,11 +88,13 @@ def test_protocol_slips_are_caught_on_the_cpu(tmp_path, old, new, expect):
     assert len(ok) < 7 or not np.array_equal(I, Ir), "a protocol slip went unnoticed"
 
 
-def test_producer_pacing_counts_every_cta_out_of_every_block(tmp_path, monkeypatch):
-    """Pacing of the TMA producers (pq_mma.cu: pace_setup / pace_leave / pace_wait), forced on for a small epoch: blocks of two
-    row tiles.  Results are unchanged (pacing is rate control only), and after the last paced launch every CTA of its grid has
-    counted itself out of every block exactly once — a producer that missed one would leave the others waiting on the
-    hardware."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_producer_pacing_counts_every_cta_out_of_every_block(tmp_path, monkeypatch, mode):
+    """Pacing of the TMA producers (pq_mma.cu: pace_blocks_for / pace_leave / pace_wait), forced on for a small search: blocks of
+    two row tiles.  Results are unchanged (pacing is rate control only), and after each paced launch every CTA of a cohort has
+    counted itself out of every block exactly once — a producer that missed one would leave the others waiting on the hardware.
+    mode 1: single-wave grids only; mode 2: larger grids pace wave by wave (cohorts of n_sms CTAs)."""
+    monkeypatch.setenv("PROQA_B200_PACE", str(mode))
     monkeypatch.setenv("PROQA_B200_PACE_MIN_TILES", "1")
     monkeypatch.setenv("PROQA_B200_PACE_SHIFT", "1")
     lib = harness.build_host_emu(tmp_path, real_filter=True)
@@ -104,9 +106,10 @@ def test_producer_pacing_counts_every_cta_out_of_every_block(tmp_path, monkeypat
     import ctypes
     buf = (ctypes.c_uint32 * 64)()
     n = lib.emu_last_pace(buf, 64)
-    assert n >= 1, "no paced launch"
     counts = list(buf)[:min(n, 64)]
-    # one counter per block of two row tiles of every paced epoch (the bootstrap epoch runs one CTA per row tile and group —
-    # more CTAs than SMs here — and stays unpaced; the second epoch has 16 row tiles: 8 blocks), each left exactly once by every
-    # CTA of the epoch's grid
-    assert n == 8 and len(set(counts)) == 1 and 2 <= counts[0] <= n_sms, counts
+    # The bootstrap epoch (8 row tiles: 4 blocks) runs one CTA per row tile and group, 16 CTAs on 5 SMs: unpaced in mode 1, four
+    # cohorts of 5, 5, 5 and 1 CTAs in mode 2.  The second epoch has 16 row tiles (8 blocks) and a single-wave grid of 4 CTAs.
+    if mode == 1:
+        assert counts == [4] * 8, counts
+    else:
+        assert counts == [5] * 12 + [1] * 4 + [4] * 8, counts
