@@ -19,7 +19,7 @@ except Exception as e:
     print("parse failed", sys.argv[1], e); print(open(sys.argv[1].replace(".json",".err")).read()[-2000:])
 PY
 }
-timeout -s KILL 300 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > $O/zf_reference.json 2> $O/zf_reference.err; tail -c 400 $O/zf_reference.json; echo
+# (reference arm: see the previous call)
 timeout -s KILL 500 python bench.py --gpus 1 --steps 20 --warmup 3 > $O/zf_default.json 2> $O/zf_default.err; show $O/zf_default.json
 timeout -s KILL 200 python bench.py --workload trec --steps 10 --warmup 3 --no-cpu-baseline > $O/zf_trec.json 2> $O/zf_trec.err; show $O/zf_trec.json
 timeout -s KILL 300 python bench.py --workload c5 --rows 12500000 --steps 5 --warmup 2 --no-cpu-baseline > $O/zf_c5.json 2> $O/zf_c5.err; show $O/zf_c5.json
