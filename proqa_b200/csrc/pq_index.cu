@@ -577,6 +577,8 @@ int pq_index_create(int d, int metric, int device, pq_index** out) {
     }
     const char* ks = getenv("PROQA_B200_K1_SETS");
     if (ks && (atoi(ks) == 2 || atoi(ks) == 4)) plan_k1_sets() = atoi(ks);
+    const char* la = getenv("PROQA_B200_LOOSE_ABOVE");
+    if (la && atof(la) > 0.0) plan_loose_above() = atof(la);
     const char* gr = getenv("PROQA_B200_GROWTH");
     if (gr && atoll(gr) > 1) plan_growth_override() = atoll(gr);
     const char* br = getenv("PROQA_B200_BOOT_ROWS");

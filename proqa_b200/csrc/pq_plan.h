@@ -21,9 +21,14 @@ constexpr int kPlanMaxMTiles = 4;    // query tiles one CTA keeps in tensor memo
 //           instructions for the same products (ncu: 6.0e9 vs 4.3e9 in the last C2 epoch; sustained SM clock 1612 vs 1676 MHz).
 constexpr int kPlanSetsLoose = 4, kPlanSetsTight = 2;
 // expected share of 32x32 chunks with a survivor when rows [begin, ..) are filtered at the threshold known after `seen` rows
+// (tuning hook, PROQA_B200_LOOSE_ABOVE: the share above which an epoch runs the four-set variant)
+inline double& plan_loose_above() {
+    static double v = 0.10;
+    return v;
+}
 inline int plan_sets_for(double k, double seen_rows) {
     const double per_pair = 1.5 * k / std::max(1.0, seen_rows);
-    return 1024.0 * per_pair > 0.10 ? kPlanSetsLoose : kPlanSetsTight;
+    return 1024.0 * per_pair > plan_loose_above() ? kPlanSetsLoose : kPlanSetsTight;
 }
 
 // (tuning hook, PROQA_B200_K1_SETS: epilogue warp sets of the k = 1 pass; 0 = the default)
