@@ -33,6 +33,8 @@ struct FfmaParams {
     int cap;
     int n_stages;
     int metric;
+    int ctas_per_batch;    // CTAs [b * ctas_per_batch, ...) serve query batch b
+    int nq_total;          // queries over all batches (the last batch may hold fewer than nq)
 };
 
 struct FfmaCtrl {                 // lives right after the tile stages in shared memory
@@ -157,7 +159,15 @@ __device__ __forceinline__ bool ffma_tile(const uint8_t* stage, const float4* qs
 
 template <int QT>
 __global__ void __launch_bounds__(kFfmaThreads, 1)
-pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p) {
+pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p_all) {
+    // this CTA's query batch: its queries, thresholds and output lists
+    FfmaParams p = p_all;
+    const int batch = (int)blockIdx.x / p_all.ctas_per_batch;
+    const int cta = (int)blockIdx.x - batch * p_all.ctas_per_batch;
+    p.queries = p_all.queries + (size_t)batch * p_all.nq * kDim;
+    p.gthr = p_all.gthr + (size_t)batch * kFfmaMaxQ;
+    p.out_keys = p_all.out_keys + (size_t)batch * p_all.ctas_per_batch * p_all.nq * p_all.k;
+    p.nq = min(p_all.nq, p_all.nq_total - batch * p_all.nq);
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stages = smem;
     uint8_t* tail = smem + (size_t)p.n_stages * kFfmaStageBytes;
@@ -166,7 +176,7 @@ pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p
     uint64_t* bufs = reinterpret_cast<uint64_t*>(tail + kFfmaCtrlBytes + kFfmaQsmBytes);
 
     const int t = threadIdx.x;
-    const int tile0 = blockIdx.x * p.tiles_per_cta;
+    const int tile0 = cta * p.tiles_per_cta;
     int ntiles = p.n_tiles - tile0;
     ntiles = ntiles < 0 ? 0 : (ntiles > p.tiles_per_cta ? p.tiles_per_cta : ntiles);
 
@@ -224,7 +234,7 @@ pq_ffma_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FfmaParams p
         uint64_t* buf = bufs + (size_t)q * p.cap;
         ffma_compact(buf, ctrl, q, p);
         const int n = ctrl->cnt[q] < p.k ? ctrl->cnt[q] : p.k;
-        uint64_t* out = p.out_keys + ((size_t)blockIdx.x * p.nq + q) * p.k;
+        uint64_t* out = p.out_keys + ((size_t)cta * p_all.nq + q) * p.k;   // (list stride: the full batch size, also in a short batch)
         for (int i = t; i < p.k; i += kFfmaThreads) out[i] = (i < n) ? buf[i] : 0ull;
         __syncthreads();
     }
@@ -265,6 +275,9 @@ cudaError_t ffma_scan_launch(const FfmaLaunch& a, cudaStream_t stream) {
     p.k = a.k;
     p.cap = ffma_cap_for_k(a.k);
     p.metric = a.metric;
+    p.ctas_per_batch = a.n_ctas;
+    p.nq_total = a.nq_total > 0 ? a.nq_total : a.nq;
+    const int n_batches = a.n_batches > 0 ? a.n_batches : 1;
     const size_t buf_bytes = (size_t)a.nq * p.cap * 8 + kFfmaCtrlBytes + kFfmaQsmBytes;
     p.n_stages = 3;
     while (p.n_stages > 1 && (size_t)p.n_stages * kFfmaStageBytes + buf_bytes > (size_t)kSmemLimit) --p.n_stages;
@@ -275,7 +288,7 @@ cudaError_t ffma_scan_launch(const FfmaLaunch& a, cudaStream_t stream) {
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        kern<<<a.n_ctas, kFfmaThreads, smem, stream>>>(*a.tmap_rows_f32, p);
+        kern<<<a.n_ctas * n_batches, kFfmaThreads, smem, stream>>>(*a.tmap_rows_f32, p);
         return cudaGetLastError();
     };
     switch (qh) {

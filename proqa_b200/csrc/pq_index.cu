@@ -386,13 +386,22 @@ int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norm
     const int qmax = ffma_max_queries_for_k(k);
     if (qmax < 1) return set_error(PQ_ERR_UNSUPPORTED, "k=%d is above what the fp32 scan supports", k);
     const int n_tiles = (int)((ix->ntotal + kFfmaTileRows - 1) / kFfmaTileRows);
-    const int n_ctas = std::max(1, std::min(ix->n_sms, n_tiles));
-    int rc = ix->ws_scan_keys.ensure((size_t)n_ctas * qmax * k * 8);
-    if (!rc) rc = ix->ws_gthr.ensure(kFfmaMaxQ * 4);
+    // Query batches of qmax (<= 8) share one launch: CTAs [b * n_ctas, (b + 1) * n_ctas) scan the rows for batch b.  With few
+    // batches each takes every SM it can use; with many (k-means: thousands of points whose k = 1 certificate failed, against
+    // 10,000 centroids) a batch gets fewer CTAs, each scanning more of the rows — about two waves of CTAs in all.  (Until round 2
+    // every batch was three stream operations of its own: 170k re-run points cost 0.5 s of launches.)
+    const int kMaxBatchesPerLaunch = 16384;
+    const int n_batches_all = (nq + qmax - 1) / qmax;
+    const int per_launch = std::min(n_batches_all, kMaxBatchesPerLaunch);
+    const int n_ctas = std::max(1, std::min(std::min(ix->n_sms, n_tiles), 2 * ix->n_sms / per_launch));
+    int rc = ix->ws_scan_keys.ensure((size_t)per_launch * n_ctas * qmax * k * 8);
+    if (!rc) rc = ix->ws_gthr.ensure((size_t)per_launch * kFfmaMaxQ * 4);
     if (rc) return rc;
-    for (int q0 = 0; q0 < nq; q0 += qmax) {
-        const int nqb = std::min(qmax, nq - q0);
-        PQ_CUDA(cudaMemsetAsync(ix->ws_gthr.p, 0, kFfmaMaxQ * 4, ix->stream));
+    for (int b0 = 0; b0 < n_batches_all; b0 += per_launch) {
+        const int nb = std::min(per_launch, n_batches_all - b0);
+        const int q0 = b0 * qmax;
+        const int nq_l = std::min(nq - q0, nb * qmax);
+        PQ_CUDA(cudaMemsetAsync(ix->ws_gthr.p, 0, (size_t)nb * kFfmaMaxQ * 4, ix->stream));
         FfmaLaunch f;
         f.tmap_rows_f32 = &ix->tmap_f32;
         f.row_norms = (const float*)ix->norms.p;
@@ -401,9 +410,11 @@ int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norm
         f.gthr = (uint32_t*)ix->ws_gthr.p;
         f.n_rows = ix->ntotal;
         f.n_ctas = n_ctas;
-        f.nq = nqb;
+        f.nq = std::min(qmax, nq_l);
         f.k = k;
         f.metric = ix->metric;
+        f.n_batches = nb;
+        f.nq_total = nq_l;
         ix->prof_begin();
         PQ_CUDA(ffma_scan_launch(f, ix->stream));
         ix->prof_end();
@@ -411,11 +422,14 @@ int search_fp32_scan(pq_index* ix, int nq, const float* dq, const float* dq_norm
         memset(&m, 0, sizeof(m));
         m.keys = (const uint64_t*)ix->ws_scan_keys.p;
         m.q_stride = k;
-        m.list_stride = (long long)nqb * k;
+        m.list_stride = (long long)f.nq * k;
         m.n_lists = n_ctas;
         m.list_len = k;
         m.gthr = (const uint32_t*)ix->ws_gthr.p;
-        m.nq = nqb;
+        m.batch_q = f.nq;
+        m.batch_stride = (long long)n_ctas * f.nq * k;
+        m.gthr_batch_stride = kFfmaMaxQ;
+        m.nq = nq_l;
         m.k = k;
         m.metric = ix->metric;
         m.q_norms = dq_norms + q0;

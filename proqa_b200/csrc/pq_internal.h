@@ -10,8 +10,10 @@ namespace pq {
 enum Metric : int { kMetricIP = 0, kMetricL2 = 1 };
 
 // ------------------------------------------------------------------------------------------------
-// Exact fp32 streaming scan (pq_ffma.cu).  One launch scans local rows [0, n_rows) for up to 8
-// queries held in shared memory and leaves one sorted k-list per (CTA, query).
+// Exact fp32 streaming scan (pq_ffma.cu).  A CTA scans its share of local rows [0, n_rows) for up to 8
+// queries held in shared memory and leaves one sorted k-list per (CTA, query).  One launch takes n_batches
+// such query batches (CTAs [b * n_ctas, (b + 1) * n_ctas) serve batch b): thousands of queries re-run after a
+// failed tensor-tier certificate against a small corpus (k-means: 10,000 centroids) are one launch, not thousands.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFfmaTileRows = 128;
 constexpr int kFfmaThreads = 256;
@@ -21,14 +23,16 @@ constexpr int kFfmaStageBytes = kFfmaTileRows * 512;
 struct FfmaLaunch {
     const CUtensorMap* tmap_rows_f32;  // host copy of the [rows,128] fp32 tensor map (box 32 x 128, SWIZZLE_128B)
     const float* row_norms;            // squared row norms (used by L2 only)
-    const float* queries_dev;          // nq x 128 fp32, device
-    uint64_t* out_keys;                // [n_ctas][nq][k]
-    uint32_t* gthr;                    // [nq], ordered-u32 thresholds, pre-initialised by the caller
+    const float* queries_dev;          // nq_total x 128 fp32, device
+    uint64_t* out_keys;                // [n_batches][n_ctas][nq][k]
+    uint32_t* gthr;                    // [n_batches][kFfmaMaxQ], ordered-u32 thresholds, pre-initialised by the caller
     long long n_rows;
-    int n_ctas;
-    int nq;
+    int n_ctas;                        // CTAs per query batch
+    int nq;                            // queries per batch (<= kFfmaMaxQ)
     int k;
     int metric;
+    int n_batches = 1;
+    int nq_total = 0;                  // 0: nq (a single batch); the last batch may be short
 };
 // Returns cudaSuccess or the launch error.  *cap_out receives the per-query buffer capacity used.
 cudaError_t ffma_scan_launch(const FfmaLaunch& a, cudaStream_t stream);
@@ -47,6 +51,9 @@ struct MergeLaunch {
     const uint32_t* counts;   // optional [q * cnt_q_stride + list]: valid entries per list (clamped to list_len)
     long long cnt_q_stride;
     const uint32_t* gthr;     // optional per-query ordered-u32 lower bound on the key's score half
+    int batch_q;              // > 0: queries come in batches of batch_q (the fp32 scan's launch shape): query q = b * batch_q + i reads
+    long long batch_stride;   //   keys + b * batch_stride + i * q_stride  and  gthr[b * gthr_batch_stride + i]
+    int gthr_batch_stride;    //   (callers zero the struct first)
     int nq;
     int k;
     int metric;

@@ -48,13 +48,14 @@ __global__ void __launch_bounds__(kSelThreads) pq_merge_lists_kernel(const Merge
     const MergeLaunch& a = p.a;
     const int q = blockIdx.x;
     const int t = threadIdx.x;
-    const uint64_t* base = a.keys + (size_t)q * a.q_stride;
+    const int qb = a.batch_q > 0 ? q / a.batch_q : 0, qi = a.batch_q > 0 ? q - qb * a.batch_q : q;   // (batch, query in the batch)
+    const uint64_t* base = a.keys + (size_t)qb * a.batch_stride + (size_t)qi * a.q_stride;
     const long long total = (long long)a.n_lists * a.list_len;
     constexpr int kPer = 4, kStep = kSelThreads * kPer;
 
     if (t == 0) {
         s_fill = 0;
-        s_bar = a.gthr ? ((unsigned long long)a.gthr[q] << 32) : 0ull;
+        s_bar = a.gthr ? ((unsigned long long)a.gthr[a.batch_q > 0 ? qb * a.gthr_batch_stride + qi : q] << 32) : 0ull;
     }
     __syncthreads();
     for (long long r0 = 0; r0 < total; r0 += kStep) {

@@ -30,16 +30,16 @@ def test_fp32_scan_bit_exact(scan, metric, nq, nb, k, n_sms):
     xb, xq = data.corpus(nb), data.queries(nq)
     D, I, st = harness.run_fp32_scan_emu(scan, xb, xq, k, metric, n_sms=n_sms)
     _exact(D, I, *oracle.engine_spec(xq, xb, k, metric))
-    assert st[2] >= 1 and st[4] == st[2]          # one merge per scan launch
+    assert st[2] == 1 and st[4] == 1              # query batches of up to 8, all in ONE scan launch and one merge launch
 
 
-def test_large_k_runs_one_query_per_launch(scan):
+def test_large_k_runs_one_query_per_batch(scan):
     """trec_process.py:76 / online_sampler.py:113 shapes: k in the thousands — the shared-memory buffers leave room for one
-    query per launch and a single TMA stage."""
+    query per batch (CTA) and a single TMA stage."""
     xb, xq = data.corpus(12_000), data.queries(2)
     D, I, st = harness.run_fp32_scan_emu(scan, xb, xq, 10000, 0, n_sms=3)
     _exact(D, I, *oracle.engine_spec(xq, xb, 10000, 0))
-    assert st[2] == 2
+    assert st[2] == 1 and st[4] == 1              # (two batches of one query, one launch)
 
 
 def test_ties_padding_id_base_and_non_finite_rows(scan):
@@ -63,3 +63,13 @@ def test_scan_does_not_depend_on_the_thread_schedule(scan, schedule):
     finally:
         scan.emu_set_schedule(0)
     _exact(D, I, *oracle.engine_spec(xq, xb, 50, 1))
+
+
+def test_many_query_batches_share_one_launch(scan):
+    """The k-means re-run shape: many queries (here 37: five batches, the last one short) against a small corpus, k = 1 — one scan
+    launch whose CTAs are dealt to the batches, one merge launch, results bit-exact."""
+    xb, xq = data.corpus(2_000), data.queries(37)
+    for metric in (0, 1):
+        D, I, st = harness.run_fp32_scan_emu(scan, xb, xq, 1, metric, n_sms=4)
+        _exact(D, I, *oracle.engine_spec(xq, xb, 1, metric))
+        assert st[2] == 1 and st[4] == 1
