@@ -277,6 +277,54 @@ static int staged_add_rows(pq_index* ix, float* dst_dev, const float* x_host, in
     return PQ_OK;
 }
 
+// Large query matrices and result arrays of a host-buffer search (group_paras.py:51 hands index.search all 21M points: 10.75 GB of
+// pageable memory; C5 returns 98 MB) go through the same pinned double buffer: a plain cudaMemcpy from / to pageable memory
+// runs at 7-9 GB/s (measured: 2M points in 0.116 s, C5 results 14.5 ms), the staged path at what add() gets (29 GB/s).
+constexpr size_t kStagedCopyMinBytes = 8u << 20;
+static int staged_upload(pq_index* ix, void* dst_dev, const void* src_host, size_t bytes) {
+    StagingBuffers& sb = g_staging_of[ix->device & 63];
+    std::unique_lock<std::mutex> staging_lock(g_staging_mu[ix->device & 63], std::defer_lock);
+    if (bytes >= kStagedCopyMinBytes) staging_lock.lock();
+    if (bytes < kStagedCopyMinBytes || !sb.init()) {
+        PQ_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ix->stream));
+        return PQ_OK;
+    }
+    int which = 0;
+    for (size_t a = 0; a < bytes; a += StagingBuffers::kBytes, which ^= 1) {
+        const size_t n = std::min(StagingBuffers::kBytes, bytes - a);
+        PQ_CUDA(cudaEventSynchronize(sb.done[which]));  // the H2D that last used this buffer has finished
+        parallel_memcpy(sb.buf[which], (const char*)src_host + a, n);
+        PQ_CUDA(cudaMemcpyAsync((char*)dst_dev + a, sb.buf[which], n, cudaMemcpyHostToDevice, ix->stream));
+        PQ_CUDA(cudaEventRecord(sb.done[which], ix->stream));
+    }
+    PQ_CUDA(cudaStreamSynchronize(ix->stream));  // the pinned buffers are free again before the lock is
+    return PQ_OK;
+}
+// Device -> pageable host memory; returns with the copy complete.
+static int staged_download(pq_index* ix, void* dst_host, const void* src_dev, size_t bytes) {
+    StagingBuffers& sb = g_staging_of[ix->device & 63];
+    std::unique_lock<std::mutex> staging_lock(g_staging_mu[ix->device & 63], std::defer_lock);
+    if (bytes >= kStagedCopyMinBytes) staging_lock.lock();
+    if (bytes < kStagedCopyMinBytes || !sb.init()) {
+        PQ_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ix->stream));
+        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+        return PQ_OK;
+    }
+    const size_t chunk = StagingBuffers::kBytes, n_chunks = (bytes + chunk - 1) / chunk;
+    for (size_t i = 0; i <= n_chunks; ++i) {  // chunk i flies into one buffer while the host copies chunk i - 1 out of the other
+        if (i < n_chunks) {
+            PQ_CUDA(cudaMemcpyAsync(sb.buf[i & 1], (const char*)src_dev + i * chunk, std::min(chunk, bytes - i * chunk), cudaMemcpyDeviceToHost,
+                                    ix->stream));
+            PQ_CUDA(cudaEventRecord(sb.done[i & 1], ix->stream));
+        }
+        if (i >= 1) {
+            PQ_CUDA(cudaEventSynchronize(sb.done[(i - 1) & 1]));
+            parallel_memcpy((char*)dst_host + (i - 1) * chunk, sb.buf[(i - 1) & 1], std::min(chunk, bytes - (i - 1) * chunk));
+        }
+    }
+    return PQ_OK;
+}
+
 // fp16 rows (what get_embed.py --fp16 writes, get_embed.py:147-151) -> fp32 rows: exact, and half the bytes over PCIe.
 __global__ void pq_half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n_elems) {
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -646,13 +694,19 @@ int pq_index_search(pq_index* ix, int64_t nq, const float* xq, int64_t k, float*
     if (!rc) rc = ix->ws_D.ensure((size_t)nq * k * 4);
     if (!rc) rc = ix->ws_I.ensure((size_t)nq * k * 8);
     if (rc) return rc;
-    PQ_CUDA(cudaMemcpyAsync(ix->ws_q.p, xq, (size_t)nq * kDim * 4, cudaMemcpyHostToDevice, ix->stream));
+    rc = staged_upload(ix, ix->ws_q.p, xq, (size_t)nq * kDim * 4);
+    if (rc) return rc;
     rc = search_device_impl(ix, nq, (const float*)ix->ws_q.p, k, (float*)ix->ws_D.p, (long long*)ix->ws_I.p);
     if (rc) return rc;
-    PQ_CUDA(cudaMemcpyAsync(D, ix->ws_D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
-    PQ_CUDA(cudaMemcpyAsync(I, ix->ws_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ix->stream));
-    PQ_CUDA(cudaStreamSynchronize(ix->stream));
-    return PQ_OK;
+    if ((size_t)nq * k * 8 < kStagedCopyMinBytes) {  // small results (every eval_retrieval.py shape): two plain copies, one wait
+        PQ_CUDA(cudaMemcpyAsync(D, ix->ws_D.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, ix->stream));
+        PQ_CUDA(cudaMemcpyAsync(I, ix->ws_I.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, ix->stream));
+        PQ_CUDA(cudaStreamSynchronize(ix->stream));
+        return PQ_OK;
+    }
+    rc = staged_download(ix, D, ix->ws_D.p, (size_t)nq * k * 4);
+    if (!rc) rc = staged_download(ix, I, ix->ws_I.p, (size_t)nq * k * 8);
+    return rc;
 }
 
 int pq_index_search_device(pq_index* ix, int64_t nq, const float* xq_dev, int64_t k, float* D_dev, int64_t* I_dev) {
