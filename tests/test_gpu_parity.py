@@ -334,3 +334,19 @@ def test_many_waves_of_ctas_paced_wave_by_wave():
     sample = np.arange(0, 20_000, 487)                             # 42 queries spread over the groups
     Dr, Ir = oracle.engine_spec(xq[sample], xb, 10, 0)
     _assert_bit_exact(D[sample], I[sample], Dr, Ir)
+
+
+def test_large_query_and_result_arrays_take_the_staged_copies():
+    """pq_index_search moves host arrays of 8 MB or more through the pinned double buffer (pq_index.cu: staged_upload /
+    staged_download; group_paras.py:51 hands index.search 10.75 GB of points, C5 returns 98 MB).  20,000 queries = 10 MB up;
+    k = 100: D 8 MB and I 16 MB down (odd sizes, so no copy ends on a round boundary); the result must be the same bits as small
+    searches of the same queries, which take the plain copies."""
+    xb, xq = data.corpus(120_000), data.queries(20_011)
+    ix = _index(0, xb, "auto")
+    D, I = ix.search(xq, 100)
+    assert D.shape == (20_011, 100) and I.shape == (20_011, 100)
+    for lo in (0, 9_973, 20_011 - 7):                              # slices small enough for the plain-copy path
+        Ds, Is = ix.search(xq[lo:lo + 7], 100)
+        _assert_bit_exact(D[lo:lo + 7], I[lo:lo + 7], Ds, Is)
+    sample = np.array([0, 4_999, 20_010])
+    _assert_bit_exact(D[sample], I[sample], *oracle.engine_spec(xq[sample], xb, 100, 0))
