@@ -5,9 +5,11 @@
 // GEMM with K = 128.  This file runs it on the 5th-generation tensor cores and never writes the
 // score matrix:
 //
-//   pq_mma_filter_kernel  (one CTA per SM, warp-specialised, 576 threads)
+//   pq_mma_filter_kernel  (one CTA per SM, warp-specialised, 576 threads; a 320-thread variant with two epilogue sets runs the
+//                 tight-threshold epochs)
 //     warp 0      TMA producer: corpus tiles (128 rows x 256 B bf16, SWIZZLE_128B; L2 also the tile's 128 row norms)
-//                 through a 6-stage shared-memory ring, mbarrier completion
+//                 through a 6-stage shared-memory ring, mbarrier completion; paced against the slowest CTA of its wave so that
+//                 the CTA groups (which all stream the same rows for different queries) share every tile through L2 (pace_*)
 //     warp 1      issues tcgen05.mma in the TS form: the stationary operand — up to 4 query tiles of 128 queries, written
 //                 once per CTA into tensor memory with tcgen05.st — times the streamed corpus tile from shared memory;
 //                 M=128 queries x N=128 rows x K=16, bf16 -> fp32, into two 128-column TMEM accumulators
@@ -1769,7 +1771,7 @@ int search_mma_filter(pq_index* ix, int nq_total, const float* dq_all, int k, fl
             mp.cap = ep.cap;
             mp.n_sub = plan_n_sub(gs, ep);
             mp.sets = ep.sets;
-            mp.pace = nullptr;   // (set per launch by pace_setup; the repair launches run unpaced)
+            mp.pace = nullptr;   // (set per launch by PaceArea::assign; the repair launches run unpaced)
             mp.pace_shift = 0;
             mp.pace_blocks = 0;
             mp.pace_cohort = 1;
