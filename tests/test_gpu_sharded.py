@@ -1,5 +1,5 @@
 """-m gpu, needs two GPUs: the one-process-per-GPU layout (proqa_b200/sharded.py) under torchrun — NCCL all-gather + merge kernel,
-thresholds exchanged through CUDA-IPC peer mailboxes — against the oracle (tools/gpu_runs/r02_sharded_check.py)."""
+thresholds exchanged through CUDA-IPC peer mailboxes — against the oracle (tests/workers/sharded_check.py)."""
 import os
 import subprocess
 import sys
@@ -16,7 +16,7 @@ def test_two_ranks_row_sharded_with_threshold_exchange():
         pytest.skip("one GPU in this box (tests/test_gpu_multi.py covers the exchange with two shards on one device)")
     port = 29500 + os.getpid() % 500
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), os.path.join(ROOT, "tools", "gpu_runs", "r02_sharded_check.py")],
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "workers", "sharded_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

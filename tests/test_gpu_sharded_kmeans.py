@@ -1,6 +1,6 @@
 """-m gpu: k-means with the points sharded over GPUs (proqa_b200/sharded_clustering.py on pq_kmeans_set_centroids /
 _partial_device / _finish_device), one process, against the single-GPU Clustering (validated on a B200 in round 2; the two-rank
-run under torchrun is tools/gpu_runs/r02_sharded_kmeans.py)."""
+run under torchrun is tests/workers/sharded_kmeans.py)."""
 import numpy as np
 import pytest
 

@@ -1,4 +1,4 @@
-"""torchrun --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 tools/gpu_runs/r02_sharded_check.py
+"""torchrun --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 tests/workers/sharded_check.py
 One process per GPU: ShardedIndexFlat (NCCL all-gather + merge kernel) with the threshold exchange over CUDA-IPC peer mailboxes,
 against the oracle on rank 0.  Prints PASS/FAIL lines; exit code 1 on any failure."""
 import os

@@ -1,5 +1,5 @@
 """Round-2 hardware check of ShardedClustering across ranks:
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/gpu_runs/r02_sharded_kmeans.py
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/workers/sharded_kmeans.py
 Every rank trains on the same array; rank 0 compares with the single-GPU Clustering."""
 import os
 import sys

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 timeout -s KILL 600 python -m pytest tests/test_gpu_xchg.py -m gpu -x -q > $O/f_xchg_tests.log 2>&1
 echo "xchg tests exit $?"; tail -12 $O/f_xchg_tests.log
-timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29621 tools/gpu_runs/r02_sharded_check.py > $O/f_sharded_check.log 2>&1
+timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29621 tests/workers/sharded_check.py > $O/f_sharded_check.log 2>&1
 echo "sharded check rc=$?"; grep -E "PASS|FAIL|Error|error" $O/f_sharded_check.log | head -20
 timeout -s KILL 900 python -m pytest tests -m gpu -x -q > $O/f_pytest.log 2>&1
 echo "all gpu tests exit $?"; tail -6 $O/f_pytest.log

@@ -7,7 +7,7 @@ O=gpurun_out
 nvidia-smi -L | head -3
 timeout -s KILL 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_sharded.py tests/test_gpu_sharded_kmeans.py tests/test_gpu_reference_script.py tests/test_gpu_xchg.py -m gpu -q > $O/zb_pytest.log 2>&1
 echo "2-gpu tests exit $?"; tail -5 $O/zb_pytest.log
-timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/gpu_runs/r02_sharded_check.py > $O/zb_sharded_check.log 2>&1
+timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/workers/sharded_check.py > $O/zb_sharded_check.log 2>&1
 echo "sharded check rc=$?"; grep -E "PASS|FAIL|Error|error" $O/zb_sharded_check.log | head -20
 timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2 --steps 20 --warmup 3 > $O/zb_c2_g2.json 2> $O/zb_c2_g2.err
 echo "bench g2 rc=$?"
